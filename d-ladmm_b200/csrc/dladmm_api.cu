@@ -1,0 +1,449 @@
+// C-ABI entry points of libdladmm.so (see include/dladmm.h) and the per-layer launch schedule.
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "simt_gemm.cuh"
+#include "umma_path.cuh"
+
+namespace dladmm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- workspace carving -------------------------------------------------------------------------
+struct Workspace {
+  // forward
+  float* Ap;    // (m x dp)      A, K-major padded
+  float* Wp;    // nW x (d x mp) W_k, K-major padded
+  // backward
+  float* Atp;   // (d x mp)      A^T
+  float* Wtp;   // nW x (m x dp) W_k^T
+  float* cZ;    // (d x B) carried dZ / dx1
+  float* cE;    // (m x B)
+  float* cL;    // (m x B)
+  float* dR;    // (m x B)
+  float* part;  // SL_COUNT x ncolTiles x prow
+  size_t bytes;
+  int mp, dp, nW, ncolTiles, prow;
+};
+
+// tied variant passes the same W pointer in every layer: map layer -> index of its unique weight
+struct WeightMap {
+  std::vector<const float*> uniq;
+  std::vector<int> idx;
+  explicit WeightMap(const dladmm_problem* p) : idx(p->K, 0) {
+    for (int k = 0; k < p->K; ++k) {
+      size_t j = 0;
+      while (j < uniq.size() && uniq[j] != p->layers[k].W) ++j;
+      if (j == uniq.size()) uniq.push_back(p->layers[k].W);
+      idx[k] = (int)j;
+    }
+  }
+};
+
+static int unique_weights(const dladmm_problem* p) { return (int)WeightMap(p).uniq.size(); }
+static int weight_index(const dladmm_problem* p, int k) { return WeightMap(p).idx[k]; }
+
+static Workspace carve(const dladmm_problem* p, int for_backward) {
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  w.mp = round_up(p->m, 32);
+  w.dp = round_up(p->d, 32);
+  w.nW = unique_weights(p);
+  w.ncolTiles = (int)((p->B + SG_BN - 1) / SG_BN);
+  w.prow = round_up(std::max(p->m, p->d), 32);
+  char* base = (char*)p->workspace;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) {
+    float* r = (float*)(base + off);
+    off += round_up64((i64)nfloats * 4, 256);
+    return r;
+  };
+  w.Ap = take((size_t)p->m * w.dp);
+  w.Wp = take((size_t)w.nW * p->d * w.mp);
+  if (for_backward) {
+    w.Atp = take((size_t)p->d * w.mp);
+    w.Wtp = take((size_t)w.nW * p->m * w.dp);
+    w.cZ = take((size_t)p->d * p->B);
+    w.cE = take((size_t)p->m * p->B);
+    w.cL = take((size_t)p->m * p->B);
+    w.dR = take((size_t)p->m * p->B);
+    w.part = take((size_t)SL_COUNT * w.ncolTiles * w.prow);
+  }
+  w.bytes = off;
+  return w;
+}
+
+static int validate(const dladmm_problem* p, int for_backward) {
+  DL_REQUIRE(p != nullptr, "problem is NULL");
+  DL_REQUIRE(p->abi_version == DLADMM_ABI_VERSION, "ABI version mismatch: got %d, library is %d", p->abi_version,
+             DLADMM_ABI_VERSION);
+  DL_REQUIRE(p->family >= 0 && p->family <= 2, "unknown family %d", p->family);
+  DL_REQUIRE(p->precision >= 0 && p->precision <= 2, "unknown precision %d", p->precision);
+  DL_REQUIRE(p->m > 0 && p->d > 0 && p->K > 0, "m, d, K must be positive (m=%d d=%d K=%d)", p->m, p->d, p->K);
+  DL_REQUIRE(p->B >= 0, "B must be non-negative");
+  DL_REQUIRE(p->layers != nullptr, "layers is NULL");
+  DL_REQUIRE(p->A && (p->B == 0 || (p->X && p->Z0 && p->E0 && p->L0 && p->Z && p->E && p->L && p->T)),
+             "A, X, Z0, E0, L0, Z, E, L, T must be non-NULL");
+  for (int k = 0; k < p->K; ++k) {
+    const dladmm_layer& l = p->layers[k];
+    DL_REQUIRE(l.W != nullptr, "layer %d: W is NULL", k);
+    DL_REQUIRE(l.beta1.ptr && l.theta1.ptr, "layer %d: beta1/theta1 missing", k);
+    if (p->family == DLADMM_FAMILY_A) DL_REQUIRE(l.beta2.ptr && l.theta2.ptr, "layer %d: family A needs beta2, theta2", k);
+    if (p->family == DLADMM_FAMILY_B)
+      DL_REQUIRE(l.beta2.ptr && l.beta3.ptr && l.ss2.ptr && l.theta2.ptr, "layer %d: family B needs beta2, beta3, ss2, theta2", k);
+    if (p->family == DLADMM_FAMILY_C)
+      DL_REQUIRE(l.beta3.ptr && l.ss2.ptr && l.ss2_2.ptr, "layer %d: family C needs beta3, ss2(_1), ss2_2", k);
+    if (l.ss1.ptr) DL_REQUIRE(l.ss1.row_stride == 0 && l.ss1.col_period == 0, "layer %d: ss1 must be a (1,1) scalar", k);
+  }
+  if (for_backward) {
+    DL_REQUIRE(p->last_only == 0, "backward needs every iterate (last_only must be 0)");
+    DL_REQUIRE(p->maskZ != nullptr, "backward needs maskZ from the forward");
+    DL_REQUIRE(p->family == DLADMM_FAMILY_C || p->maskE != nullptr, "backward needs maskE from the forward");
+  }
+  if (p->B > 0) {
+    Workspace w = carve(p, for_backward);
+    if (p->workspace == nullptr || p->workspace_bytes < w.bytes) {
+      set_error("workspace too small: need %zu bytes, got %zu", w.bytes, p->workspace_bytes);
+      return DLADMM_ERR_WORKSPACE;
+    }
+  }
+  return DLADMM_OK;
+}
+
+static int check_device() {
+  int dev = 0;
+  DL_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  DL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; this library is sm_100a only and has no fallback", dev, major);
+    return DLADMM_ERR_DEVICE;
+  }
+  return DLADMM_OK;
+}
+
+// slab addressing -----------------------------------------------------------------------------------
+struct Slabs {
+  const dladmm_problem* p;
+  i64 zs, ms;   // slab sizes in elements
+  explicit Slabs(const dladmm_problem* q) : p(q), zs((i64)q->d * q->B), ms((i64)q->m * q->B) {}
+  int slot(int k) const { return p->last_only ? (k & 1) : k; }
+  const float* Zin(int k) const { return k == 0 ? p->Z0 : p->Z + zs * slot(k - 1); }   // Z_{k-1}
+  const float* Ein(int k) const { return k == 0 ? p->E0 : p->E + ms * slot(k - 1); }
+  const float* Lin(int k) const { return k == 0 ? p->L0 : p->L + ms * slot(k - 1); }
+  float* Zout(int k) const { return p->Z + zs * slot(k); }
+  float* Eout(int k) const { return p->E + ms * slot(k); }
+  float* Lout(int k) const { return p->L + ms * slot(k); }
+  float* Tslab(int k) const { return p->T + ms * slot(k); }                            // T_k, k = 0..K
+  uint8_t* mZ(int k) const { return p->maskZ ? p->maskZ + zs * slot(k) : nullptr; }
+  uint8_t* mE(int k) const { return p->maskE ? p->maskE + ms * slot(k) : nullptr; }
+};
+
+static const dladmm_bparam& betaL(const dladmm_problem* p, const dladmm_layer& l) {
+  return p->family == DLADMM_FAMILY_A ? l.beta1 : l.beta3;
+}
+
+// launch helpers --------------------------------------------------------------------------------------
+template <class BLoad, class Epi>
+static int launch_simt(int M, i64 N, int Kd, const float* Aw, int lda, const BLoad& bl, const Epi& epi, float* part,
+                       int ncolTiles, int prow, cudaStream_t st) {
+  dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
+  simt_gemm_kernel<BLoad, Epi><<<grid, SG_THREADS, 0, st>>>(M, N, Kd, Aw, lda, bl, epi, part, ncolTiles, prow);
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+static int prepare_weights(const dladmm_problem* p, const Workspace& w, bool transposed, cudaStream_t st) {
+  // A (m x d): normal copy -> Ap (m x dp); transposed -> Atp (d x mp)
+  {
+    PrepJobs jobs; jobs.n = 1;
+    jobs.j[0].src = p->A;
+    jobs.j[0].dst_n = transposed ? nullptr : w.Ap;
+    jobs.j[0].dst_t = transposed ? w.Atp : nullptr;
+    int R = p->m, C = p->d, ldn = w.dp, ldt = w.mp;
+    dim3 grid((std::max(C, ldn) + 31) / 32, (std::max(R, ldt) + 31) / 32, 1);
+    prep_weights_kernel<<<grid, 256, 0, st>>>(jobs, R, C, ldn, ldt);
+    DL_CUDA(cudaGetLastError());
+  }
+  // W_k (d x m): normal -> Wp (d x mp); transposed -> Wtp (m x dp)
+  std::vector<const float*> uniq = WeightMap(p).uniq;
+  for (size_t base = 0; base < uniq.size(); base += 32) {
+    PrepJobs jobs; jobs.n = (int)std::min<size_t>(32, uniq.size() - base);
+    for (int i = 0; i < jobs.n; ++i) {
+      size_t idx = base + i;
+      jobs.j[i].src = uniq[idx];
+      jobs.j[i].dst_n = transposed ? nullptr : w.Wp + idx * (size_t)p->d * w.mp;
+      jobs.j[i].dst_t = transposed ? w.Wtp + idx * (size_t)p->m * w.dp : nullptr;
+    }
+    int R = p->d, C = p->m, ldn = w.mp, ldt = w.dp;
+    dim3 grid((std::max(C, ldn) + 31) / 32, (std::max(R, ldt) + 31) / 32, jobs.n);
+    prep_weights_kernel<<<grid, 256, 0, st>>>(jobs, R, C, ldn, ldt);
+    DL_CUDA(cudaGetLastError());
+  }
+  return DLADMM_OK;
+}
+
+// ---- forward ----------------------------------------------------------------------------------------
+template <int FAM>
+static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_t st) {
+  Slabs s(p);
+  const int m = p->m, d = p->d;
+  const i64 B = p->B;
+  int rc;
+  // T_0 = A Z0 + E0 - X
+  {
+    BPlain bl{p->Z0, B};
+    EpiT0 epi{p->E0, p->X, s.Tslab(0), B};
+    if ((rc = launch_simt(m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;
+  }
+  for (int k = 0; k < p->K; ++k) {
+    const dladmm_layer& l = p->layers[k];
+    const float* Wk = w.Wp + (size_t)weight_index(p, k) * d * w.mp;
+    {
+      BVar bl{s.Lin(k), s.Tslab(k), make_bp(l.beta1), B};
+      EpiZ epi{s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
+      if ((rc = launch_simt(d, B, m, Wk, w.mp, bl, epi, nullptr, 0, 0, st))) return rc;
+    }
+    {
+      BPlain bl{s.Zout(k), B};
+      EpiELT<FAM> epi{p->X, s.Ein(k), s.Lin(k), s.Eout(k), s.Lout(k), s.Tslab(k + 1), s.mE(k),
+                      make_bp(l.beta2), make_bp(l.ss2), make_bp(l.ss2_2), make_bp(l.theta2), make_bp(betaL(p, l)), B};
+      if ((rc = launch_simt(m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;
+    }
+  }
+  return DLADMM_OK;
+}
+
+// ---- backward ---------------------------------------------------------------------------------------
+static void add_job(ReduceJobs& jobs, int slot, const dladmm_bparam& q, int rows) {
+  if (q.grad == nullptr || q.ptr == nullptr || q.col_period != 0) return;   // per-slot params use atomics
+  ReduceJob& j = jobs.j[jobs.n++];
+  j.slot = slot;
+  j.scalar = q.row_stride == 0;
+  j.rows = rows;
+  j.grad = q.grad;
+}
+
+static void add_m1_jobs(const dladmm_problem* p, ReduceJobs& jobs, const dladmm_layer& l) {
+  add_job(jobs, SL_BL, betaL(p, l), p->m);
+  if (p->family == DLADMM_FAMILY_B) {
+    add_job(jobs, SL_TH2, l.theta2, p->m);
+    add_job(jobs, SL_SS2, l.ss2, p->m);
+    add_job(jobs, SL_B2, l.beta2, p->m);
+  } else if (p->family == DLADMM_FAMILY_A) {
+    add_job(jobs, SL_TH2, l.theta2, p->m);
+    add_job(jobs, SL_B2, l.beta2, p->m);
+  } else {
+    add_job(jobs, SL_SS2, l.ss2, p->m);
+    add_job(jobs, SL_B2, l.ss2_2, p->m);
+  }
+}
+
+static int launch_reduce(const ReduceJobs& jobs, const Workspace& w, cudaStream_t st) {
+  if (jobs.n == 0) return DLADMM_OK;
+  int maxrows = 1;
+  for (int i = 0; i < jobs.n; ++i)
+    if (!jobs.j[i].scalar) maxrows = std::max(maxrows, jobs.j[i].rows);
+  dim3 grid((maxrows + 7) / 8, jobs.n);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(jobs, w.part, w.ncolTiles, w.prow);
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+static M1Args make_m1(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& w, int j) {
+  Slabs s(p);
+  const dladmm_layer& l = p->layers[j];
+  M1Args a;
+  a.Tn = s.Tslab(j + 1);
+  a.Ek = s.Eout(j);
+  a.Ep = s.Ein(j);
+  a.Lp = s.Lin(j);
+  a.maskE = s.mE(j);
+  a.gE = g->gE ? g->gE + s.ms * j : nullptr;
+  a.gL = g->gL ? g->gL + s.ms * j : nullptr;
+  a.gT = g->gT ? g->gT + s.ms * (j + 1) : nullptr;
+  a.bL = make_bp(betaL(p, l));
+  a.b2 = make_bp(l.beta2);
+  a.ss2 = make_bp(l.ss2);
+  a.ss2_2 = make_bp(l.ss2_2);
+  a.th2 = make_bp(l.theta2);
+  a.dR = w.dR; a.cE = w.cE; a.cL = w.cL;
+  a.B = p->B;
+  return a;
+}
+
+template <int FAM>
+static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& w, cudaStream_t st) {
+  Slabs s(p);
+  const int m = p->m, d = p->d, K = p->K;
+  const i64 B = p->B;
+  int rc;
+  // top layer: elementwise cotangent flow with nothing carried
+  {
+    M1Args a = make_m1(p, g, w, K - 1);
+    dim3 grid(w.ncolTiles, (m + 7) / 8);
+    m1_kernel<FAM><<<grid, 256, 0, st>>>(m, B, a, w.part, w.ncolTiles, w.prow);
+    DL_CUDA(cudaGetLastError());
+    ReduceJobs jobs; jobs.n = 0;
+    add_m1_jobs(p, jobs, p->layers[K - 1]);
+    if ((rc = launch_reduce(jobs, w, st))) return rc;
+  }
+  for (int k = K - 1; k >= 0; --k) {
+    const dladmm_layer& l = p->layers[k];
+    const int wi = weight_index(p, k);
+    // BG1: dZ_k = gZ_k + carried + A^T dR ; dx1 -> cZ
+    {
+      BPlain bl{w.dR, B};
+      EpiBG1 epi{g->gZ ? g->gZ + s.zs * k : nullptr, k == K - 1 ? nullptr : w.cZ, s.mZ(k), make_bp(l.theta1), w.cZ, B};
+      if ((rc = launch_simt(d, B, m, w.Atp, w.mp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
+    }
+    // BG3: gW -= s1 * dx1 * V_k^T
+    if (l.gW) {
+      BVar ql{s.Lin(k), s.Tslab(k), make_bp(l.beta1), B};
+      int tiles = ((d + NT_BM - 1) / NT_BM) * ((m + NT_BN - 1) / NT_BN);
+      int split = std::max(1, std::min<int>((592 + tiles - 1) / tiles, (int)((B + 255) / 256)));
+      i64 chunk = round_up64((B + split - 1) / split, NT_BK);
+      split = (int)((B + chunk - 1) / chunk);
+      dim3 grid((d + NT_BM - 1) / NT_BM, (m + NT_BN - 1) / NT_BN, split);
+      simt_gemm_nt_kernel<BVar><<<grid, NT_THREADS, 0, st>>>(d, m, B, chunk, w.cZ, ql, l.ss1.ptr, -1.f, l.gW, m);
+      DL_CUDA(cudaGetLastError());
+    }
+    // BG2: dV = -s1 W^T dx1 ; carried dL, dT ; fused elementwise part of layer k-1
+    {
+      BPlain bl{w.cZ, B};
+      EpiBG2<FAM> epi;
+      epi.Lp = s.Lin(k); epi.Tk = s.Tslab(k);
+      epi.b1 = make_bp(l.beta1); epi.ss1 = make_bp(l.ss1);
+      epi.cLin = w.cL; epi.cEin = w.cE;
+      epi.has_prev = k > 0;
+      epi.prev = make_m1(p, g, w, k > 0 ? k - 1 : 0);
+      epi.B = B;
+      const float* Wt = w.Wtp + (size_t)wi * m * w.dp;
+      if ((rc = launch_simt(m, B, d, Wt, w.dp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
+    }
+    ReduceJobs jobs; jobs.n = 0;
+    add_job(jobs, SL_TH1, l.theta1, d);
+    add_job(jobs, SL_B1, l.beta1, m);
+    add_job(jobs, SL_SS1, l.ss1, m);
+    if (k > 0) add_m1_jobs(p, jobs, p->layers[k - 1]);
+    if ((rc = launch_reduce(jobs, w, st))) return rc;
+  }
+  return DLADMM_OK;
+}
+
+// ---- objective --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) objective_kernel(const float* __restrict__ Z, const float* __restrict__ E,
+                                                        const float* __restrict__ T, i64 zs, i64 ms, float alpha,
+                                                        float* __restrict__ out) {
+  // grid.y = layer k; out[k] += alpha*sum|Z_k| + sum|E_k - T_{k+1}|
+  const int k = blockIdx.y;
+  const float* z = Z + zs * k;
+  const float* e = E + ms * k;
+  const float* t = T + ms * (k + 1);
+  float s = 0.f;
+  for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < zs; i += (i64)gridDim.x * 256) s += alpha * fabsf(z[i]);
+  for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < ms; i += (i64)gridDim.x * 256) s += fabsf(e[i] - t[i]);
+  __shared__ float sm[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = sm[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(out + k, v);
+  }
+}
+
+}  // namespace dladmm
+
+using namespace dladmm;
+
+extern "C" {
+
+const char* dladmm_last_error(void) { return g_err; }
+
+int dladmm_query(int device, dladmm_caps* caps) {
+  if (!caps) { set_error("caps is NULL"); return DLADMM_ERR_INVALID; }
+  memset(caps, 0, sizeof(*caps));
+  caps->abi_version = DLADMM_ABI_VERSION;
+  cudaDeviceProp prop;
+  DL_CUDA(cudaGetDeviceProperties(&prop, device));
+  caps->cc_major = prop.major;
+  caps->cc_minor = prop.minor;
+  caps->sm_count = prop.multiProcessorCount;
+  caps->supported = prop.major == 10;
+  caps->has_tcgen05 = DLADMM_HAS_UMMA;
+  caps->total_mem = (int64_t)prop.totalGlobalMem;
+  return DLADMM_OK;
+}
+
+size_t dladmm_workspace_bytes(const dladmm_problem* p, int for_backward) {
+  if (!p || !p->layers || p->K <= 0) return 0;
+  dladmm_problem q = *p;
+  q.workspace = nullptr;
+  Workspace w = carve(&q, for_backward);
+  size_t extra = umma_workspace_bytes(&q, for_backward);
+  return w.bytes + extra;
+}
+
+int dladmm_forward(const dladmm_problem* p, void* stream) {
+  int rc = validate(p, 0);
+  if (rc) return rc;
+  if (p->B == 0) return DLADMM_OK;
+  if ((rc = check_device())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w = carve(p, 0);
+  if (p->precision != DLADMM_PREC_FP32) return umma_forward(p, (char*)p->workspace + w.bytes, st);
+  if ((rc = prepare_weights(p, w, false, st))) return rc;
+  switch (p->family) {
+    case DLADMM_FAMILY_A: return forward_simt<DLADMM_FAMILY_A>(p, w, st);
+    case DLADMM_FAMILY_B: return forward_simt<DLADMM_FAMILY_B>(p, w, st);
+    default: return forward_simt<DLADMM_FAMILY_C>(p, w, st);
+  }
+}
+
+int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* stream) {
+  int rc = validate(p, 1);
+  if (rc) return rc;
+  if (!g) { set_error("cotangents is NULL"); return DLADMM_ERR_INVALID; }
+  if (p->B == 0) return DLADMM_OK;
+  if ((rc = check_device())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w = carve(p, 1);
+  if (p->precision != DLADMM_PREC_FP32) return umma_backward(p, g, (char*)p->workspace + w.bytes, st);
+  if ((rc = prepare_weights(p, w, true, st))) return rc;
+  switch (p->family) {
+    case DLADMM_FAMILY_A: return backward_simt<DLADMM_FAMILY_A>(p, g, w, st);
+    case DLADMM_FAMILY_B: return backward_simt<DLADMM_FAMILY_B>(p, g, w, st);
+    default: return backward_simt<DLADMM_FAMILY_C>(p, g, w, st);
+  }
+}
+
+int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* stream) {
+  DL_REQUIRE(p && out, "problem/out is NULL");
+  DL_REQUIRE(p->last_only == 0, "objective needs every iterate (last_only must be 0)");
+  DL_REQUIRE(p->Z && p->E && p->T && p->K > 0, "Z, E, T must be non-NULL");
+  int rc;
+  if ((rc = check_device())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * p->K, st));
+  if (p->B == 0) return DLADMM_OK;
+  i64 zs = (i64)p->d * p->B, ms = (i64)p->m * p->B;
+  int bx = (int)std::min<i64>((zs + 255) / 256, 592);
+  objective_kernel<<<dim3(bx, p->K), 256, 0, st>>>(p->Z, p->E, p->T, zs, ms, alpha, out);
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+}  // extern "C"

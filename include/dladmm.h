@@ -1,0 +1,177 @@
+/*
+ * dladmm.h -- C ABI of the B200-native D-LADMM hot path (libdladmm.so).
+ *
+ * The reference (xhchrn/D-LADMM) is pure Python with no FFI; its "plugin API" for this path is the
+ * nn.Module contract of DLADMMNet.  The entry points below are what an autograd.Function behind that
+ * module binds (ctypes), and each one cites the reference code it replaces:
+ *
+ *   dladmm_forward   <- DLADMMNet.forward, all K layers
+ *                       main_syn_l1l1_scalar.py:80-127 (scalar), main_syn_l1l1_full.py:59-106 (full),
+ *                       main_syn_l1l1_scalar_tied.py:82-129 (tied), main_syn_lasso_scalar.py:65-112 (lasso),
+ *                       main_lena.py:61-98 (lena), main_syn_l1l1_ltheta.py:67-104 (ltheta)
+ *   dladmm_backward  <- autograd of the above (total_loss.backward(), main_syn_l1l1_scalar.py:301)
+ *   dladmm_gen_syn   <- gen_syn_data.py:12-47 (Gaussian unit-column A; Bernoulli*Gaussian Z, E; X = AZ+E)
+ *   dladmm_objective <- per-layer L1-L1 objective, main_syn_l1l1_scalar.py:333-334
+ *
+ * Conventions
+ *   - All matrices are float32, row-major.  Activations are (features x B) with the batch (problem
+ *     instances, "columns") contiguous, exactly as the reference holds them (SURVEY.md preamble).
+ *   - Every pointer in dladmm_problem / dladmm_layer is a DEVICE pointer owned by the caller (PyTorch's
+ *     caching allocator).  The library never allocates or frees device memory; scratch is the caller's
+ *     `workspace` (size from dladmm_workspace_bytes).  The dladmm_layer array itself lives on the HOST.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation inside.
+ *   - Return value 0 on success, negative dladmm_status otherwise; dladmm_last_error() gives the message
+ *     for the calling thread.  There is no CPU fallback: a device that is not sm_100 is an error.
+ */
+#ifndef DLADMM_H_
+#define DLADMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLADMM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DLADMM_API __attribute__((visibility("default")))
+#else
+#define DLADMM_API
+#endif
+
+typedef enum dladmm_status {
+  DLADMM_OK = 0,
+  DLADMM_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  DLADMM_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  DLADMM_ERR_WORKSPACE = -3,    /* workspace too small */
+  DLADMM_ERR_DEVICE = -4        /* device is not sm_100 (no fallback) */
+} dladmm_status;
+
+/* E-step family.  A: lena/ltheta, B: scalar/full/tied, C: lasso. */
+typedef enum dladmm_family { DLADMM_FAMILY_A = 0, DLADMM_FAMILY_B = 1, DLADMM_FAMILY_C = 2 } dladmm_family;
+
+/* Arithmetic of the two matrix products per layer.  Epilogues are always fp32 with the reference's
+ * operation order (no FMA contraction). */
+typedef enum dladmm_precision {
+  DLADMM_PREC_FP32 = 0,     /* CUDA-core FFMA, fp32 products and accumulation */
+  DLADMM_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3 passes (big*big + big*small + small*big), fp32 accumulate in TMEM */
+  DLADMM_PREC_TF32 = 2      /* tcgen05 kind::tf32, single pass (stated-tolerance option) */
+} dladmm_precision;
+
+/* A learnable parameter broadcast against a (rows x B) activation.
+ *   value(row, col) = ptr[row * row_stride + (col_period ? col % col_period : 0)]
+ *   (1,1) scalar: row_stride 0, col_period 0;  (rows,1): row_stride 1, col_period 0;
+ *   (rows,bs) per batch slot (main_lena.py:35-36): row_stride bs, col_period bs.
+ * `grad` (backward only; may be NULL) has the parameter's own shape, must be zero-initialised by the
+ * caller, and is accumulated into.  ptr == NULL means "parameter absent" (e.g. ss1 outside the tied variant). */
+typedef struct dladmm_bparam {
+  const float* ptr;
+  float* grad;
+  int32_t row_stride;
+  int32_t col_period;
+} dladmm_bparam;
+
+/* Per-layer parameters; reference names in comments (state_dict keys `<name>.<k>`). */
+typedef struct dladmm_layer {
+  dladmm_bparam beta1;    /* beta1.k  : V_k = L_{k-1} + beta1*T_k ; family A also L-update */
+  dladmm_bparam beta2;    /* beta2.k  : family A,B E-step */
+  dladmm_bparam beta3;    /* beta3.k  : family B,C L-update */
+  dladmm_bparam ss1;      /* ss1.k    : tied only (main_syn_l1l1_scalar_tied.py:96) */
+  dladmm_bparam ss2;      /* ss2.k (B) or ss2_1.k (C) */
+  dladmm_bparam ss2_2;    /* ss2_2.k  : C only (main_syn_lasso_scalar.py:103) */
+  dladmm_bparam theta1;   /* active_para.k  (Z threshold); lena: fixed 0.025 */
+  dladmm_bparam theta2;   /* active_para1.k (E threshold, A,B); lena: fixed 0.06 */
+  const float* W;         /* fc[k].weight (d,m) dense row-major; tied: same pointer in every layer */
+  float* gW;              /* d(loss)/dW, (d,m), zero-initialised by caller, accumulated (backward only) */
+} dladmm_layer;
+
+typedef struct dladmm_problem {
+  int32_t abi_version;    /* DLADMM_ABI_VERSION */
+  int32_t family;         /* dladmm_family */
+  int32_t precision;      /* dladmm_precision */
+  int32_t m, d, K;        /* A is (m,d); K unrolled layers */
+  int64_t B;              /* columns (problem instances) in this call; every (rows x B) array has pitch B */
+  int32_t last_only;      /* 0: Z/E/L hold K slabs and T holds K+1 (reference API, a10);
+                             1: inference only, slabs are reused modulo 2 (Z/E/L: 2 slabs, T: 2 slabs);
+                                the final iterate is slab (K-1)%2, T_K is slab K%2 */
+  int32_t reserved;
+  const float* A;         /* (m,d) */
+  const float* X;         /* (m,B) observation */
+  const float* Z0;        /* (d,B) */
+  const float* E0;        /* (m,B) */
+  const float* L0;        /* (m,B) */
+  const dladmm_layer* layers;  /* HOST array of K entries */
+  float* Z;               /* out (K,d,B)   */
+  float* E;               /* out (K,m,B)   */
+  float* L;               /* out (K,m,B)   */
+  float* T;               /* out (K+1,m,B), T[0] = A Z0 + E0 - X */
+  uint8_t* maskZ;         /* out (K,d,B) or NULL: bit0 = [x-theta>0], bit1 = [-x-theta>0] of the Z prox (training) */
+  uint8_t* maskE;         /* out (K,m,B) or NULL: same for the E prox (families A,B) */
+  void* workspace;
+  size_t workspace_bytes;
+} dladmm_problem;
+
+/* Upstream cotangents for backward; each may be NULL (= zero).  Shapes as the forward outputs. */
+typedef struct dladmm_cotangents {
+  const float* gZ;        /* (K,d,B)   */
+  const float* gE;        /* (K,m,B)   */
+  const float* gL;        /* (K,m,B)   */
+  const float* gT;        /* (K+1,m,B) */
+} dladmm_cotangents;
+
+typedef struct dladmm_caps {
+  int32_t abi_version;
+  int32_t cc_major, cc_minor;
+  int32_t sm_count;
+  int32_t supported;      /* 1 iff cc 10.x */
+  int32_t has_tcgen05;    /* tensor-core precisions available in this build */
+  int64_t total_mem;
+} dladmm_caps;
+
+typedef struct dladmm_gen_desc {
+  int32_t m, d;
+  int64_t B;              /* columns generated in this call */
+  int64_t col_offset;     /* global index of the first column (shards reproduce the same stream) */
+  uint64_t seed;
+  float p;                /* Bernoulli keep probability (gen_syn_data.py -p) */
+  float mu, sigma;        /* Gaussian amplitude (gen_syn_data.py:24-25) */
+  int32_t dense_noise;    /* 0: E = Bern(p)*N(mu,sigma); 1: E ~ N(0, sigma_e) dense (gen_syn_unseen_data_lasso.py:41-42) */
+  float sigma_e;
+  int32_t generate_A;     /* 1: draw A ~ N(0,1) and normalise columns (gen_syn_data.py:14-16); 0: use A as given */
+  float* A;               /* (m,d) in/out */
+  float* Zs;              /* out (d,B) ground-truth sparse code */
+  float* Es;              /* out (m,B) ground-truth noise */
+  float* X;               /* out (m,B) = A Zs + Es */
+  void* workspace;        /* scratch, dladmm_gen_workspace_bytes(m, d) bytes */
+  size_t workspace_bytes;
+} dladmm_gen_desc;
+
+/* Bytes of scratch the caller must provide in problem->workspace. */
+DLADMM_API size_t dladmm_workspace_bytes(const dladmm_problem* p, int for_backward);
+
+DLADMM_API int dladmm_forward(const dladmm_problem* p, void* stream);
+
+/* Requires the outputs and masks of a forward over the same problem (last_only == 0, masks non-NULL). */
+DLADMM_API int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* stream);
+
+DLADMM_API size_t dladmm_gen_workspace_bytes(int32_t m, int32_t d);
+
+/* Counter-based (Philox4x32-10) generator: the value of element (row, global column) depends only on
+ * (seed, row, col_offset + column), so column shards on different GPUs reproduce one global stream. */
+DLADMM_API int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream);
+
+/* Per-layer L1-L1 objective summed over the batch: out[k] = sum_{b} ( alpha*||Z_k[:,b]||_1 + ||X[:,b] - A Z_k[:,b]||_1 ),
+ * k = 0..K-1, from the iterates a forward (last_only == 0) left in p->Z/E/T, using X - A Z_k = E_k - T_{k+1}
+ * (no extra matrix product).  `out` is K floats on the device, overwritten. */
+DLADMM_API int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* stream);
+
+DLADMM_API int dladmm_query(int device, dladmm_caps* caps);
+
+DLADMM_API const char* dladmm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLADMM_H_ */

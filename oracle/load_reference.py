@@ -1,0 +1,82 @@
+"""Load the reference's own ``DLADMMNet`` classes from /root/reference (build container only).
+
+TEST INFRASTRUCTURE -- not product code.  Used by ``oracle/make_golden.py`` and by the CPU
+tests that pin ``oracle/dladmm_oracle.py`` to the reference.  ``/root/reference`` does not
+exist on the GPU box, so nothing marked ``gpu`` may import this module.
+
+The reference scripts hard-code ``.cuda()`` in ``DLADMMNet.__init__`` (e.g.
+main_syn_l1l1_scalar.py:40-44) and most of them run training at import time, so the class is
+extracted by AST (``ClassDef DLADMMNet``) and executed in a namespace holding only the names
+the class body needs.  ``Tensor.cuda`` / ``Module.cuda`` are patched to identity while the
+class is constructed so that it runs on CPU, unmodified.
+"""
+import ast
+import contextlib
+import os
+from math import sqrt
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REFERENCE_ROOT = os.environ.get("DLADMM_REFERENCE_ROOT", "/root/reference")
+
+# variant name -> reference script that declares the class
+VARIANT_FILES = {
+    "lena": "main_lena.py",                       # family A, (m x bs) betas, fixed thresholds
+    "ltheta": "main_syn_l1l1_ltheta.py",          # family A, (m,1) betas, learnable thresholds
+    "scalar": "main_syn_l1l1_scalar.py",          # family B, (1,1) params
+    "full": "main_syn_l1l1_full.py",              # family B, per-row params
+    "tied": "main_syn_l1l1_scalar_tied.py",       # family B, one shared fc + ss1
+    "lasso": "main_syn_lasso_scalar.py",          # family C, linear E-step
+}
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, VARIANT_FILES["scalar"]))
+
+
+@contextlib.contextmanager
+def cuda_is_identity():
+    """Patch ``.cuda()`` to a no-op so the reference's constructors run on CPU."""
+    t_cuda, m_cuda = torch.Tensor.cuda, nn.Module.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, nn.Module.cuda = t_cuda, m_cuda
+
+
+def load_class(variant, alpha=0.001, script=None):
+    """Return the reference ``DLADMMNet`` class object for ``variant`` (unmodified source)."""
+    path = os.path.join(REFERENCE_ROOT, script or VARIANT_FILES[variant])
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    nodes = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DLADMMNet"]
+    if not nodes:
+        raise RuntimeError("no DLADMMNet class in %s" % path)
+    module = ast.Module(body=nodes, type_ignores=[])
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "sqrt": sqrt, "alpha": alpha,
+          "__name__": "reference_" + variant}
+    exec(compile(module, path, "exec"), ns)
+    return ns["DLADMMNet"]
+
+
+def build(variant, m, n, d, batch_size, A, Z0, E0, L0, layers, alpha=0.001):
+    """Instantiate the reference model on CPU with its own default initialisation."""
+    cls = load_class(variant, alpha=alpha)
+    with cuda_is_identity():
+        model = cls(m=m, n=n, d=d, batch_size=batch_size, A=A, Z0=Z0, E0=E0, L0=L0, layers=layers)
+    return model
+
+
+def run(model, x):
+    """Forward through the reference; always returns (Z, E, L, T-or-None) lists."""
+    with cuda_is_identity():
+        out = model(x)
+    if len(out) == 4:
+        return out
+    Z, E, L = out
+    return Z, E, L, None
