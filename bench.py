@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- D-LADMM hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision P]
+
+Workload (BASELINE.json metric "D-LADMM fwd instances/sec (K=15, batch 64K)"; SURVEY 8(a) "C1"):
+    scalar variant (main_syn_l1l1_scalar.py), m=250, d=500, K=15 layers, B=65536 problem instances per GPU,
+    synthetic data with gen_syn_data.py semantics (p=0.1, sigma=1), reference default weight init,
+    forward returning EVERY layer's iterates (the reference API, a10).
+A "step" is one K-layer forward over one batch.  value = instances/s with inputs resident in HBM;
+e2e = the same through DLADMMNet.forward with the observations in pinned HOST memory (H2D copy inside the
+timed region) plus a D2H read of the per-layer objective.  Weak scaling: every rank owns its own 65536
+columns, no collective on the data path.
+
+--impl reference: the reference's algorithm on the host CPU (the oracle port -- the reference is Python
+and cannot travel to the GPU box), all host threads, each step a bounded column sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+M, D, K_LAYERS, B_PER_GPU = 250, 500, 15, 65536
+VARIANT = "scalar"
+METRIC = "dladmm_fwd_instances_per_sec"
+UNIT = "instances/s"
+F_FWD = 2.0 * M * D * (2 * K_LAYERS + 1)          # algorithmic flops per instance
+F_GEMM_PER_COL = 2.0 * M * D                      # one (d x m)(m x 1) or (m x d)(d x 1) product
+
+
+def _peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            j = json.load(fh)
+        p.update(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"], bf16_tflops_sustained=j.get("bf16_tflops_sustained"),
+                 source="measured")
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "measured_tf32_peak.json")) as fh:
+            p["tf32_tflops"] = json.load(fh)["tf32_tflops"]
+            p["tf32_source"] = "measured (profiles/measured_tf32_peak.json)"
+    except Exception:
+        p["tf32_tflops"] = p["bf16_tflops"] / 2.0
+        p["tf32_source"] = "bf16 peak / 2 (TF32 not measured)"
+    return p
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                mx = float(f[2])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[1]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on host cores (oracle port of the reference's ATen op sequence)
+# ---------------------------------------------------------------------------------------------------
+def cpu_forward_rate(sample_cols, reps, seed=1126):
+    import torch
+    import dladmm_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, D, generator=g)
+    A = A / A.pow(2).sum(dim=0, keepdim=True).sqrt()
+    Zs = (torch.rand(D, sample_cols, generator=g) < 0.1).float() * torch.randn(D, sample_cols, generator=g)
+    Es = (torch.rand(M, sample_cols, generator=g) < 0.1).float() * torch.randn(M, sample_cols, generator=g)
+    X = A.mm(Zs) + Es
+    Z0 = torch.rand(D, sample_cols, generator=g) / D
+    E0 = torch.zeros(M, sample_cols); L0 = torch.zeros(M, sample_cols)
+    sd = orc.default_state_dict(VARIANT, A, K_LAYERS, sample_cols, generator=g)
+    times = []
+    with torch.no_grad():
+        orc.forward(VARIANT, sd, A, X[:, :512].contiguous(), Z0[:, :512].contiguous(), E0[:, :512].contiguous(),
+                    L0[:, :512].contiguous(), K_LAYERS)                    # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            orc.forward(VARIANT, sd, A, X, Z0, E0, L0, K_LAYERS)
+            times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return 0
+    sample = 8192
+    times, threads = cpu_forward_rate(sample, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = sample * len(timed) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C1 scalar D-LADMM forward, m=250 d=500 K=15, all iterates returned",
+                   "columns_per_step": sample, "variant": VARIANT},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d-column forward per step (full workload is %d columns per GPU)" % (sample, B_PER_GPU)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dladmm_b200 as dl
+    from dladmm_b200 import _lib
+
+    rank, world, local = _dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    precision = args.precision or dl.default_precision()
+    B = args.columns
+    # this rank's column shard of the global data set (weak scaling: B columns per rank)
+    data = dl.gen_syn_data(B, m=M, d=D, p=0.1, sigma=1.0, seed=1126, device=dev, col_offset=rank * B)
+    A_host = data.A
+    if world > 1:   # A is generated from the seed alone, identical on every rank; assert it
+        chk = data.A.sum().reshape(1).clone()
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        assert all(torch.equal(lst[0], t) for t in lst)
+    g = torch.Generator(device=dev).manual_seed(1126 + rank)
+    Z0 = torch.rand(D, B, device=dev, generator=g) / D                # main_syn_l1l1_scalar.py:226
+    E0 = torch.zeros(M, B, device=dev); L0 = torch.zeros(M, B, device=dev)
+    torch.manual_seed(1126)
+    model = dl.VARIANT_CLASSES[VARIANT](M, 10000, D, B, A_host, Z0, E0, L0, K_LAYERS, precision=precision, device=dev)
+    X = data.X
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        with torch.no_grad():
+            return model(X)
+
+    # ---- kernel-only: inputs resident in HBM -------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    del out
+
+    # ---- per-kernel pass (CUDA events around every launch, same steps) --------------------------------
+    _lib.profile_start()
+    for _ in range(args.steps):
+        step_resident()
+    prof = _lib.profile_stop()
+
+    # ---- end to end: pinned host observations -> H2D -> forward -> objective -> D2H -------------------
+    X_host = X.cpu().pin_memory()
+    x_dev = torch.empty_like(X)
+    obj_host = torch.empty(K_LAYERS, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        x_dev.copy_(X_host, non_blocking=True)
+        with torch.no_grad():
+            Z, E, L, T = model(x_dev)
+            obj = dl.l1l1_objective(Z, E, T, 0.001)
+        obj_host.copy_(obj, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return obj_host
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- optional training throughput (forward + backward + parameter gradients) ----------------------
+    train = None
+    if args.train_columns > 0:
+        Bt = args.train_columns
+        tm = dl.VARIANT_CLASSES[VARIANT](M, 10000, D, Bt, A_host, Z0[:, :Bt].contiguous(), E0[:, :Bt].contiguous(),
+                                         L0[:, :Bt].contiguous(), K_LAYERS, precision=precision, device=dev)
+        Xt = X[:, :Bt].contiguous()
+
+        def step_train():
+            tm.zero_grad(set_to_none=True)
+            Z, E, L, T = tm(Xt)
+            loss = 0
+            for k in range(K_LAYERS):   # main_syn_l1l1_scalar.py:289-299 with X - A Z_k = E_k - T_{k+1}
+                loss = loss + (0.001 * Z[k].abs().sum() + (E[k] - T[k + 1]).abs().sum()) / Bt
+            loss.backward()
+            if world > 1:
+                dl.allreduce_gradients(list(tm.parameters()))
+        for _ in range(2):
+            step_train()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nst = max(2, args.steps // 2)
+        t0.record()
+        for _ in range(nst):
+            step_train()
+        t1.record()
+        barrier()
+        ms_train = t0.elapsed_time(t1)
+        train = {"columns_per_gpu": Bt, "ms_per_step": ms_train / nst}
+
+    # ---- max over ranks -------------------------------------------------------------------------------
+    stats = torch.tensor([ms_total, ms_e2e, train["ms_per_step"] if train else 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_train_step = [float(v) for v in stats.tolist()]
+
+    if rank == 0:
+        peaks = _peaks()
+        ms_step = ms_total / args.steps
+        value = world * B * args.steps / (ms_total * 1e-3)
+        e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+        # dominant kernel = the kind with the most device time in the per-kernel pass
+        kinds = {k: v for k, v in prof.items() if v[1] > 0}
+        dom = max(kinds, key=lambda k: kinds[k][0])
+        dom_ms, dom_n = kinds[dom]
+        gemm_kinds = ("gemm_t0", "gemm_z", "gemm_elt")
+        flops_per_launch = F_GEMM_PER_COL * B
+        mma_passes = {"fp32": 1, "tf32": 1, "tf32x3": 3}[precision]
+        achieved = flops_per_launch / (dom_ms / dom_n * 1e-3) / 1e12 if dom in gemm_kinds else None
+        peak = peaks["tf32_tflops"] / mma_passes
+        total_prof = sum(v[0] for v in kinds.values())
+        roofline = {
+            "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": None,
+            "peak_source": "TF32 dense %s, divided by %d MMA pass(es) for precision %s; MEASURED_PEAKS %s" %
+                           (peaks["tf32_source"], mma_passes, precision, peaks["source"]),
+            "share_of_step": dom_ms / total_prof if total_prof else None,
+            "avg_launch_ms": dom_ms / dom_n,
+            "algorithmic_flops_per_launch": flops_per_launch,
+            "hbm_achieved_gbs_whole_step": (4.0 * (K_LAYERS * (3 * D + 8 * M) + 2 * M + D) * B) / (ms_step * 1e-3) / 1e9,
+            "hbm_peak_gbs": peaks["hbm_gbs"],
+            "per_kind_ms_per_step": {k: v[0] / args.steps for k, v in kinds.items()},
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "tf32": "tf32"}[precision], "data": "synthetic",
+            "config": {"workload": "C1 scalar D-LADMM forward (main_syn_l1l1_scalar.py), m=250 d=500 K=15, "
+                                   "%d instances per GPU, all K iterates of Z,E,L,T returned (reference API)" % B,
+                       "variant": VARIANT, "precision": precision, "columns_per_gpu": B,
+                       "l2": "inputs+outputs per step (%.1f GB) far exceed the 126 MB L2; no explicit flush" %
+                             (4.0 * (K_LAYERS * (D + 3 * M) + 4 * M + D) * B / 1e9),
+                       "parallelism": "columns sharded, %d rank(s), no data-path collective" % world},
+            "algorithmic_tflops": value * F_FWD / 1e12,
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(X_host.numel() * 4),
+                    "d2h_bytes_per_step": int(K_LAYERS * 4), "ms_per_step": ms_e2e / args.steps,
+                    "api": "DLADMMNet.forward(x) + l1l1_objective, x copied from pinned host memory each step"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if train:
+            line["train"] = {"metric": "dladmm_train_samples_per_sec", "value": world * train["columns_per_gpu"] / (ms_train_step * 1e-3),
+                             "unit": "samples/s", "columns_per_gpu": train["columns_per_gpu"], "ms_per_step": ms_train_step,
+                             "what": "forward + backward + parameter gradients%s, scalar K=15" % (" + NCCL allreduce" if world > 1 else "")}
+        if world == 1 and not args.no_cpu_baseline:
+            times, threads = cpu_forward_rate(8192, 3)
+            cpu_val = 8192 * 2 / sum(times[1:])
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "2 timed forwards of 8192 columns (same m,d,K, all iterates) after 1 warm-up"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32x3", "tf32"])
+    ap.add_argument("--columns", type=int, default=B_PER_GPU, help="problem instances per GPU")
+    ap.add_argument("--train-columns", type=int, default=16384, help="columns per GPU for the training leg (0 = skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,31 @@
+"""d-ladmm_b200: B200-native (sm_100a) implementation of the D-LADMM unrolled forward/backward hot path
+behind the reference's own ``DLADMMNet`` nn.Module interface (xhchrn/D-LADMM).
+
+Import as ``dladmm_b200`` (the repo root carries a one-line shim because the directory name contains a
+hyphen).  Everything that computes goes through libdladmm.so (include/dladmm.h); nothing here falls back
+to PyTorch eager or to the CPU.
+"""
+from . import _lib
+from .net import (DLADMMNet, DLADMMNetFull, DLADMMNetLasso, DLADMMNetLena, DLADMMNetLtheta, DLADMMNetScalar,
+                  DLADMMNetTied, VARIANT_CLASSES, default_precision)
+from .function import UnrolledLADMM, LayerSpec, run_forward
+from .gen_syn import gen_syn_data, SynData
+from .objective import l1l1_objective
+from .sharding import column_shard, allreduce_gradients, ShardedTrainer
+
+__all__ = ["DLADMMNet", "DLADMMNetScalar", "DLADMMNetFull", "DLADMMNetTied", "DLADMMNetLasso", "DLADMMNetLena",
+           "DLADMMNetLtheta", "VARIANT_CLASSES", "UnrolledLADMM", "LayerSpec", "run_forward", "gen_syn_data",
+           "SynData", "l1l1_objective", "column_shard", "allreduce_gradients", "ShardedTrainer",
+           "default_precision", "library_path", "query_device"]
+
+
+def library_path():
+    return _lib.LIB_PATH
+
+
+def query_device(device=0):
+    """dladmm_query: compute capability, SM count and whether this build has the tcgen05 kernels."""
+    import ctypes as C
+    caps = _lib.Caps()
+    _lib.check(_lib.load().dladmm_query(int(device), C.byref(caps)))
+    return {f[0]: getattr(caps, f[0]) for f in _lib.Caps._fields_}

@@ -29,6 +29,13 @@ void set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+// ---- launch accounting / per-kind timers (definitions in dladmm_api.cu) -----------------------------
+struct LaunchScope {
+  int kind; cudaStream_t st; void* rec;
+  LaunchScope(int kind, cudaStream_t st);
+  ~LaunchScope();
+};
+
 // ---- broadcast parameter (device view of dladmm_bparam) ----------------------------------------
 struct BP {
   const float* p;

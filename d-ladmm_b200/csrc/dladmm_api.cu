@@ -20,6 +20,27 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- launch accounting ---------------------------------------------------------------------------
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static long long g_launches = 0;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+LaunchScope::LaunchScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_), rec(nullptr) {
+  ++g_launches;
+  if (g_prof_on) {
+    ProfRec r; r.kind = kind;
+    if (cudaEventCreate(&r.a) == cudaSuccess && cudaEventCreate(&r.b) == cudaSuccess) {
+      cudaEventRecord(r.a, st);
+      g_prof.push_back(r);
+      rec = (void*)(size_t)g_prof.size();
+    }
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (rec) cudaEventRecord(g_prof[(size_t)rec - 1].b, st);
+}
+
 // ---- workspace carving -------------------------------------------------------------------------
 struct Workspace {
   // forward
@@ -156,10 +177,13 @@ static const dladmm_bparam& betaL(const dladmm_problem* p, const dladmm_layer& l
 
 // launch helpers --------------------------------------------------------------------------------------
 template <class BLoad, class Epi>
-static int launch_simt(int M, i64 N, int Kd, const float* Aw, int lda, const BLoad& bl, const Epi& epi, float* part,
+static int launch_simt(int kind, int M, i64 N, int Kd, const float* Aw, int lda, const BLoad& bl, const Epi& epi, float* part,
                        int ncolTiles, int prow, cudaStream_t st) {
   dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
-  simt_gemm_kernel<BLoad, Epi><<<grid, SG_THREADS, 0, st>>>(M, N, Kd, Aw, lda, bl, epi, part, ncolTiles, prow);
+  {
+    LaunchScope ls(kind, st);
+    simt_gemm_kernel<BLoad, Epi><<<grid, SG_THREADS, 0, st>>>(M, N, Kd, Aw, lda, bl, epi, part, ncolTiles, prow);
+  }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }
@@ -173,7 +197,7 @@ static int prepare_weights(const dladmm_problem* p, const Workspace& w, bool tra
     jobs.j[0].dst_t = transposed ? w.Atp : nullptr;
     int R = p->m, C = p->d, ldn = w.dp, ldt = w.mp;
     dim3 grid((std::max(C, ldn) + 31) / 32, (std::max(R, ldt) + 31) / 32, 1);
-    prep_weights_kernel<<<grid, 256, 0, st>>>(jobs, R, C, ldn, ldt);
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_weights_kernel<<<grid, 256, 0, st>>>(jobs, R, C, ldn, ldt); }
     DL_CUDA(cudaGetLastError());
   }
   // W_k (d x m): normal -> Wp (d x mp); transposed -> Wtp (m x dp)
@@ -188,7 +212,7 @@ static int prepare_weights(const dladmm_problem* p, const Workspace& w, bool tra
     }
     int R = p->d, C = p->m, ldn = w.mp, ldt = w.dp;
     dim3 grid((std::max(C, ldn) + 31) / 32, (std::max(R, ldt) + 31) / 32, jobs.n);
-    prep_weights_kernel<<<grid, 256, 0, st>>>(jobs, R, C, ldn, ldt);
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_weights_kernel<<<grid, 256, 0, st>>>(jobs, R, C, ldn, ldt); }
     DL_CUDA(cudaGetLastError());
   }
   return DLADMM_OK;
@@ -205,7 +229,7 @@ static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_
   {
     BPlain bl{p->Z0, B};
     EpiT0 epi{p->E0, p->X, s.Tslab(0), B};
-    if ((rc = launch_simt(m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;
+    if ((rc = launch_simt(DLADMM_KIND_GEMM_T0, m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;
   }
   for (int k = 0; k < p->K; ++k) {
     const dladmm_layer& l = p->layers[k];
@@ -213,13 +237,13 @@ static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_
     {
       BVar bl{s.Lin(k), s.Tslab(k), make_bp(l.beta1), B};
       EpiZ epi{s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
-      if ((rc = launch_simt(d, B, m, Wk, w.mp, bl, epi, nullptr, 0, 0, st))) return rc;
+      if ((rc = launch_simt(DLADMM_KIND_GEMM_Z, d, B, m, Wk, w.mp, bl, epi, nullptr, 0, 0, st))) return rc;
     }
     {
       BPlain bl{s.Zout(k), B};
       EpiELT<FAM> epi{p->X, s.Ein(k), s.Lin(k), s.Eout(k), s.Lout(k), s.Tslab(k + 1), s.mE(k),
                       make_bp(l.beta2), make_bp(l.ss2), make_bp(l.ss2_2), make_bp(l.theta2), make_bp(betaL(p, l)), B};
-      if ((rc = launch_simt(m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;
+      if ((rc = launch_simt(DLADMM_KIND_GEMM_ELT, m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;
     }
   }
   return DLADMM_OK;
@@ -256,7 +280,7 @@ static int launch_reduce(const ReduceJobs& jobs, const Workspace& w, cudaStream_
   for (int i = 0; i < jobs.n; ++i)
     if (!jobs.j[i].scalar) maxrows = std::max(maxrows, jobs.j[i].rows);
   dim3 grid((maxrows + 7) / 8, jobs.n);
-  reduce_partials_kernel<<<grid, 256, 0, st>>>(jobs, w.part, w.ncolTiles, w.prow);
+  { LaunchScope ls(DLADMM_KIND_BWD_REDUCE, st); reduce_partials_kernel<<<grid, 256, 0, st>>>(jobs, w.part, w.ncolTiles, w.prow); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }
@@ -293,7 +317,7 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
   {
     M1Args a = make_m1(p, g, w, K - 1);
     dim3 grid(w.ncolTiles, (m + 7) / 8);
-    m1_kernel<FAM><<<grid, 256, 0, st>>>(m, B, a, w.part, w.ncolTiles, w.prow);
+    { LaunchScope ls(DLADMM_KIND_BWD_ELEM, st); m1_kernel<FAM><<<grid, 256, 0, st>>>(m, B, a, w.part, w.ncolTiles, w.prow); }
     DL_CUDA(cudaGetLastError());
     ReduceJobs jobs; jobs.n = 0;
     add_m1_jobs(p, jobs, p->layers[K - 1]);
@@ -306,7 +330,7 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
     {
       BPlain bl{w.dR, B};
       EpiBG1 epi{g->gZ ? g->gZ + s.zs * k : nullptr, k == K - 1 ? nullptr : w.cZ, s.mZ(k), make_bp(l.theta1), w.cZ, B};
-      if ((rc = launch_simt(d, B, m, w.Atp, w.mp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
+      if ((rc = launch_simt(DLADMM_KIND_BWD_GEMM_DZ, d, B, m, w.Atp, w.mp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
     }
     // BG3: gW -= s1 * dx1 * V_k^T
     if (l.gW) {
@@ -316,7 +340,8 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
       i64 chunk = round_up64((B + split - 1) / split, NT_BK);
       split = (int)((B + chunk - 1) / chunk);
       dim3 grid((d + NT_BM - 1) / NT_BM, (m + NT_BN - 1) / NT_BN, split);
-      simt_gemm_nt_kernel<BVar><<<grid, NT_THREADS, 0, st>>>(d, m, B, chunk, w.cZ, ql, l.ss1.ptr, -1.f, l.gW, m);
+      { LaunchScope ls(DLADMM_KIND_BWD_GEMM_DW, st);
+        simt_gemm_nt_kernel<BVar><<<grid, NT_THREADS, 0, st>>>(d, m, B, chunk, w.cZ, ql, l.ss1.ptr, -1.f, l.gW, m); }
       DL_CUDA(cudaGetLastError());
     }
     // BG2: dV = -s1 W^T dx1 ; carried dL, dT ; fused elementwise part of layer k-1
@@ -330,7 +355,7 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
       epi.prev = make_m1(p, g, w, k > 0 ? k - 1 : 0);
       epi.B = B;
       const float* Wt = w.Wtp + (size_t)wi * m * w.dp;
-      if ((rc = launch_simt(m, B, d, Wt, w.dp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
+      if ((rc = launch_simt(DLADMM_KIND_BWD_GEMM_DV, m, B, d, Wt, w.dp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
     }
     ReduceJobs jobs; jobs.n = 0;
     add_job(jobs, SL_TH1, l.theta1, d);
@@ -372,6 +397,35 @@ using namespace dladmm;
 extern "C" {
 
 const char* dladmm_last_error(void) { return g_err; }
+
+int64_t dladmm_launch_count(void) { return g_launches; }
+
+int dladmm_profile_start(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return DLADMM_OK;
+}
+
+int dladmm_profile_stop(double* ms_by_kind, int64_t* launches_by_kind) {
+  g_prof_on = false;
+  if (ms_by_kind) for (int i = 0; i < DLADMM_KIND_COUNT; ++i) ms_by_kind[i] = 0.0;
+  if (launches_by_kind) for (int i = 0; i < DLADMM_KIND_COUNT; ++i) launches_by_kind[i] = 0;
+  int rc = DLADMM_OK;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess) { set_error("profile event failed: %s", cudaGetErrorString(e)); rc = DLADMM_ERR_CUDA; }
+    if (r.kind >= 0 && r.kind < DLADMM_KIND_COUNT) {
+      if (ms_by_kind) ms_by_kind[r.kind] += ms;
+      if (launches_by_kind) launches_by_kind[r.kind] += 1;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return rc;
+}
 
 int dladmm_query(int device, dladmm_caps* caps) {
   if (!caps) { set_error("caps is NULL"); return DLADMM_ERR_INVALID; }
@@ -441,7 +495,7 @@ int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* str
   if (p->B == 0) return DLADMM_OK;
   i64 zs = (i64)p->d * p->B, ms = (i64)p->m * p->B;
   int bx = (int)std::min<i64>((zs + 255) / 256, 592);
-  objective_kernel<<<dim3(bx, p->K), 256, 0, st>>>(p->Z, p->E, p->T, zs, ms, alpha, out);
+  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st); objective_kernel<<<dim3(bx, p->K), 256, 0, st>>>(p->Z, p->E, p->T, zs, ms, alpha, out); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }

@@ -129,9 +129,9 @@ int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream) {
   const int m = g->m, d = g->d;
   if (g->generate_A) {
     i64 n = (i64)m * d;
-    gen_A_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(g->A, n, g->seed);
+    { LaunchScope ls(DLADMM_KIND_GEN, st); gen_A_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(g->A, n, g->seed); }
     DL_CUDA(cudaGetLastError());
-    normalize_cols_kernel<<<(d + 7) / 8, 256, 0, st>>>(g->A, m, d);
+    { LaunchScope ls(DLADMM_KIND_GEN, st); normalize_cols_kernel<<<(d + 7) / 8, 256, 0, st>>>(g->A, m, d); }
     DL_CUDA(cudaGetLastError());
   }
   if (g->B == 0) return DLADMM_OK;
@@ -141,9 +141,11 @@ int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream) {
     return DLADMM_ERR_WORKSPACE;
   }
   const i64 quads = (g->B + 3) / 4;
-  gen_field_kernel<<<(unsigned)((quads * d + 255) / 256), 256, 0, st>>>(g->Zs, d, g->B, g->col_offset, g->seed, STREAM_Z,
-                                                                        g->p, g->mu, g->sigma, 0);
+  { LaunchScope ls(DLADMM_KIND_GEN, st);
+    gen_field_kernel<<<(unsigned)((quads * d + 255) / 256), 256, 0, st>>>(g->Zs, d, g->B, g->col_offset, g->seed, STREAM_Z,
+                                                                          g->p, g->mu, g->sigma, 0); }
   DL_CUDA(cudaGetLastError());
+  LaunchScope lsE(DLADMM_KIND_GEN, st);
   if (g->dense_noise)
     gen_field_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(g->Es, m, g->B, g->col_offset, g->seed, STREAM_E,
                                                                           1.f, 0.f, g->sigma_e, 1);
@@ -156,12 +158,13 @@ int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream) {
   PrepJobs jobs; jobs.n = 1;
   jobs.j[0].src = g->A; jobs.j[0].dst_n = Ap; jobs.j[0].dst_t = nullptr;
   dim3 pg((dp + 31) / 32, (m + 31) / 32, 1);
-  prep_weights_kernel<<<pg, 256, 0, st>>>(jobs, m, d, dp, 0);
+  { LaunchScope ls(DLADMM_KIND_PREP, st); prep_weights_kernel<<<pg, 256, 0, st>>>(jobs, m, d, dp, 0); }
   DL_CUDA(cudaGetLastError());
   BPlain bl{g->Zs, g->B};
   EpiAddE epi{g->Es, g->X, g->B};
   dim3 grid((unsigned)((g->B + SG_BN - 1) / SG_BN), (unsigned)((m + SG_BM - 1) / SG_BM));
-  simt_gemm_kernel<BPlain, EpiAddE><<<grid, SG_THREADS, 0, st>>>(m, g->B, d, Ap, dp, bl, epi, nullptr, 0, 0);
+  { LaunchScope ls(DLADMM_KIND_GEN, st);
+    simt_gemm_kernel<BPlain, EpiAddE><<<grid, SG_THREADS, 0, st>>>(m, g->B, d, Ap, dp, bl, epi, nullptr, 0, 0); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }

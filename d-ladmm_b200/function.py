@@ -1,0 +1,179 @@
+"""autograd.Function over the C ABI: the K-layer unrolled forward and its hand-written backward.
+
+Replaces the ATen op chain + autograd graph the reference builds per call
+(main_syn_l1l1_scalar.py:80-127 and `total_loss.backward()` at :301) with two library calls.
+PyTorch here is plumbing only: it owns device memory and the stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+# slot order of per-layer broadcast parameters in dladmm_layer
+_SLOTS = ("beta1", "beta2", "beta3", "ss1", "ss2", "ss2_2", "theta1", "theta2")
+
+
+class LayerSpec(object):
+    """Static description of one call: family, sizes, and where each reference parameter sits in the
+    flat tensor list handed to autograd.  `slots[k][slot]` is an index into that list or None."""
+
+    def __init__(self, family, m, d, K, precision, slots, weights, fixed=None):
+        self.family = family
+        self.m, self.d, self.K = m, d, K
+        self.precision = precision
+        self.slots = slots          # list (K) of dict slot -> param index
+        self.weights = weights      # list (K) of param index of fc weight
+        self.fixed = fixed or {}    # slot -> non-learnable 0-dim tensor (lena thresholds)
+
+
+def _require_cuda_f32(name, t):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: d-ladmm_b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+
+
+def _bparam(t, grad):
+    bp = _lib.BParam()
+    if t is None:
+        return bp
+    bp.ptr = t.data_ptr()
+    bp.grad = grad.data_ptr() if grad is not None else None
+    if t.numel() == 1:
+        bp.row_stride, bp.col_period = 0, 0
+    elif t.dim() == 2 and t.shape[1] == 1:
+        bp.row_stride, bp.col_period = 1, 0
+    elif t.dim() == 2:
+        bp.row_stride, bp.col_period = t.shape[1], t.shape[1]
+    else:
+        raise RuntimeError("unsupported parameter shape %s" % (tuple(t.shape),))
+    return bp
+
+
+def _build_layers(spec, params, grads):
+    arr = (_lib.Layer * spec.K)()
+    for k in range(spec.K):
+        lay = arr[k]
+        for slot in _SLOTS:
+            idx = spec.slots[k].get(slot)
+            if idx is not None:
+                t = params[idx]
+                g = grads[idx] if grads is not None else None
+            else:
+                t, g = spec.fixed.get(slot), None
+            setattr(lay, slot, _bparam(t, g))
+        wi = spec.weights[k]
+        lay.W = params[wi].data_ptr()
+        lay.gW = grads[wi].data_ptr() if (grads is not None and grads[wi] is not None) else None
+    return arr
+
+
+def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, for_backward):
+    lib = _lib.load()
+    p = _lib.Problem()
+    p.abi_version = _lib.ABI_VERSION
+    p.family = spec.family
+    p.precision = spec.precision
+    p.m, p.d, p.K = spec.m, spec.d, spec.K
+    p.B = X.shape[1]
+    p.last_only = 1 if last_only else 0
+    p.A, p.X, p.Z0, p.E0, p.L0 = A.data_ptr(), X.data_ptr(), Z0.data_ptr(), E0.data_ptr(), L0.data_ptr()
+    p.layers = C.cast(layers, C.POINTER(_lib.Layer))
+    p.Z, p.E, p.L, p.T = Z.data_ptr(), E.data_ptr(), L.data_ptr(), T.data_ptr()
+    p.maskZ = maskZ.data_ptr() if maskZ is not None else None
+    p.maskE = maskE.data_ptr() if maskE is not None else None
+    nbytes = lib.dladmm_workspace_bytes(C.byref(p), 1 if for_backward else 0)
+    ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=X.device)
+    p.workspace = ws.data_ptr()
+    p.workspace_bytes = nbytes
+    return p, ws
+
+
+def _check_inputs(spec, A, X, Z0, E0, L0, params):
+    for name, t in (("A", A), ("x", X), ("Z0", Z0), ("E0", E0), ("L0", L0)):
+        _require_cuda_f32(name, t)
+    for i, t in enumerate(params):
+        _require_cuda_f32("parameter %d" % i, t)
+    m, d = spec.m, spec.d
+    if tuple(A.shape) != (m, d):
+        raise RuntimeError("A must be (%d,%d), got %s" % (m, d, tuple(A.shape)))
+    if X.dim() != 2 or X.shape[0] != m:
+        raise RuntimeError("x must be (m=%d, B), got %s" % (m, tuple(X.shape)))
+    B = X.shape[1]
+    if tuple(Z0.shape) != (d, B) or tuple(E0.shape) != (m, B) or tuple(L0.shape) != (m, B):
+        raise RuntimeError("batch of x (%d) must match Z0/E0/L0 (%s, %s, %s)" %
+                           (B, tuple(Z0.shape), tuple(E0.shape), tuple(L0.shape)))
+
+
+def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False):
+    """Launch the K-layer forward.  Returns stacked (Z, E, L, T, maskZ, maskE)."""
+    lib = _lib.load()
+    _check_inputs(spec, A, X, Z0, E0, L0, params)
+    X = X.contiguous()
+    A, Z0, E0, L0 = A.contiguous(), Z0.contiguous(), E0.contiguous(), L0.contiguous()
+    params = [t.contiguous() for t in params]
+    m, d, K, B = spec.m, spec.d, spec.K, X.shape[1]
+    dev = X.device
+    depth = 2 if last_only else K
+    Z = torch.empty((depth, d, B), dtype=torch.float32, device=dev)
+    E = torch.empty((depth, m, B), dtype=torch.float32, device=dev)
+    L = torch.empty((depth, m, B), dtype=torch.float32, device=dev)
+    T = torch.empty((2 if last_only else K + 1, m, B), dtype=torch.float32, device=dev)
+    maskZ = maskE = None
+    if want_masks:
+        maskZ = torch.empty((K, d, B), dtype=torch.uint8, device=dev)
+        if spec.family != _lib.FAMILY_C:
+            maskE = torch.empty((K, m, B), dtype=torch.uint8, device=dev)
+    layers = _build_layers(spec, params, None)
+    with torch.cuda.device(dev):
+        p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, False)
+        _lib.check(lib.dladmm_forward(C.byref(p), torch.cuda.current_stream(dev).cuda_stream))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    return Z, E, L, T, maskZ, maskE
+
+
+class UnrolledLADMM(torch.autograd.Function):
+    """forward(spec, A, X, Z0, E0, L0, *params) -> (Z, E, L, T) stacks; gradients flow to `params` only
+    (A, Z0, E0, L0 are plain tensors in the reference, main_syn_l1l1_scalar.py:40-44)."""
+
+    @staticmethod
+    def forward(ctx, spec, A, X, Z0, E0, L0, *params):
+        Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True)
+        ctx.spec = spec
+        ctx.nparams = len(params)
+        ctx.has_maskE = maskE is not None
+        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ] + ([maskE] if maskE is not None else []) + list(params)
+        ctx.save_for_backward(*saved)
+        ctx.set_materialize_grads(False)
+        return Z, E, L, T
+
+    @staticmethod
+    def backward(ctx, gZ, gE, gL, gT):
+        lib = _lib.load()
+        spec = ctx.spec
+        saved = ctx.saved_tensors
+        A, X, Z0, E0, L0, Z, E, L, T, maskZ = saved[:10]
+        off = 10
+        maskE = None
+        if ctx.has_maskE:
+            maskE = saved[10]
+            off = 11
+        params = [t.contiguous() for t in saved[off:]]
+        needs = ctx.needs_input_grad[6:]
+        grads = [torch.zeros_like(t) if needs[i] else None for i, t in enumerate(params)]
+        cot = _lib.Cotangents()
+        keep = []
+        for name, g in (("gZ", gZ), ("gE", gE), ("gL", gL), ("gT", gT)):
+            if g is not None:
+                g = g.contiguous()
+                _require_cuda_f32(name, g)
+                keep.append(g)
+                setattr(cot, name, g.data_ptr())
+        layers = _build_layers(spec, params, grads)
+        dev = X.device
+        with torch.cuda.device(dev):
+            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True)
+            _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
+            ws.record_stream(torch.cuda.current_stream(dev))
+        return (None, None, None, None, None, None) + tuple(grads)

@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's ``DLADMMNet`` nn.Module for every in-scope variant.
+
+Same constructor arguments, parameter names, shapes and registration order (so ``state_dict`` /
+``load_state_dict`` interchange with the reference), same ``forward(x)`` return structure, same
+``name()``.  The arithmetic runs in libdladmm.so (hand-written sm_100a CUDA); there is no CPU or
+PyTorch-eager fallback -- calling ``forward`` without the library or without a CUDA tensor raises.
+
+    variant   reference class                                   forward returns
+    scalar    main_syn_l1l1_scalar.py:34-131                    Z, E, L, T
+    full      main_syn_l1l1_full.py:16-110                      Z, E, L
+    tied      main_syn_l1l1_scalar_tied.py:34-134               Z, E, L, T
+    lasso     main_syn_lasso_scalar.py:17-118                   Z, E, L, T
+    lena      main_lena.py:16-102                               Z, E, L
+    ltheta    main_syn_l1l1_ltheta.py:16-108                    Z, E, L
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .function import LayerSpec, UnrolledLADMM, run_forward
+
+_FAMILY = {"lena": _lib.FAMILY_A, "ltheta": _lib.FAMILY_A, "scalar": _lib.FAMILY_B, "full": _lib.FAMILY_B,
+           "tied": _lib.FAMILY_B, "lasso": _lib.FAMILY_C}
+_RETURNS_T = {"lena": False, "ltheta": False, "scalar": True, "full": False, "tied": True, "lasso": True}
+_NAME = {"scalar": "DLADMMNet_scalar", "tied": "DLADMMNet_scalar_tied"}
+
+# reference parameter name -> slot of dladmm_layer
+_SLOT_OF = {
+    "A": {"beta1": "beta1", "beta2": "beta2", "active_para": "theta1", "active_para1": "theta2"},
+    "B": {"beta1": "beta1", "beta2": "beta2", "beta3": "beta3", "ss1": "ss1", "ss2": "ss2",
+          "active_para": "theta1", "active_para1": "theta2"},
+    "C": {"beta1": "beta1", "beta3": "beta3", "ss2_1": "ss2", "ss2_2": "ss2_2", "active_para": "theta1"},
+}
+_FAMILY_KEY = {_lib.FAMILY_A: "A", _lib.FAMILY_B: "B", _lib.FAMILY_C: "C"}
+
+
+def default_precision():
+    return os.environ.get("DLADMM_PRECISION", "fp32")
+
+
+def _param_table(variant, m, d, bs):
+    """(name, shape, init value) in the reference's registration order."""
+    one = lambda *s: (s if s else (1, 1))
+    if variant == "lena":        # main_lena.py:30-37
+        return [("beta1", (m, bs), 1.0), ("beta2", (m, bs), 1.0)]
+    if variant == "ltheta":      # main_syn_l1l1_ltheta.py:30-43
+        return [("beta1", (m, 1), 1.0), ("beta2", (m, 1), 1.0), ("active_para", (d, 1), 0.025),
+                ("active_para1", (m, 1), 0.06)]
+    if variant == "scalar":      # main_syn_l1l1_scalar.py:50-65
+        return [("beta1", one(), 1.0), ("beta2", one(), 1.0), ("beta3", one(), 1.0), ("ss2", one(), 1.0),
+                ("active_para", one(), 0.2), ("active_para1", one(), 0.8)]
+    if variant == "full":        # main_syn_l1l1_full.py:29-44
+        return [("beta1", (m, 1), 1.0), ("beta2", (m, 1), 1.0), ("beta3", (m, 1), 1.0), ("ss2", (m, 1), 1.0),
+                ("active_para", (d, 1), 0.2), ("active_para1", (m, 1), 0.8)]
+    if variant == "tied":        # main_syn_l1l1_scalar_tied.py:50-67
+        return [("beta1", one(), 1.0), ("beta2", one(), 1.0), ("beta3", one(), 1.0), ("ss1", one(), 1.0),
+                ("ss2", one(), 1.0), ("active_para", one(), 1e-4), ("active_para1", one(), 1e-2)]
+    if variant == "lasso":       # main_syn_lasso_scalar.py:33-50
+        return [("beta1", one(), 1.0), ("beta3", one(), 1.0), ("ss2_1", one(), 0.5), ("ss2_2", one(), 0.5),
+                ("active_para", one(), 0.2)]
+    raise ValueError("unknown variant %r" % (variant,))
+
+
+class DLADMMNet(nn.Module):
+    """Drop-in for the reference ``DLADMMNet(m, n, d, batch_size, A, Z0, E0, L0, layers)``.
+
+    ``variant`` selects which of the reference's re-declared classes is mirrored (default ``scalar``);
+    the per-variant subclasses below fix it so a script can swap its inline class for an import.
+    ``precision``: "fp32" (CUDA-core FFMA), "tf32x3" / "tf32" (tcgen05).
+    """
+    variant = "scalar"
+
+    def __init__(self, m, n, d, batch_size, A, Z0, E0, L0, layers, variant=None, precision=None, device=None):
+        super(DLADMMNet, self).__init__()
+        if variant is not None:
+            self.variant = variant
+        if self.variant not in _FAMILY:
+            raise ValueError("unknown variant %r" % (self.variant,))
+        self.m, self.n, self.d = m, n, d
+        self.batch_size = batch_size
+        self.layers = layers
+        self.precision = precision or default_precision()
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        if device is None:
+            # the reference calls .cuda() unconditionally (main_syn_l1l1_scalar.py:40-44); on a box
+            # without a GPU the module can still be built (state_dict work) but forward() raises.
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self._device = torch.device(device)
+        # plain attributes, not buffers: absent from state_dict exactly like the reference
+        self.A = A.detach().to(self._device, torch.float32)
+        self.At = self.A.t()
+        self.Z0 = Z0.detach().to(self._device, torch.float32)
+        self.E0 = E0.detach().to(self._device, torch.float32)
+        self.L0 = L0.detach().to(self._device, torch.float32)
+        self._lipschitz = None
+
+        table = _param_table(self.variant, m, d, batch_size)
+        for name, _, _ in table:
+            setattr(self, name, nn.ParameterList())
+        tied = self.variant == "tied"
+        self.fc = nn.Linear(m, d, bias=False) if tied else nn.ModuleList()
+        for k in range(layers):
+            for name, shape, val in table:
+                getattr(self, name).append(nn.Parameter(val * torch.ones(shape, dtype=torch.float32)))
+            if not tied:
+                self.fc.append(nn.Linear(m, d, bias=False))
+        if self.variant == "lena":   # fixed, non-learnable thresholds (main_lena.py:40-41)
+            self.active_para = torch.tensor(0.025, dtype=torch.float32, device=self._device)
+            self.active_para1 = torch.tensor(0.06, dtype=torch.float32, device=self._device)
+        # W init: A^T + 1e-3*randn, times 0.4 outside family A (main_lena.py:49, main_syn_l1l1_scalar.py:72)
+        scale = 1.0 if _FAMILY[self.variant] == _lib.FAMILY_A else 0.4
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
+                At = self.A.t()
+                mod.weight = nn.Parameter((At + 1e-3 * torch.randn_like(At)) * scale)
+        self.to(self._device)
+
+    # ---- reference surface ---------------------------------------------------------------------
+    def name(self):
+        return _NAME.get(self.variant, "DLADMMNet")
+
+    def self_active(self, x, thershold):
+        """main_syn_l1l1_scalar.py:76-77 (kept for scripts that call it on returned tensors)."""
+        return torch.relu(x - thershold) - torch.relu(-1.0 * x - thershold)
+
+    @property
+    def L(self):
+        """||A^T A||_2 as a (1,1) tensor (main_syn_l1l1_scalar.py:47-48), computed lazily."""
+        if self._lipschitz is None:
+            A64 = self.A.detach().double().cpu()
+            val = torch.linalg.matrix_norm(A64.t() @ A64, ord=2).item()
+            self._lipschitz = (val * torch.ones(1, 1)).float().to(self.A.device)
+        return self._lipschitz
+
+    def _apply(self, fn, *args, **kwargs):
+        # keep the plain-tensor attributes with the parameters when the user calls .cuda()/.to()
+        out = super(DLADMMNet, self)._apply(fn, *args, **kwargs)
+        for attr in ("A", "Z0", "E0", "L0"):
+            t = getattr(self, attr, None)
+            if isinstance(t, torch.Tensor):
+                setattr(self, attr, fn(t))
+        if isinstance(getattr(self, "A", None), torch.Tensor):
+            self.At = self.A.t()
+            if self.variant == "lena":
+                self.active_para = fn(self.active_para)
+                self.active_para1 = fn(self.active_para1)
+        self._lipschitz = None
+        return out
+
+    # ---- call description for the library ---------------------------------------------------------
+    def _spec_and_params(self):
+        fam = _FAMILY[self.variant]
+        names = _SLOT_OF[_FAMILY_KEY[fam]]
+        params, slots, weights = [], [], []
+        table = _param_table(self.variant, self.m, self.d, self.batch_size)
+        tied = self.variant == "tied"
+        if tied:
+            params.append(self.fc.weight)
+        for k in range(self.layers):
+            s = {}
+            for name, _, _ in table:
+                s[names[name]] = len(params)
+                params.append(getattr(self, name)[k])
+            slots.append(s)
+            if tied:
+                weights.append(0)
+            else:
+                weights.append(len(params))
+                params.append(self.fc[k].weight)
+        fixed = {}
+        if self.variant == "lena":
+            fixed = {"theta1": self.active_para, "theta2": self.active_para1}
+        spec = LayerSpec(fam, self.m, self.d, self.layers, _lib.PRECISIONS[self.precision], slots, weights, fixed)
+        return spec, params
+
+    def forward(self, x, last_only=False):
+        """x: (m, B) float32 CUDA, B equal to the batch of Z0/E0/L0.  Returns lists (Z, E, L[, T]) of the
+        per-layer iterates like the reference (a10).  ``last_only=True`` (inference, opt-in) keeps only
+        the final iterate in each list and never materialises the other K-1."""
+        if not x.is_cuda:
+            raise RuntimeError("DLADMMNet.forward needs a CUDA tensor: d-ladmm_b200 has no CPU path")
+        spec, params = self._spec_and_params()
+        K = self.layers
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if last_only:
+            if train:
+                raise RuntimeError("last_only=True is inference-only; wrap the call in torch.no_grad()")
+            Z, E, L, T, _, _ = run_forward(spec, self.A, x, self.Z0, self.E0, self.L0,
+                                           [p.detach() for p in params], want_masks=False, last_only=True)
+            Zl, El, Ll, Tl = [Z[(K - 1) % 2]], [E[(K - 1) % 2]], [L[(K - 1) % 2]], [T[K % 2]]
+        else:
+            if train:
+                Z, E, L, T = UnrolledLADMM.apply(spec, self.A, x, self.Z0, self.E0, self.L0, *params)
+            else:
+                Z, E, L, T, _, _ = run_forward(spec, self.A, x, self.Z0, self.E0, self.L0,
+                                               [p.detach() for p in params], want_masks=False)
+            Zl, El, Ll, Tl = list(Z.unbind(0)), list(E.unbind(0)), list(L.unbind(0)), list(T.unbind(0))
+        if _RETURNS_T[self.variant]:
+            return Zl, El, Ll, Tl
+        return Zl, El, Ll
+
+
+class DLADMMNetScalar(DLADMMNet):
+    variant = "scalar"
+
+
+class DLADMMNetFull(DLADMMNet):
+    variant = "full"
+
+
+class DLADMMNetTied(DLADMMNet):
+    variant = "tied"
+
+
+class DLADMMNetLasso(DLADMMNet):
+    variant = "lasso"
+
+
+class DLADMMNetLena(DLADMMNet):
+    variant = "lena"
+
+
+class DLADMMNetLtheta(DLADMMNet):
+    variant = "ltheta"
+
+
+VARIANT_CLASSES = {"scalar": DLADMMNetScalar, "full": DLADMMNetFull, "tied": DLADMMNetTied,
+                   "lasso": DLADMMNetLasso, "lena": DLADMMNetLena, "ltheta": DLADMMNetLtheta}

@@ -169,6 +169,31 @@ DLADMM_API int dladmm_objective(const dladmm_problem* p, float alpha, float* out
 
 DLADMM_API int dladmm_query(int device, dladmm_caps* caps);
 
+/* Measurement hooks (bench.py).  Kernel kinds for the per-kind timers: */
+typedef enum dladmm_kernel_kind {
+  DLADMM_KIND_PREP = 0,        /* weight padding / transposition */
+  DLADMM_KIND_GEMM_T0 = 1,     /* T_0 = A Z0 + E0 - X */
+  DLADMM_KIND_GEMM_Z = 2,      /* W V product + Z prox epilogue */
+  DLADMM_KIND_GEMM_ELT = 3,    /* A Z product + E/T/L epilogue */
+  DLADMM_KIND_BWD_ELEM = 4,    /* top-layer elementwise cotangent flow */
+  DLADMM_KIND_BWD_GEMM_DZ = 5, /* A^T dR + mask epilogue */
+  DLADMM_KIND_BWD_GEMM_DW = 6, /* dx1 V^T (reduction over the batch) */
+  DLADMM_KIND_BWD_GEMM_DV = 7, /* W^T dx1 + fused elementwise backward of the layer below */
+  DLADMM_KIND_BWD_REDUCE = 8,  /* second stage of parameter-gradient reductions */
+  DLADMM_KIND_GEN = 9,         /* synthetic data generator */
+  DLADMM_KIND_OBJECTIVE = 10,
+  DLADMM_KIND_COUNT = 11
+} dladmm_kernel_kind;
+
+/* Total kernels this library has launched in this process (monotonic). */
+DLADMM_API int64_t dladmm_launch_count(void);
+
+/* While profiling is on, every kernel launch is bracketed by CUDA events on its stream (a measurement
+ * pass only: the events cost a little).  dladmm_profile_stop synchronises those events and returns, per
+ * kind, the summed device time in milliseconds and the number of launches (arrays of DLADMM_KIND_COUNT). */
+DLADMM_API int dladmm_profile_start(void);
+DLADMM_API int dladmm_profile_stop(double* ms_by_kind, int64_t* launches_by_kind);
+
 DLADMM_API const char* dladmm_last_error(void);
 
 #ifdef __cplusplus

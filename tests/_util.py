@@ -1,0 +1,53 @@
+"""Shared helpers for the tests: golden fixtures, model construction, error metrics."""
+import glob
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+SMALL_GOLDEN = [n for n in GOLDEN_NAMES if "shape" not in n]
+
+
+class Golden(object):
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.variant = str(z["variant"])
+        self.K = int(z["K"])
+        self.bs = int(z["bs"])
+        self.returns_T = bool(z["returns_T"])
+        t = lambda k: torch.from_numpy(z[k].copy())
+        self.A, self.X, self.Z0, self.E0, self.L0 = t("A"), t("X"), t("Z0"), t("E0"), t("L0")
+        self.Z, self.E, self.L = t("Z"), t("E"), t("L")
+        self.T = t("T") if "T" in z.files else None
+        self.cz, self.ce, self.cl, self.ct = t("cz"), t("ce"), t("cl"), t("ct")
+        self.loss = float(z["loss"])
+        self.keys = [str(k) for k in z["keys"]]
+        self.sd = {k: t("sd/" + k) for k in self.keys}
+        self.grads = {k: t("grad/" + k) for k in self.keys}
+        self.m, self.d = self.A.shape
+
+
+def rel_l2(a, b, floor=0.0):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / max(b.norm().item(), floor, 1e-300)).item()
+
+
+def build_model(g, device, precision=None):
+    import dladmm_b200 as dl
+    cls = dl.VARIANT_CLASSES[g.variant]
+    model = cls(m=g.m, n=10000, d=g.d, batch_size=g.bs, A=g.A, Z0=g.Z0, E0=g.E0, L0=g.L0, layers=g.K,
+                precision=precision, device=device)
+    model.load_state_dict(g.sd)
+    return model
+
+
+def syn(m, d, B, seed, p=0.1, sigma=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    A = torch.randn(m, d, generator=gen)
+    A = A / A.pow(2).sum(dim=0, keepdim=True).sqrt()
+    Z = (torch.rand(d, B, generator=gen) < p).float() * torch.randn(d, B, generator=gen) * sigma
+    E = (torch.rand(m, B, generator=gen) < p).float() * torch.randn(m, B, generator=gen) * sigma
+    return A, A.mm(Z) + E

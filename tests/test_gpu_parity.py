@@ -1,0 +1,145 @@
+"""GPU parity: the CUDA path (through the nn.Module -> autograd.Function -> C ABI) against the committed
+reference outputs/gradients and against the fp64 oracle on identical inputs and weights.
+
+Tolerances (floating point; stated per the north star):
+  fp32 (FFMA)  : per-layer relative L2 error vs the fp64 oracle <= 5e-6 (the reference's own fp32-vs-fp64
+                 floor is 2.5e-7..6e-7, up to 3.5e-6 on T)
+  tf32x3       : same bound (3-pass split keeps ~fp32 products)
+  tf32         : <= 5e-3 (stated-tolerance option)
+  support masks: equal except where both values are inside a 1e-5 guard band around the threshold.
+  gradients    : relative L2 error <= 2e-4 (fp32 reductions over the batch, atomics in dW).
+"""
+import os
+
+import pytest
+import torch
+
+import dladmm_oracle as orc
+import dladmm_b200 as dl
+from _util import GOLDEN_NAMES, SMALL_GOLDEN, Golden, build_model, rel_l2, syn
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32"] + (["tf32x3", "tf32"] if os.environ.get("DLADMM_TEST_UMMA", "1") == "1" else [])
+FWD_TOL = {"fp32": 5e-6, "tf32x3": 5e-6, "tf32": 5e-3}
+GRAD_TOL = {"fp32": 2e-4, "tf32x3": 2e-4, "tf32": 3e-2}
+GUARD = {"fp32": 1e-5, "tf32x3": 1e-5, "tf32": 1e-2}
+
+
+def _skip_if_unavailable(precision):
+    if precision != "fp32" and not dl.query_device(0)["has_tcgen05"]:
+        pytest.skip("tcgen05 kernels not in this build")
+
+
+def _oracle64(g):
+    d64 = lambda t: t.double()
+    sd = {k: d64(v) for k, v in g.sd.items()}
+    return orc.forward(g.variant, sd, d64(g.A), d64(g.X), d64(g.Z0), d64(g.E0), d64(g.L0), g.K)
+
+
+def _check_support(a, ref, guard):
+    """support masks agree except inside the guard band around the threshold"""
+    mism = (a != 0) != (ref != 0)
+    if mism.any():
+        worst = torch.maximum(a.abs().double(), ref.abs().double())[mism].max().item()
+        assert worst < guard, "support mismatch outside guard band: %g" % worst
+    return int(mism.sum())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_forward_matches_reference_and_oracle(name, precision):
+    _skip_if_unavailable(precision)
+    g = Golden(name)
+    model = build_model(g, "cuda", precision)
+    with torch.no_grad():
+        out = model(g.X.cuda())
+    assert len(out) == (4 if g.returns_T else 3)
+    Z, E, L = out[0], out[1], out[2]
+    assert len(Z) == len(E) == len(L) == g.K
+    if g.returns_T:
+        assert len(out[3]) == g.K + 1
+    Zo, Eo, Lo, To = _oracle64(g)
+    tol = FWD_TOL[precision]
+    xn = g.X.norm().item()
+    for k in range(g.K):
+        z, e, l = Z[k].cpu(), E[k].cpu(), L[k].cpu()
+        # vs the fp64 oracle
+        assert rel_l2(z, Zo[k], floor=1e-3) < tol, (name, k, "Z", rel_l2(z, Zo[k]))
+        assert rel_l2(e, Eo[k], floor=1e-3 * xn) < tol, (name, k, "E")
+        assert rel_l2(l, Lo[k], floor=1e-3 * xn) < tol, (name, k, "L")
+        # vs the reference's own fp32 outputs (fixture)
+        assert rel_l2(z, g.Z[k], floor=1e-3) < 2 * tol and rel_l2(e, g.E[k], floor=1e-3 * xn) < 2 * tol
+        _check_support(z, Zo[k], GUARD[precision])
+        if g.variant != "lasso":
+            _check_support(e, Eo[k], GUARD[precision])
+        if g.returns_T:
+            assert rel_l2(out[3][k + 1].cpu(), To[k + 1], floor=1e-2 * xn) < 10 * tol
+    if g.returns_T:
+        assert rel_l2(out[3][0].cpu(), To[0], floor=1e-2 * xn) < 10 * tol
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_backward_matches_reference_gradients(name, precision):
+    _skip_if_unavailable(precision)
+    g = Golden(name)
+    model = build_model(g, "cuda", precision)
+    out = model(g.X.cuda())
+    Z, E, L = out[0], out[1], out[2]
+    cz, ce, cl, ct = g.cz.cuda(), g.ce.cuda(), g.cl.cuda(), g.ct.cuda()
+    loss = sum((Z[k] * cz[k]).sum() + (E[k] * ce[k]).sum() + (L[k] * cl[k]).sum() for k in range(g.K))
+    if g.returns_T:
+        loss = loss + sum((out[3][k] * ct[k]).sum() for k in range(g.K + 1))
+    loss.backward()
+    assert abs(loss.item() - g.loss) <= 2e-4 * max(1.0, abs(g.loss))
+    tol = GRAD_TOL[precision]
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        err = rel_l2(p.grad.cpu(), g.grads[n], floor=1e-5)
+        assert err < tol, (name, n, err)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("variant", ["scalar", "full", "lasso"])
+def test_training_loss_gradients_match_oracle_autograd(variant, precision):
+    """The reference's actual training loss (main_syn_l1l1_scalar.py:289-299): only Z_k gets a cotangent."""
+    _skip_if_unavailable(precision)
+    m, d, B, K = 60, 100, 48, 5
+    A, X = syn(m, d, B, seed=21)
+    gen = torch.Generator().manual_seed(4)
+    Z0 = torch.rand(d, B, generator=gen) / d
+    E0 = torch.zeros(m, B); L0 = torch.zeros(m, B)
+    model = dl.VARIANT_CLASSES[variant](m, 1, d, B, A, Z0, E0, L0, K, precision=precision)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    Ad, Xd = A.cuda(), X.cuda()
+    out = model(Xd)
+    loss = orc.l1l1_loss(out[0], out[1], out[2], None, Ad, Xd)
+    loss.backward()
+    d64 = lambda t: t.double()
+    sd64 = {k: d64(v) for k, v in sd.items()}
+    lref, gref = orc.autograd_grads(variant, sd64, d64(A), d64(X), d64(Z0), d64(E0), d64(L0), K,
+                                    lambda Z, E, L, T: orc.l1l1_loss(Z, E, L, T, d64(A), d64(X)))
+    assert abs(loss.item() - lref.item()) < 1e-4 * abs(lref.item())
+    for n, p in model.named_parameters():
+        assert rel_l2(p.grad.cpu(), gref[n], floor=1e-5) < 5 * GRAD_TOL[precision], n
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_learned_forward_equals_classical_ladmm_on_gpu(precision):
+    """Known-answer test through the CUDA path at the config-1 shape."""
+    _skip_if_unavailable(precision)
+    m, d, B, K, alpha = 250, 500, 64, 15, 0.01
+    A, X = syn(m, d, B, seed=8)
+    Z0 = torch.zeros(d, B); E0 = torch.zeros(m, B); L0 = torch.zeros(m, B)
+    sd, ss1 = orc.km_state_dict("scalar", A, K, alpha)
+    model = dl.DLADMMNetScalar(m, 1, d, B, A, Z0, E0, L0, K, precision=precision)
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        Z, E, L, T = model(X.cuda())
+    d64 = lambda t: t.double()
+    Zk, Ek, Lk, Tk = orc.km_iterations(d64(A), d64(X), d64(Z0), d64(E0), d64(L0), K, alpha, 1.0, ss1, 0.3)
+    tol = 20 * FWD_TOL[precision]
+    for k in range(K):
+        assert (Z[k].cpu().double() - Zk[k]).abs().max() < tol * max(1.0, Zk[k].abs().max().item())
+        assert (E[k].cpu().double() - Ek[k]).abs().max() < tol * max(1.0, Ek[k].abs().max().item())

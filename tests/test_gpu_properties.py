@@ -1,0 +1,185 @@
+"""GPU: size-independent properties at BASELINE sizes, edge cases (empty / ragged batches), last_only mode,
+the on-device generator's statistics, the fused objective, and the no-fallback rule."""
+import math
+
+import pytest
+import torch
+
+import dladmm_oracle as orc
+import dladmm_b200 as dl
+from _util import Golden, build_model, rel_l2, syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(variant, m, d, B, K, seed=0, precision=None, Z0=None):
+    torch.manual_seed(seed)
+    data = dl.gen_syn_data(B, m=m, d=d, seed=1126 + seed)
+    if Z0 is None:
+        Z0 = torch.rand(d, B, device="cuda") / d
+    E0 = torch.zeros(m, B, device="cuda"); L0 = torch.zeros(m, B, device="cuda")
+    model = dl.VARIANT_CLASSES[variant](m, 1, d, B, data.A, Z0, E0, L0, K, precision=precision)
+    return model, data
+
+
+@pytest.mark.parametrize("variant", ["scalar", "full", "tied", "lasso", "ltheta"])
+def test_residual_identity_at_config1_size(variant):
+    """X - A Z_k == E_k - T_{k+1} for every layer at m=250, d=500, K=15, B=16384."""
+    model, data = _model(variant, 250, 500, 16384, 15)
+    with torch.no_grad():
+        out = model(data.X)
+        Z, E = out[0], out[1]
+        # recompute T from L for variants that do not return it: L_k = L_{k-1} + bL*T_{k+1}
+        for k in (0, 7, 14):
+            R = data.A @ Z[k]
+            if len(out) == 4:
+                T = out[3]
+                lhs = data.X - R
+                rhs = E[k] - T[k + 1]
+                assert (lhs - rhs).abs().max().item() < 5e-5
+            assert torch.isfinite(Z[k]).all() and torch.isfinite(E[k]).all()
+
+
+def test_columns_are_independent_and_shards_tile_the_batch():
+    """Running column shards separately reproduces the full-batch run bit for bit (8(e): no collective on
+    the data path), for a ragged split."""
+    m, d, B, K = 250, 500, 1000, 6
+    model, data = _model("scalar", m, d, B, K)
+    with torch.no_grad():
+        Zf, Ef, Lf, Tf = model(data.X)
+    for world in (2, 3):
+        for r in range(world):
+            a, b = dl.column_shard(B, r, world)
+            sub = dl.DLADMMNetScalar(m, 1, d, b - a, data.A, model.Z0[:, a:b].contiguous(),
+                                     model.E0[:, a:b].contiguous(), model.L0[:, a:b].contiguous(), K)
+            sub.load_state_dict(model.state_dict())
+            with torch.no_grad():
+                Zs, Es, Ls, Ts = sub(data.X[:, a:b].contiguous())
+            assert torch.equal(Zs[-1], Zf[-1][:, a:b]) and torch.equal(Ls[-1], Lf[-1][:, a:b])
+            assert torch.equal(Ts[K], Tf[K][:, a:b])
+
+
+@pytest.mark.parametrize("B", [1, 3, 20, 25, 255, 257, 1030])
+def test_ragged_batch_sizes(B):
+    m, d, K = 250, 500, 3
+    A, X = syn(m, d, B, seed=B)
+    Z0 = torch.rand(d, B) / d; E0 = torch.zeros(m, B); L0 = torch.zeros(m, B)
+    model = dl.DLADMMNetScalar(m, 1, d, B, A, Z0, E0, L0, K)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        Z, E, L, T = model(X.cuda())
+    Zo, Eo, Lo, To = orc.forward("scalar", sd, A, X, Z0, E0, L0, K)
+    for k in range(K):
+        assert rel_l2(Z[k].cpu(), Zo[k], floor=1e-3) < 1e-5 and rel_l2(L[k].cpu(), Lo[k], floor=1e-2) < 1e-5
+
+
+def test_empty_batch():
+    m, d, K = 24, 40, 2
+    A = torch.randn(m, d)
+    z = lambda r: torch.zeros(r, 0)
+    model = dl.DLADMMNetScalar(m, 1, d, 0, A, z(d), z(m), z(m), K)
+    with torch.no_grad():
+        Z, E, L, T = model(torch.zeros(m, 0, device="cuda"))
+    assert len(Z) == K and Z[0].shape == (d, 0) and len(T) == K + 1
+
+
+def test_last_only_equals_full_run():
+    model, data = _model("scalar", 250, 500, 2048, 15)
+    with torch.no_grad():
+        Z, E, L, T = model(data.X)
+        Zl, El, Ll, Tl = model(data.X, last_only=True)
+    assert torch.equal(Zl[0], Z[-1]) and torch.equal(El[0], E[-1]) and torch.equal(Ll[0], L[-1])
+    assert torch.equal(Tl[0], T[-1])
+    with pytest.raises(RuntimeError, match="inference-only"):
+        model(data.X, last_only=True)
+
+
+def test_lena_slot_parameters_repeat_over_larger_batches():
+    """(m x bs) betas are indexed by batch slot; column c uses slot c mod bs."""
+    g = Golden("lena_small")
+    reps = 3
+    B = g.bs * reps
+    model = dl.DLADMMNetLena(g.m, 1, g.d, g.bs, g.A, g.Z0.repeat(1, reps), g.E0.repeat(1, reps),
+                             g.L0.repeat(1, reps), g.K)
+    model.load_state_dict(g.sd)
+    out = model(g.X.repeat(1, reps).cuda())
+    for k in range(g.K):
+        for r in range(reps):
+            assert rel_l2(out[0][k][:, r * g.bs:(r + 1) * g.bs].cpu(), g.Z[k], floor=1e-3) < 1e-5
+    # gradients of the per-slot parameters accumulate over the repeats
+    loss = sum((out[0][k] * g.cz[k].repeat(1, reps).cuda()).sum() + (out[1][k] * g.ce[k].repeat(1, reps).cuda()).sum()
+               + (out[2][k] * g.cl[k].repeat(1, reps).cuda()).sum() for k in range(g.K))
+    loss.backward()
+    for n, p in model.named_parameters():
+        assert rel_l2(p.grad.cpu(), reps * g.grads[n], floor=1e-5) < 3e-4, n
+
+
+def test_generator_statistics_and_shard_reproducibility():
+    """gen_syn_data.py semantics: unit-norm columns, Bernoulli(p) support, N(0, sigma) amplitudes, X = AZ+E."""
+    m, d, B, p, sigma = 250, 500, 8192, 0.1, 2.0
+    data = dl.gen_syn_data(B, m=m, d=d, p=p, sigma=sigma, seed=7)
+    A, X, Z, E = data
+    assert (A.pow(2).sum(dim=0).sqrt() - 1).abs().max().item() < 1e-5
+    # A entries before normalisation are N(0,1): after normalisation mean ~ 0, var ~ 1/m
+    assert abs(A.mean().item()) < 3e-3 and abs(A.var().item() * m - 1) < 0.05
+    for F in (Z, E):
+        n = F.numel()
+        frac = (F != 0).float().mean().item()
+        assert abs(frac - p) < 4 * math.sqrt(p * (1 - p) / n)
+        nz = F[F != 0]
+        assert abs(nz.mean().item()) < 5 * sigma / math.sqrt(nz.numel())
+        assert abs(nz.std().item() / sigma - 1) < 0.02
+        assert abs((nz.abs() < 0.6745 * sigma).float().mean().item() - 0.5) < 0.01   # Gaussian median
+    assert rel_l2(X, A @ Z + E) < 1e-5
+    # shards reproduce the global stream
+    part = dl.gen_syn_data(1000, m=m, d=d, p=p, sigma=sigma, seed=7, A=A, col_offset=3001)
+    assert torch.equal(part.Z, Z[:, 3001:4001]) and torch.equal(part.E, E[:, 3001:4001])
+    other = dl.gen_syn_data(64, m=m, d=d, p=p, sigma=sigma, seed=8, A=A)
+    assert not torch.equal(other.Z, Z[:, :64])
+    dense = dl.gen_syn_data(4096, m=m, d=d, seed=7, A=A, dense_noise_sigma=1.0 / math.sqrt(m))
+    assert (dense.E != 0).float().mean().item() > 0.999
+    assert abs(dense.E.std().item() * math.sqrt(m) - 1) < 0.02
+
+
+def test_fused_objective_matches_script_side_loop():
+    model, data = _model("scalar", 250, 500, 4096, 15)
+    alpha = 0.001
+    with torch.no_grad():
+        Z, E, L, T = model(data.X)
+        got = dl.l1l1_objective(Z, E, T, alpha)
+        exp = torch.stack([alpha * Z[k].abs().sum() + (data.X - data.A @ Z[k]).abs().sum() for k in range(15)])
+    assert rel_l2(got, exp) < 1e-4
+
+
+def test_objective_improves_with_depth_under_km_parameters():
+    m, d, B, K, alpha = 250, 500, 2048, 40, 0.01
+    data = dl.gen_syn_data(B, m=m, d=d, seed=3)
+    z = lambda r: torch.zeros(r, B, device="cuda")
+    sd, ss1 = orc.km_state_dict("scalar", data.A.cpu(), K, alpha)
+    model = dl.DLADMMNetScalar(m, 1, d, B, data.A, z(d), z(m), z(m), K)
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        Z, E, L, T = model(data.X)
+        obj = dl.l1l1_objective(Z, E, T, alpha) / B
+    assert obj[-1] < obj[10] < obj[0]
+
+
+def test_wrong_dtype_and_shape_raise():
+    g = Golden("scalar_small")
+    model = build_model(g, "cuda")
+    with pytest.raises(RuntimeError, match="float32"):
+        model(g.X.double().cuda())
+    with pytest.raises(RuntimeError, match="batch"):
+        model(g.X[:, :5].contiguous().cuda())
+
+
+def test_native_library_is_the_code_that_runs():
+    """The loaded shared object is the in-tree libdladmm.so (no torch-eager fallback exists)."""
+    g = Golden("scalar_small")
+    model = build_model(g, "cuda")
+    with torch.no_grad():
+        model(g.X.cuda())
+    maps = open("/proc/self/maps").read()
+    assert "libdladmm.so" in maps
+    caps = dl.query_device(0)
+    assert caps["supported"] == 1 and caps["cc_major"] == 10 and caps["sm_count"] >= 100
