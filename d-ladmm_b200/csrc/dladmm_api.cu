@@ -7,7 +7,6 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
-#include "umma_path.cuh"
 
 namespace dladmm {
 
@@ -367,6 +366,12 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
   return DLADMM_OK;
 }
 
+}  // namespace dladmm
+
+#include "umma_path.cuh"
+
+namespace dladmm {
+
 // ---- objective --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) objective_kernel(const float* __restrict__ Z, const float* __restrict__ E,
                                                         const float* __restrict__ T, i64 zs, i64 ms, float alpha,
@@ -455,10 +460,16 @@ int dladmm_forward(const dladmm_problem* p, void* stream) {
   int rc = validate(p, 0);
   if (rc) return rc;
   if (p->B == 0) return DLADMM_OK;
+  if (p->workspace_bytes < dladmm_workspace_bytes(p, 0)) {
+    set_error("workspace too small: need %zu bytes, got %zu", dladmm_workspace_bytes(p, 0), p->workspace_bytes);
+    return DLADMM_ERR_WORKSPACE;
+  }
   if ((rc = check_device())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w = carve(p, 0);
-  if (p->precision != DLADMM_PREC_FP32) return umma_forward(p, (char*)p->workspace + w.bytes, st);
+  // tensor-core precisions need a 16-byte pitch for TMA (B % 4 == 0); other batch sizes run the FFMA kernels,
+  // which are fp32 throughout (never less accurate than the precision asked for)
+  if (umma_eligible(p)) return umma_forward(p, (char*)p->workspace + w.bytes, st);
   if ((rc = prepare_weights(p, w, false, st))) return rc;
   switch (p->family) {
     case DLADMM_FAMILY_A: return forward_simt<DLADMM_FAMILY_A>(p, w, st);
@@ -475,7 +486,7 @@ int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* s
   if ((rc = check_device())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w = carve(p, 1);
-  if (p->precision != DLADMM_PREC_FP32) return umma_backward(p, g, (char*)p->workspace + w.bytes, st);
+  // backward products currently run on the FFMA kernels for every precision (fp32 products, fp32 accumulate)
   if ((rc = prepare_weights(p, w, true, st))) return rc;
   switch (p->family) {
     case DLADMM_FAMILY_A: return backward_simt<DLADMM_FAMILY_A>(p, g, w, st);

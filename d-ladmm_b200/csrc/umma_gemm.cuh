@@ -1,0 +1,358 @@
+// tcgen05 / TMEM / TMA matrix product with fused epilogue (sm_100a), the tensor-core arithmetic of the
+// D-LADMM layer (DLADMM_PREC_TF32X3 and DLADMM_PREC_TF32).
+//
+//   C[j, b] = sum_k  Wt[j, k] * Act[k, b]          j: feature row, b: batch column (problem instance)
+//
+// Mapping onto one tcgen05.mma (cta_group::1, kind::tf32, fp32 accumulate in TMEM):
+//   M (TMEM lanes, 128)      = batch columns        -> UMMA "A" = Act tile, MN-major (batch contiguous), TMA
+//   N (TMEM columns, <=256)  = feature rows         -> UMMA "B" = prepared weights, K-major, TMA
+//   K (8 per instruction)    = reduction index
+// so that in the epilogue the 32 lanes of a warp hold 32 consecutive batch columns of one feature row:
+// every global access of the fused epilogue is a coalesced 128-byte row segment, and per-row parameters are
+// warp-uniform.
+//
+// 3xTF32: operands are pre-split as x = big + small; three MMAs per k-step accumulate
+// big*big + big*small + small*big in the same TMEM accumulator (fp32-level products).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Persistent over (batch tile, feature tile) pairs,
+// two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace dladmm {
+namespace umma {
+
+constexpr int TILE_B = 128;      // batch columns per tile (UMMA M)
+constexpr int TILE_N = 256;      // feature rows per tile (UMMA N)
+constexpr int UMMA_K = 8;        // tf32
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr int CH = 16;            // feature rows per epilogue step (one tcgen05.ld.32x32b.x16)
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------------
+// instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): addresses/offsets in 16-byte units
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
+// MN-major 32-bit operands have exactly one legal swizzled layout: 128-byte rows whose four 32-byte chunks are
+// permuted by (row % 4) -- UMMA layout type 1 (SWIZZLE_128B_BASE32B), written by TMA with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Atom = 32 elements (MN) x 4 rows (K) = 512 bytes.  (Plain SWIZZLE_128B
+// with an MN-major tf32 operand silently multiplies by zero; measured on B200.)
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;
+constexpr uint32_t A_ATOM_BYTES = 512;
+
+// ---- kernel ----------------------------------------------------------------------------------------------
+struct GemmShape {
+  int n_feat;        // valid feature rows (epilogue bound); weights are zero padded to a multiple of TILE_N
+  int n_ntiles;      // ceil(n_feat / TILE_N)
+  int k_chunks;      // ceil(Kdim / KC)
+  i64 B;             // batch columns
+  i64 n_btiles;      // ceil(B / TILE_B)
+};
+
+template <int NPASS, int KC>
+struct SmemPlan {
+  static constexpr int NOPS = NPASS == 3 ? 2 : 1;                    // big (+ small)
+  static constexpr int A_BYTES = TILE_B * KC * 4;                    // one operand part
+  static constexpr int B_BYTES = TILE_N * KC * 4;
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+};
+
+// Epi: functor with State/In types; per CH-feature chunk of one batch column the kernel calls
+//   epi.load(in, row0, b, valid, n_feat)  (global inputs, issued before the accumulator is read) and
+//   epi.apply(state, in, row0, b, valid, acc[CH], n_feat, column_group)
+template <class Epi, int NPASS, int KC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_constant__ CUtensorMap tmA_small,
+                 const __grid_constant__ CUtensorMap tmB_big, const __grid_constant__ CUtensorMap tmB_small,
+                 GemmShape gs, Epi epi) {
+  using Plan = SmemPlan<NPASS, KC>;
+  constexpr int STAGES = Plan::STAGES;
+  constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
+  constexpr uint32_t B_SBO = 8 * KC * 4;            // 8 rows of KC floats
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * Plan::STAGE_BYTES);
+  uint64_t* full = bars;                   // [STAGES]
+  uint64_t* empty = bars + STAGES;         // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;     // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const i64 ntiles = gs.n_btiles * gs.n_ntiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_big); prefetch_tmap(&tmB_big);
+    if (NPASS == 3) { prefetch_tmap(&tmA_small); prefetch_tmap(&tmB_small); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = (int)(tile % gs.n_ntiles);
+        const i64 bt = tile / gs.n_ntiles;
+        const int b0 = (int)(bt * TILE_B);             // batch column (TMA coordinates are 32-bit)
+        const int j0 = nt * TILE_N;
+        for (int kc = 0; kc < gs.k_chunks; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * Plan::STAGE_BYTES;
+          mbar_expect_tx(&full[s], Plan::STAGE_BYTES);
+#pragma unroll
+          for (int op = 0; op < Plan::NOPS; ++op) {
+            const CUtensorMap* ma = op == 0 ? &tmA_big : &tmA_small;
+            const CUtensorMap* mb = op == 0 ? &tmB_big : &tmB_small;
+            uint8_t* a_dst = st + op * Plan::A_BYTES;
+            uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES + op * Plan::B_BYTES;
+            // activation: 4 boxes of (32 batch columns x KC rows), 128 B per row
+#pragma unroll
+            for (int g = 0; g < TILE_B / 32; ++g) tma_load_2d(a_dst + g * (KC * 128), ma, &full[s], b0 + g * 32, kc * KC);
+            // weights: one box of (KC k x 256 rows)
+            tma_load_2d(b_dst, mb, &full[s], kc * KC, j0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t aph = 0;
+      for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TILE_N;
+        for (int kc = 0; kc < gs.k_chunks; ++kc) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * Plan::STAGE_BYTES);
+          const uint32_t a_big = st, a_small = st + Plan::A_BYTES;
+          const uint32_t b_big = st + Plan::NOPS * Plan::A_BYTES, b_small = b_big + Plan::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < KC / UMMA_K; ++ks) {
+            // A (MN-major, 128B swizzle / 32B atoms): rows of 32 batch columns (128 B); one k-step = 8 rows = 2 atoms
+            // (SBO = 512 B apart); batch groups of 32 are KC*128 B apart (LBO)
+            const uint64_t da_big = make_sdesc(a_big + ks * 1024, KC * 128, A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
+            // B (K-major): rows of KC floats; 8-row groups B_SBO apart; advance 32 B per k-step inside the swizzled row
+            const uint64_t db_big = make_sdesc(b_big + ks * 32, 16, B_SBO, B_LAYOUT);
+            const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+            if (NPASS == 3) {
+              const uint64_t da_small = make_sdesc(a_small + ks * 1024, KC * 128, A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
+              const uint64_t db_small = make_sdesc(b_small + ks * 32, 16, B_SBO, B_LAYOUT);
+              umma_tf32(d_tmem, da_small, db_big, idesc, first);
+              umma_tf32(d_tmem, da_big, db_small, idesc, 1u);
+              umma_tf32(d_tmem, da_big, db_big, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da_big, db_big, idesc, first);
+            }
+          }
+          umma_commit(&empty[s]);                      // frees the smem stage when these MMAs retire
+          if (kc == gs.k_chunks - 1) umma_commit(&tfull[acc]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;                            // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t aph = 0;
+    typename Epi::State state;
+    epi.begin(state);
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nt = (int)(tile % gs.n_ntiles);
+      const i64 bt = tile / gs.n_ntiles;
+      const i64 b = bt * TILE_B + q * 32 + lane;
+      const int j0 = nt * TILE_N;
+      const bool valid = b < gs.B;
+      typename Epi::In in;
+      epi.load(in, j0, b, valid, gs.n_feat);           // global inputs of the first chunk fly while the MMAs finish
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + acc * TILE_N + ((uint32_t)(q * 32) << 16);
+      // CH rows per step: small enough that the unrolled body stays inside the instruction cache, large enough
+      // (CH loads per input array per thread) to keep HBM busy from 4 warps
+#pragma unroll 1
+      for (int c = 0; c < TILE_N / CH; ++c) {
+        const int row0 = j0 + c * CH;
+        if (row0 >= gs.n_feat) break;                  // warp-uniform
+        float v[CH];
+        tmem_ld16(t0 + c * CH, v);
+        epi.apply(state, in, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);
+        if (c + 1 < TILE_N / CH && row0 + CH < gs.n_feat) epi.load(in, row0 + CH, b, valid, gs.n_feat);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+    epi.end(state);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side: tensor maps ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D fp32 row-major matrix (rows x cols, pitch in elements); box = (box_cols x box_rows); OOB reads give zeros
+inline int make_tmap_2d(CUtensorMap* out, const float* base, i64 rows, i64 cols, i64 pitch, int box_cols, int box_rows,
+                        CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DLADMM_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld pitch=%lld box=%dx%d", (int)r, rows, cols, pitch, box_cols,
+              box_rows);
+    return DLADMM_ERR_CUDA;
+  }
+  return DLADMM_OK;
+}
+
+}  // namespace umma
+}  // namespace dladmm
