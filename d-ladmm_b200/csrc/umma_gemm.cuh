@@ -14,8 +14,8 @@
 // 3xTF32: operands are pre-split as x = big + small; three MMAs per k-step accumulate
 // big*big + big*small + small*big in the same TMEM accumulator (fp32-level products).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Persistent over (batch tile, feature tile) pairs,
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; two warps per quadrant split the feature rows).  Persistent over (batch tile, feature tile) pairs,
 // two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -27,7 +27,8 @@ namespace umma {
 constexpr int TILE_B = 128;      // batch columns per tile (UMMA M)
 constexpr int TILE_N = 256;      // feature rows per tile (UMMA N)
 constexpr int UMMA_K = 8;        // tf32
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // two per TMEM lane quadrant, each owning half of the tile's feature rows
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_WARP0 = 2;
 constexpr int CH = 16;            // feature rows per epilogue step (one tcgen05.ld.32x32b.x16)
 
@@ -193,7 +194,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
     prefetch_tmap(&tmA_big); prefetch_tmap(&tmB_big);
     if (NPASS == 3) { prefetch_tmap(&tmA_small); prefetch_tmap(&tmB_small); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -278,6 +279,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
   } else {
     // ===== epilogue warps =====
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
+    const int half = (warp - EPI_WARP0) >> 2;          // which half of the tile's feature rows
+    constexpr int ROWS_PER_WARP = TILE_N / (EPI_WARPS / 4);
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
@@ -288,20 +291,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
       const int j0 = nt * TILE_N;
       const bool valid = b < gs.B;
       typename Epi::In in;
-      epi.load(in, j0, b, valid, gs.n_feat);           // global inputs of the first chunk fly while the MMAs finish
+      const int jw = j0 + half * ROWS_PER_WARP;        // first feature row of this warp
+      epi.load(in, jw, b, valid, gs.n_feat);           // global inputs of the first chunk fly while the MMAs finish
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + acc * TILE_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t t0 = tmem_base + acc * TILE_N + half * ROWS_PER_WARP + ((uint32_t)(q * 32) << 16);
       // CH rows per step: small enough that the unrolled body stays inside the instruction cache, large enough
       // (CH loads per input array per thread) to keep HBM busy from 4 warps
 #pragma unroll 1
-      for (int c = 0; c < TILE_N / CH; ++c) {
-        const int row0 = j0 + c * CH;
+      for (int c = 0; c < ROWS_PER_WARP / CH; ++c) {
+        const int row0 = jw + c * CH;
         if (row0 >= gs.n_feat) break;                  // warp-uniform
         float v[CH];
         tmem_ld16(t0 + c * CH, v);
         epi.apply(state, in, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);
-        if (c + 1 < TILE_N / CH && row0 + CH < gs.n_feat) epi.load(in, row0 + CH, b, valid, gs.n_feat);
+        if (c + 1 < ROWS_PER_WARP / CH && row0 + CH < gs.n_feat) epi.load(in, row0 + CH, b, valid, gs.n_feat);
       }
       tc_fence_before();
       __syncwarp();

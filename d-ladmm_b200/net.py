@@ -37,7 +37,7 @@ _FAMILY_KEY = {_lib.FAMILY_A: "A", _lib.FAMILY_B: "B", _lib.FAMILY_C: "C"}
 
 
 def default_precision():
-    return os.environ.get("DLADMM_PRECISION", "fp32")
+    return os.environ.get("DLADMM_PRECISION", "tf32x3")
 
 
 def _param_table(variant, m, d, bs):
