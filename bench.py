@@ -36,6 +36,11 @@ F_FWD = 2.0 * M * D * (2 * K_LAYERS + 1)          # algorithmic flops per instan
 F_GEMM_PER_COL = 2.0 * M * D                      # one (d x m)(m x 1) or (m x d)(d x 1) product
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+# (profiles/r01_ncu_full_summary.md), keyed by (precision, kernel kind)
+TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 463.263488e6 + 279.419136e6, ("tf32x3", "gemm_z"): 264.145920e6 + 213.329408e6}
+
+
 def _peaks():
     p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
     try:
@@ -304,19 +309,38 @@ def run_ours(args):
         gemm_kinds = ("gemm_t0", "gemm_z", "gemm_elt")
         flops_per_launch = F_GEMM_PER_COL * B
         mma_passes = {"fp32": 1, "tf32": 1, "tf32x3": 3}[precision]
-        achieved = flops_per_launch / (dom_ms / dom_n * 1e-3) / 1e12 if dom in gemm_kinds else None
-        peak = peaks["tf32_tflops"] / mma_passes
+        # algorithmic HBM bytes per launch of each fused product kernel: operands read +
+        # epilogue inputs read + outputs written; 3xTF32 carries the split operand arrays (V_big/V_small, Z_small)
+        x3 = precision == "tf32x3"
+        bytes_per_launch = {
+            "gemm_t0": 4.0 * B * ((2 * D if x3 else D) + 3 * M + M + (2 * M if x3 else M)),
+            "gemm_z": 4.0 * B * ((2 * M if x3 else M) + D + (2 * D if x3 else D)),
+            "gemm_elt": 4.0 * B * ((2 * D if x3 else D) + 3 * M + 3 * M + (2 * M if x3 else M)),
+        }
+        avg_ms = dom_ms / dom_n
+        tensor_peak = peaks["tf32_tflops"] / mma_passes
+        tensor_ach = flops_per_launch / (avg_ms * 1e-3) / 1e12 if dom in gemm_kinds else None
+        hbm_ach = bytes_per_launch.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9 if dom in gemm_kinds else None
+        tensor_frac = tensor_ach / tensor_peak if tensor_ach else None
+        hbm_frac = hbm_ach / peaks["hbm_gbs"] if hbm_ach else None
         total_prof = sum(v[0] for v in kinds.values())
+        # the binding roofline of the dominant kernel is the one it sits closer to
+        hbm_bound = (hbm_frac or 0) >= (tensor_frac or 0)
         roofline = {
-            "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": None,
-            "peak_source": "TF32 dense %s, divided by %d MMA pass(es) for precision %s; MEASURED_PEAKS %s" %
-                           (peaks["tf32_source"], mma_passes, precision, peaks["source"]),
+            "bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
+            "achieved": hbm_ach if hbm_bound else tensor_ach,
+            "peak": peaks["hbm_gbs"] if hbm_bound else tensor_peak,
+            "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": hbm_frac if hbm_bound else tensor_frac,
+            "traffic": TRAFFIC_NCU.get((precision, dom)),
+            "peak_source": "HBM copy %s; TF32 dense %s / %d MMA pass(es) for precision %s" %
+                           (peaks["source"], peaks["tf32_source"], mma_passes, precision),
+            "tensor": {"achieved_tflops": tensor_ach, "peak_tflops": tensor_peak, "frac": tensor_frac},
+            "hbm": {"achieved_gbs": hbm_ach, "peak_gbs": peaks["hbm_gbs"], "frac": hbm_frac,
+                    "algorithmic_bytes_per_launch": bytes_per_launch.get(dom)},
             "share_of_step": dom_ms / total_prof if total_prof else None,
-            "avg_launch_ms": dom_ms / dom_n,
+            "avg_launch_ms": avg_ms,
             "algorithmic_flops_per_launch": flops_per_launch,
-            "hbm_achieved_gbs_whole_step": (4.0 * (K_LAYERS * (3 * D + 8 * M) + 2 * M + D) * B) / (ms_step * 1e-3) / 1e9,
-            "hbm_peak_gbs": peaks["hbm_gbs"],
             "per_kind_ms_per_step": {k: v[0] / args.steps for k, v in kinds.items()},
         }
         line = {
