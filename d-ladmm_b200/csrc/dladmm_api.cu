@@ -486,7 +486,11 @@ int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* s
   if ((rc = check_device())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w = carve(p, 1);
-  // backward products currently run on the FFMA kernels for every precision (fp32 products, fp32 accumulate)
+  if (p->workspace_bytes < dladmm_workspace_bytes(p, 1)) {
+    set_error("workspace too small: need %zu bytes, got %zu", dladmm_workspace_bytes(p, 1), p->workspace_bytes);
+    return DLADMM_ERR_WORKSPACE;
+  }
+  if (umma_eligible(p)) return umma_backward(p, g, w, (char*)p->workspace + w.bytes, st);
   if ((rc = prepare_weights(p, w, true, st))) return rc;
   switch (p->family) {
     case DLADMM_FAMILY_A: return backward_simt<DLADMM_FAMILY_A>(p, g, w, st);

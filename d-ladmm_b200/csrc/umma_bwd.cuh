@@ -1,0 +1,329 @@
+// tcgen05 backward: epilogues of the two activation-side products (A^T dR and W^T dx1), the batch-reduction
+// product dW -= s1 * dx1 * V^T (both operands K-major, split over CTAs along the batch), and the launch schedule.
+// Recurrences: SURVEY.md 7.1 / oracle manual_backward; arithmetic identical to epilogues.cuh (m1_quad, EpiBG1/2).
+#pragma once
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "umma_gemm.cuh"
+#include "umma_epilogues.cuh"
+
+namespace dladmm {
+namespace umma {
+
+// where row-reduced parameter-gradient partial sums go.
+//   PS  (all parameters scalar): one entry per epilogue warp of the grid  -> part[slot * nentries + entry]
+//   !PS: one entry per (32-column group, feature row)                     -> part[(slot * ngroups + group) * prow + row]
+struct RedOut { float* part; int nentries; int ngroups; int prow; };
+
+template <bool PS>
+__device__ __forceinline__ void red_contrib(const BP& q, const RedOut& ro, int slot, float& acc, int row, i64 col, i64 group,
+                                            bool ok, float val, int lane) {
+  if (q.g == nullptr) return;                       // warp-uniform
+  if (q.period) {                                   // per-slot parameter (main_lena.py:35-36): direct accumulation
+    if (ok) atomicAdd(q.g + (i64)row * q.rs + col % q.period, val);
+    return;
+  }
+  if (PS) {
+    acc += ok ? val : 0.f;
+  } else {
+    const float s = warp_sum(ok ? val : 0.f);
+    if (lane == 0) ro.part[((i64)slot * ro.ngroups + group) * ro.prow + row] = s;
+  }
+}
+
+template <bool PS, int NRED>
+__device__ __forceinline__ void red_finish(const RedOut& ro, const int (&slots)[NRED], float (&acc)[NRED], int entry, int lane) {
+  if (!PS) return;
+#pragma unroll
+  for (int r = 0; r < NRED; ++r) {
+    const float s = warp_sum(acc[r]);
+    if (lane == 0) ro.part[(i64)slots[r] * ro.nentries + entry] = s;
+  }
+}
+
+// dZ_k = gZ_k + carried + A^T dR ; dx1 = dZ_k * (m+ + m-) ; dtheta1 ; dx1 is written as (raw, small) = next operand
+template <int NPASS, bool PS>
+struct UEpiBG1 {
+  static constexpr int CHUNK = CH;
+  struct State { float red[1]; int lane; };
+  struct In { float gz[CH], cz[CH]; unsigned mk[CH]; };
+  const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
+  BP th1; float* dx1; float* __restrict__ dx1s; RedOut ro; i64 B;
+  __device__ __forceinline__ void begin(State& st) const { st.red[0] = 0.f; st.lane = threadIdx.x & 31; }
+  __device__ __forceinline__ void end(State& st, int entry, int lane) const {
+    const int slots[1] = {SL_TH1};
+    if (th1.g && th1.period == 0) red_finish<PS, 1>(ro, slots, st.red, entry, lane);
+  }
+  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const bool ok = valid && row0 + i < n_feat;
+      const i64 off = (i64)(row0 + i) * B + b;
+      in.gz[i] = (ok && gZ) ? __ldg(gZ + off) : 0.f;
+      in.cz[i] = (ok && cZin) ? cZin[off] : 0.f;
+      in.mk[i] = ok ? (unsigned)__ldg(maskZ + off) : 0u;
+    }
+  }
+  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat,
+                                        i64 group) const {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int row = row0 + i;
+      if (row >= n_feat) continue;                  // warp-uniform
+      const bool ok = valid;
+      const i64 off = (i64)row * B + b;
+      const float dz = v[i] + in.gz[i] + in.cz[i];
+      const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
+      const float o = dz * (mp + mn);
+      red_contrib<PS>(th1, ro, SL_TH1, st.red[0], row, b, group, ok, dz * (mn - mp), st.lane);
+      if (ok) {
+        dx1[off] = o;
+        if (NPASS == 3) dx1s[off] = o - tf32_trunc(o);
+      }
+    }
+  }
+};
+
+// dV = -s1 * W^T dx1 ; dbeta1, dss1 ; carried dL, dT ; then the elementwise cotangent flow of layer k-1 (m1):
+// writes dR (raw, small) for the next A^T dR product, carried dE and dL.
+template <int FAM, int NPASS, bool PS>
+struct UEpiBG2 {
+  static constexpr int CHUNK = 8;
+  static constexpr int C8 = 8;
+  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; };
+  struct In { float lp[C8], tk[C8], cl[C8], ce[C8], ek[C8], ep[C8], lpp[C8], gl[C8], ge[C8], gt[C8]; unsigned mk[C8]; };
+  // layer k
+  const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
+  int has_prev;
+  // layer k-1 (m1)
+  const float* __restrict__ Ek; const float* __restrict__ Ep; const float* __restrict__ Lpp; const uint8_t* __restrict__ maskE;
+  const float* __restrict__ gE; const float* __restrict__ gL; const float* __restrict__ gT;
+  BP bL, b2, ss2, ss2_2, th2;
+  float* __restrict__ dR; float* __restrict__ dRs; float* cE; float* cL;
+  RedOut ro; i64 B;
+  __device__ __forceinline__ void begin(State& st) const {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) st.red[r] = 0.f;
+    st.b1.init(b1); st.bL.init(bL); st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2);
+    st.s1 = ss1.p ? __ldg(ss1.p) : 1.f;
+    st.lane = threadIdx.x & 31;
+  }
+  __device__ __forceinline__ void end(State& st, int entry, int lane) const {
+    const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
+    red_finish<PS, 6>(ro, slots, st.red, entry, lane);
+  }
+  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
+#pragma unroll
+    for (int i = 0; i < C8; ++i) {
+      const bool ok = valid && row0 + i < n_feat;
+      const i64 off = (i64)(row0 + i) * B + b;
+      in.lp[i] = ok ? __ldg(Lp + off) : 0.f;
+      in.tk[i] = ok ? __ldg(Tk + off) : 0.f;
+      in.cl[i] = ok ? cLin[off] : 0.f;
+      if (has_prev) {
+        in.ce[i] = ok ? cEin[off] : 0.f;
+        in.ek[i] = ok ? __ldg(Ek + off) : 0.f;
+        in.lpp[i] = ok ? __ldg(Lpp + off) : 0.f;
+        if (FAM == DLADMM_FAMILY_B) in.ep[i] = ok ? __ldg(Ep + off) : 0.f;
+        if (FAM != DLADMM_FAMILY_C) in.mk[i] = ok ? (unsigned)__ldg(maskE + off) : 0u;
+        in.gl[i] = (ok && gL) ? __ldg(gL + off) : 0.f;
+        in.ge[i] = (ok && gE) ? __ldg(gE + off) : 0.f;
+        in.gt[i] = (ok && gT) ? __ldg(gT + off) : 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[C8], int n_feat,
+                                        i64 group) const {
+#pragma unroll
+    for (int i = 0; i < C8; ++i) {
+      const int row = row0 + i;
+      if (row >= n_feat) continue;                  // warp-uniform
+      const bool ok = valid;
+      const i64 off = (i64)row * B + b;
+      const float vb1 = st.b1.at(row, b);
+      const float tk = in.tk[i];
+      const float var = in.lp[i] + vb1 * tk;          // V_k recomputed
+      const float dV = -st.s1 * v[i];
+      red_contrib<PS>(b1, ro, SL_B1, st.red[4], row, b, group, ok, dV * tk, st.lane);
+      red_contrib<PS>(ss1, ro, SL_SS1, st.red[5], row, b, group, ok, -var * v[i], st.lane);
+      float dL = in.cl[i] + dV;
+      float dT = vb1 * dV;
+      if (!has_prev) continue;                      // warp-uniform
+      // ---- layer k-1: (dL, dT, dE) -> dR, carried dE, carried dL (m1_quad in epilogues.cuh) ----
+      dL += in.gl[i];
+      float dE = in.ce[i] + in.ge[i];
+      dT += in.gt[i];
+      const float tn = tk, ek = in.ek[i], lpp = in.lpp[i];
+      const float vbL = st.bL.at(row, b);
+      red_contrib<PS>(bL, ro, SL_BL, st.red[0], row, b, group, ok, dL * tn, st.lane);
+      const float dTt = dT + vbL * dL;
+      const float dEt = dE + dTt;
+      float dRv, nE, nL;
+      if (FAM == DLADMM_FAMILY_B) {
+        const float ep = in.ep[i];
+        const float vb2 = st.b2.at(row, b), vs2 = st.ss2.at(row, b);
+        const float that = (tn - ek) + ep;
+        const float q = lpp + vb2 * that;
+        const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
+        const float du = dEt * (mp + mn);
+        red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
+        const float dQ = -vs2 * du;
+        red_contrib<PS>(ss2, ro, SL_SS2, st.red[2], row, b, group, ok, -du * q, st.lane);
+        const float dThat = vb2 * dQ;
+        red_contrib<PS>(b2, ro, SL_B2, st.red[3], row, b, group, ok, dQ * that, st.lane);
+        dRv = dTt + dThat; nE = du + dThat; nL = dL + dQ;
+      } else if (FAM == DLADMM_FAMILY_A) {
+        const float vb2 = st.b2.at(row, b);
+        const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
+        const float du = dEt * (mp + mn);
+        red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
+        red_contrib<PS>(b2, ro, SL_B2, st.red[3], row, b, group, ok, -du * lpp, st.lane);
+        dRv = dTt - du; nE = 0.f; nL = dL - vb2 * du;
+      } else {
+        const float v1 = st.ss2.at(row, b), v2 = st.ss2_2.at(row, b);
+        red_contrib<PS>(ss2, ro, SL_SS2, st.red[2], row, b, group, ok, dEt * (ek - tn), st.lane);
+        red_contrib<PS>(ss2_2, ro, SL_B2, st.red[3], row, b, group, ok, -dEt * lpp, st.lane);
+        dRv = dTt - v1 * dEt; nE = 0.f; nL = dL - v2 * dEt;
+      }
+      if (ok) {
+        dR[off] = dRv;
+        if (NPASS == 3) dRs[off] = dRv - tf32_trunc(dRv);
+        cE[off] = nE;
+        cL[off] = nL;
+      }
+    }
+  }
+};
+
+// ---- dW[i,j] += alpha * sum_b P[i,b] * Q[j,b]  (P = dx1 (d x B), Q = V_k (m x B)), K = batch ------------------
+// Both operands are K-major (batch contiguous).  One 128 x 256 output tile per CTA over a slice of the batch;
+// partial results are added to dW with fp32 reductions (red.global.add).
+template <int NPASS, int KC>
+struct NtPlan {
+  static constexpr int NOPS = NPASS == 3 ? 2 : 1;
+  static constexpr int A_BYTES = 128 * KC * 4;
+  static constexpr int B_BYTES = TILE_N * KC * 4;
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+struct NtShape {
+  int M, N;            // valid rows of P (d) and of Q (m)
+  i64 B;
+  i64 chunk;           // batch columns per CTA (multiple of KC)
+  int ldc;
+};
+
+template <int NPASS, int KC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constant__ CUtensorMap tmP_small,
+               const __grid_constant__ CUtensorMap tmQ_big, const __grid_constant__ CUtensorMap tmQ_small, NtShape ns,
+               const float* __restrict__ s1ptr, float sign, float* __restrict__ C) {
+  using Plan = NtPlan<NPASS, KC>;
+  constexpr int STAGES = Plan::STAGES;
+  constexpr uint32_t LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
+  constexpr uint32_t SBO = 8 * KC * 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * Plan::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * 128;
+  const int n0 = blockIdx.z * TILE_N;                 // tile of Q rows (columns of dW)
+  const i64 b_begin = (i64)blockIdx.y * ns.chunk;
+  i64 b_end = b_begin + ns.chunk;
+  if (b_end > ns.B) b_end = ns.B;
+  const int k_chunks = b_end > b_begin ? (int)((b_end - b_begin + KC - 1) / KC) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP_big); prefetch_tmap(&tmQ_big);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (k_chunks > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * Plan::STAGE_BYTES;
+          mbar_expect_tx(&full[s], Plan::STAGE_BYTES);
+          const int bc = (int)(b_begin + (i64)kc * KC);
+#pragma unroll
+          for (int op = 0; op < Plan::NOPS; ++op) {
+            tma_load_2d(st + op * Plan::A_BYTES, op == 0 ? &tmP_big : &tmP_small, &full[s], bc, i0);
+            tma_load_2d(st + Plan::NOPS * Plan::A_BYTES + op * Plan::B_BYTES, op == 0 ? &tmQ_big : &tmQ_small, &full[s], bc, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
+        int s = 0; uint32_t ph = 0;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * Plan::STAGE_BYTES);
+          const uint32_t a_big = st, a_small = st + Plan::A_BYTES;
+          const uint32_t b_big = st + Plan::NOPS * Plan::A_BYTES, b_small = b_big + Plan::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < KC / UMMA_K; ++ks) {
+            const uint64_t da = make_sdesc(a_big + ks * 32, 16, SBO, LAYOUT);
+            const uint64_t db = make_sdesc(b_big + ks * 32, 16, SBO, LAYOUT);
+            const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+            if (NPASS == 3) {
+              const uint64_t das = make_sdesc(a_small + ks * 32, 16, SBO, LAYOUT);
+              const uint64_t dbs = make_sdesc(b_small + ks * 32, 16, SBO, LAYOUT);
+              umma_tf32(tmem_base, das, db, idesc, first);
+              umma_tf32(tmem_base, da, dbs, idesc, 1u);
+              umma_tf32(tmem_base, da, db, idesc, 1u);
+            } else {
+              umma_tf32(tmem_base, da, db, idesc, first);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (kc == k_chunks - 1) umma_commit(tfull);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      const int half = (warp - EPI_WARP0) >> 2;
+      const int row = i0 + q * 32 + lane;               // row of dW (TMEM lane)
+      const float alpha = sign * (s1ptr ? __ldg(s1ptr) : 1.f);
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + half * (TILE_N / 2) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < (TILE_N / 2) / 16; ++c) {
+        const int j0 = n0 + half * (TILE_N / 2) + c * 16;
+        if (j0 >= ns.N) break;
+        float v[16];
+        tmem_ld16(t0 + c * 16, v);
+        if (row < ns.M) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (j0 + i < ns.N) atomicAdd(C + (i64)row * ns.ldc + j0 + i, alpha * v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+}  // namespace umma
+}  // namespace dladmm

@@ -54,12 +54,13 @@ __device__ __forceinline__ void store_split_rna(float* __restrict__ big, float* 
 // T_0 = A Z0 + E0 - X, and V_0 = L0 + beta1_0 * T_0 for the first Z-step
 template <int NPASS, bool PSCALAR>
 struct UEpiT0 {
+  static constexpr int CHUNK = CH;
   struct State { PV<PSCALAR> b1; };
   struct In { float e0[CH], x[CH], l0[CH]; };
   const float* __restrict__ E0; const float* __restrict__ X; const float* __restrict__ L0; float* __restrict__ T0;
   BP b1; float* __restrict__ Vb; float* __restrict__ Vs; i64 B;
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
-  __device__ __forceinline__ void end(State&) const {}
+  __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -88,12 +89,13 @@ struct UEpiT0 {
 // Z_k = act(Z_{k-1} - [ss1*] acc, theta1); Z_small = Z - trunc_tf32(Z) is the second operand part of A Z_k
 template <int NPASS, bool PSCALAR>
 struct UEpiZ {
+  static constexpr int CHUNK = CH;
   struct State { PV<PSCALAR> th1; float s1; };
   struct In { float zp[CH]; };
   const float* __restrict__ Zp; float* __restrict__ Zk; float* __restrict__ Zs; uint8_t* __restrict__ maskZ;
   BP th1; BP ss1; i64 B;
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; }
-  __device__ __forceinline__ void end(State&) const {}
+  __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -121,6 +123,7 @@ struct UEpiZ {
 // E_k, T_{k+1}, L_k from acc = A Z_k; then V_{k+1} = L_k + beta1_{k+1} * T_{k+1} (split) unless this is the last layer
 template <int FAM, int NPASS, bool PSCALAR>
 struct UEpiELT {
+  static constexpr int CHUNK = CH;
   struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; };
   struct In { float x[CH], lp[CH], ep[CH]; };
   const float* __restrict__ X; const float* __restrict__ Ep; const float* __restrict__ Lp;
@@ -131,7 +134,7 @@ struct UEpiELT {
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
   }
-  __device__ __forceinline__ void end(State&) const {}
+  __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {

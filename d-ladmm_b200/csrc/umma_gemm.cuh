@@ -122,6 +122,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+
 // ---- descriptors ---------------------------------------------------------------------------------------
 // instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -281,6 +294,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
     const int half = (warp - EPI_WARP0) >> 2;          // which half of the tile's feature rows
     constexpr int ROWS_PER_WARP = TILE_N / (EPI_WARPS / 4);
+    constexpr int CHK = Epi::CHUNK;                    // feature rows per epilogue step
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
@@ -299,20 +313,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
       // CH rows per step: small enough that the unrolled body stays inside the instruction cache, large enough
       // (CH loads per input array per thread) to keep HBM busy from 4 warps
 #pragma unroll 1
-      for (int c = 0; c < ROWS_PER_WARP / CH; ++c) {
-        const int row0 = jw + c * CH;
+      for (int c = 0; c < ROWS_PER_WARP / CHK; ++c) {
+        const int row0 = jw + c * CHK;
         if (row0 >= gs.n_feat) break;                  // warp-uniform
-        float v[CH];
-        tmem_ld16(t0 + c * CH, v);
+        float v[CHK];
+        tmem_ld(t0 + c * CHK, v);
         epi.apply(state, in, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);
-        if (c + 1 < ROWS_PER_WARP / CH && row0 + CH < gs.n_feat) epi.load(in, row0 + CH, b, valid, gs.n_feat);
+        if (c + 1 < ROWS_PER_WARP / CHK && row0 + CHK < gs.n_feat) epi.load(in, row0 + CHK, b, valid, gs.n_feat);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
-    epi.end(state);
+    epi.end(state, (int)blockIdx.x * EPI_WARPS + (warp - EPI_WARP0), lane);
   }
   tc_fence_before();
   __syncthreads();

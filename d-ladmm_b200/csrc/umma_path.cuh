@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "umma_gemm.cuh"
 #include "umma_epilogues.cuh"
+#include "umma_bwd.cuh"
 
 #define DLADMM_HAS_UMMA 1
 
@@ -48,10 +49,50 @@ static inline bool umma_eligible(const dladmm_problem* p) {
   return p->precision != DLADMM_PREC_FP32 && (p->B % 4) == 0;
 }
 
+struct UBwdWorkspace {
+  float *Atb, *Ats;    // A^T (d256 x mp): features of A^T dR on the N side, K = m
+  float *Wtb, *Wts;    // nW x (m256 x dp): W^T, features of W^T dx1 on the N side, K = d
+  float *cZs;          // (d x B) small part of dx1
+  float *dRs;          // (m x B) small part of dR
+  float *Vb, *Vs;      // (m x B) V_k recomputed per layer
+  float *part;         // parameter-gradient partial sums of the tcgen05 epilogues
+  size_t bytes;
+  int m256, d256, mp, dp, nW, ngroups, prow, nentries;
+};
+
+static UBwdWorkspace ucarve_bwd(const dladmm_problem* p, char* base) {
+  UBwdWorkspace w;
+  memset(&w, 0, sizeof(w));
+  w.m256 = round_up(p->m, umma::TILE_N);
+  w.d256 = round_up(p->d, umma::TILE_N);
+  w.mp = round_up(p->m, 32);
+  w.dp = round_up(p->d, 32);
+  w.nW = unique_weights(p);
+  w.ngroups = (int)(((p->B + umma::TILE_B - 1) / umma::TILE_B) * (umma::TILE_B / 32));
+  w.prow = round_up(std::max(p->m, p->d), 32);
+  w.nentries = 256 * umma::EPI_WARPS;      // upper bound of (grid x epilogue warps)
+  size_t off = 0;
+  auto take = [&](size_t nfloats) {
+    float* r = (float*)(base + off);
+    off += round_up64((i64)nfloats * 4, 1024);
+    return r;
+  };
+  w.Atb = take((size_t)w.d256 * w.mp);
+  w.Ats = take((size_t)w.d256 * w.mp);
+  w.Wtb = take((size_t)w.nW * w.m256 * w.dp);
+  w.Wts = take((size_t)w.nW * w.m256 * w.dp);
+  w.cZs = take((size_t)p->d * p->B);
+  w.dRs = take((size_t)p->m * p->B);
+  w.Vb = take((size_t)p->m * p->B);
+  w.Vs = take((size_t)p->m * p->B);
+  w.part = take(std::max((size_t)SL_COUNT * w.ngroups * w.prow, (size_t)SL_COUNT * w.nentries));
+  w.bytes = off;
+  return w;
+}
+
 static inline size_t umma_workspace_bytes(const dladmm_problem* p, int for_backward) {
-  (void)for_backward;
   if (p->precision == DLADMM_PREC_FP32) return 0;
-  return ucarve(p, nullptr).bytes + 1024;
+  return (for_backward ? ucarve_bwd(p, nullptr).bytes : ucarve(p, nullptr).bytes) + 1024;
 }
 
 // dense (R x C) -> zero padded (Rpad x Cpad) big/small (tf32 round-to-nearest split) or a plain padded copy
@@ -115,6 +156,59 @@ static int uprepare_weights(const dladmm_problem* p, const UWorkspace& w, cudaSt
   return DLADMM_OK;
 }
 
+// dst (Rpad x Cpad) = src^T, src is (C x R) dense; zero padded; tf32 split as above
+template <int NPASS>
+static __global__ void __launch_bounds__(256) prep_split_t_kernel(SplitJobs jobs, int R, int C, int Rpad, int Cpad) {
+  __shared__ float tile[32][33];
+  const SplitJob jb = jobs.j[blockIdx.z];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {          // read src[c][r] coalesced along r
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && r < R) ? jb.src[(i64)c * R + r] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {          // write dst[r][c] coalesced along c
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    if (r >= Rpad || c >= Cpad) continue;
+    const float v = tile[tx][ty + 8 * i];
+    if (NPASS == 3) {
+      const float b = umma::tf32_rna(v);
+      jb.big[(i64)r * Cpad + c] = b;
+      jb.small[(i64)r * Cpad + c] = v - b;
+    } else {
+      jb.big[(i64)r * Cpad + c] = v;
+    }
+  }
+}
+
+// V_k = L_{k-1} + beta1_k * T_k as split MMA operand (backward recomputation)
+template <int NPASS>
+static __global__ void __launch_bounds__(256) make_v_kernel(const float* __restrict__ L, const float* __restrict__ T, BP b1, int rows,
+                                                            i64 B, float* __restrict__ Vb, float* __restrict__ Vs) {
+  const i64 quads = (B + 3) / 4;
+  const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= quads * rows) return;
+  const int row = (int)(idx / quads);
+  const i64 col = (idx % quads) * 4;
+  const i64 rem = B - col;
+  const int nv = rem >= 4 ? 4 : (int)rem;
+  const bool vec = (B & 3) == 0;
+  const i64 off = (i64)row * B + col;
+  Quad l = load4(L, off, nv, vec), t = load4(T, off, nv, vec);
+  float b[4]; bp_at4(b1, row, col, b);
+  float vb[4], vs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float v = fadd(l.v[j], fmul(b[j], t.v[j]));
+    if (NPASS == 3) { vb[j] = umma::tf32_rna(v); vs[j] = v - vb[j]; } else { vb[j] = v; vs[j] = 0.f; }
+  }
+  store4(Vb, off, vb, nv, vec);
+  if (NPASS == 3) store4(Vs, off, vs, nv, vec);
+}
+
 static int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -130,7 +224,7 @@ static int device_sm_count() {
 // (n_pad x k_pad) K-major arrays.
 template <class Epi, int NPASS>
 static int launch_umma(int kind, const float* act_big, const float* act_small, int Kdim, const float* w_big, const float* w_small,
-                       int n_pad, int k_pad, int n_feat, i64 B, const Epi& epi, cudaStream_t st) {
+                       int n_pad, int k_pad, int n_feat, i64 B, const Epi& epi, cudaStream_t st, int grid_override = 0) {
   constexpr int KC = NPASS == 3 ? 16 : 32;
   using Plan = umma::SmemPlan<NPASS, KC>;
   CUtensorMap tAb, tAs, tBb, tBs;
@@ -157,7 +251,7 @@ static int launch_umma(int kind, const float* act_big, const float* act_small, i
     attr_set = true;
   }
   const i64 ntiles = gs.n_btiles * gs.n_ntiles;
-  const int grid = (int)std::min<i64>(ntiles, device_sm_count());
+  const int grid = grid_override > 0 ? grid_override : (int)std::min<i64>(ntiles, device_sm_count());
   {
     LaunchScope ls(kind, st);
     kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tAb, tAs, tBb, tBs, gs, epi);
@@ -210,17 +304,185 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   return DLADMM_OK;
 }
 
-static int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {
-  char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
-  UWorkspace w = ucarve(p, base);
-  const bool x3 = p->precision == DLADMM_PREC_TF32X3;
-  // are all broadcast parameters of the call (1,1) scalars?
+template <int NPASS>
+static int launch_nt(const float* P, const float* Ps, int M, const float* Q, const float* Qs, int N, i64 B, const float* s1ptr,
+                     float* C, int ldc, cudaStream_t st) {
+  constexpr int KC = NPASS == 3 ? 16 : 32;
+  using Plan = umma::NtPlan<NPASS, KC>;
+  const CUtensorMapSwizzle sw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tP, tPs, tQ, tQs;
+  int rc;
+  if ((rc = umma::make_tmap_2d(&tP, P, M, B, B, KC, 128, sw))) return rc;
+  if ((rc = umma::make_tmap_2d(&tQ, Q, N, B, B, KC, umma::TILE_N, sw))) return rc;
+  if (NPASS == 3) {
+    if ((rc = umma::make_tmap_2d(&tPs, Ps, M, B, B, KC, 128, sw))) return rc;
+    if ((rc = umma::make_tmap_2d(&tQs, Qs, N, B, B, KC, umma::TILE_N, sw))) return rc;
+  } else {
+    tPs = tP; tQs = tQ;
+  }
+  const int mt = (M + 127) / 128, nt = (N + umma::TILE_N - 1) / umma::TILE_N;
+  int split = std::max(1, device_sm_count() / (mt * nt));
+  i64 chunk = round_up64((B + split - 1) / split, KC);
+  split = (int)((B + chunk - 1) / chunk);
+  umma::NtShape ns;
+  ns.M = M; ns.N = N; ns.B = B; ns.chunk = chunk; ns.ldc = ldc;
+  auto kern = umma::umma_nt_kernel<NPASS, KC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL));
+    attr_set = true;
+  }
+  {
+    LaunchScope ls(DLADMM_KIND_BWD_GEMM_DW, st);
+    kern<<<dim3(mt, split, nt), umma::NUM_THREADS, Plan::TOTAL, st>>>(tP, tPs, tQ, tQs, ns, s1ptr, -1.f, C);
+  }
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+template <int FAM, int NPASS, bool PS>
+static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& sw, const UBwdWorkspace& w,
+                         cudaStream_t st) {
+  Slabs s(p);
+  const int m = p->m, d = p->d, K = p->K;
+  const i64 B = p->B;
+  int rc;
+  // transposed, split weights
+  {
+    SplitJobs jobs; jobs.n = 1;
+    jobs.j[0].src = p->A; jobs.j[0].big = w.Atb; jobs.j[0].small = w.Ats;
+    dim3 grid((w.mp + 31) / 32, (w.d256 + 31) / 32, 1);
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, d, m, w.d256, w.mp); }
+    DL_CUDA(cudaGetLastError());
+    std::vector<const float*> uniq = WeightMap(p).uniq;
+    for (size_t base = 0; base < uniq.size(); base += 32) {
+      SplitJobs wj; wj.n = (int)std::min<size_t>(32, uniq.size() - base);
+      for (int i = 0; i < wj.n; ++i) {
+        size_t idx = base + i;
+        wj.j[i].src = uniq[idx];
+        wj.j[i].big = w.Wtb + idx * (size_t)w.m256 * w.dp;
+        wj.j[i].small = w.Wts + idx * (size_t)w.m256 * w.dp;
+      }
+      dim3 g2((w.dp + 31) / 32, (w.m256 + 31) / 32, wj.n);
+      { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<NPASS><<<g2, 256, 0, st>>>(wj, m, d, w.m256, w.dp); }
+      DL_CUDA(cudaGetLastError());
+    }
+  }
+  // top layer: elementwise cotangent flow with nothing carried (FFMA-path kernel), then split dR
+  {
+    M1Args a = make_m1(p, g, sw, K - 1);
+    dim3 grid(sw.ncolTiles, (m + 7) / 8);
+    { LaunchScope ls(DLADMM_KIND_BWD_ELEM, st); m1_kernel<FAM><<<grid, 256, 0, st>>>(m, B, a, sw.part, sw.ncolTiles, sw.prow); }
+    DL_CUDA(cudaGetLastError());
+    ReduceJobs jobs; jobs.n = 0;
+    add_m1_jobs(p, jobs, p->layers[K - 1]);
+    if ((rc = launch_reduce(jobs, sw, st))) return rc;
+    if (NPASS == 3) {
+      i64 n = (i64)m * B;
+      { LaunchScope ls(DLADMM_KIND_PREP, st); split_trunc_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(sw.dR, w.dRs, n); }
+      DL_CUDA(cudaGetLastError());
+    }
+  }
+  // one grid for both activation-side products so that the per-warp partial entries line up
+  const i64 nbt = (B + umma::TILE_B - 1) / umma::TILE_B;
+  const i64 tiles_dz = nbt * ((d + umma::TILE_N - 1) / umma::TILE_N), tiles_dv = nbt * ((m + umma::TILE_N - 1) / umma::TILE_N);
+  const int grid = (int)std::min<i64>(std::max(tiles_dz, tiles_dv), std::min(device_sm_count(), 256));
+  umma::RedOut ro;
+  ro.part = w.part; ro.nentries = grid * umma::EPI_WARPS; ro.ngroups = w.ngroups; ro.prow = w.prow;
+  for (int k = K - 1; k >= 0; --k) {
+    const dladmm_layer& l = p->layers[k];
+    const size_t wi = (size_t)weight_index(p, k);
+    {
+      umma::UEpiBG1<NPASS, PS> epi;
+      epi.gZ = g->gZ ? g->gZ + s.zs * k : nullptr;
+      epi.cZin = k == K - 1 ? nullptr : sw.cZ;
+      epi.maskZ = s.mZ(k);
+      epi.th1 = make_bp(l.theta1);
+      epi.dx1 = sw.cZ; epi.dx1s = w.cZs; epi.ro = ro; epi.B = B;
+      if ((rc = launch_umma<umma::UEpiBG1<NPASS, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DZ, sw.dR, w.dRs, m, w.Atb, w.Ats, w.d256, w.mp, d, B,
+                                                             epi, st, grid)))
+        return rc;
+    }
+    if (l.gW) {
+      const i64 quads = (B + 3) / 4;
+      { LaunchScope ls(DLADMM_KIND_PREP, st);
+        make_v_kernel<NPASS><<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(s.Lin(k), s.Tslab(k), make_bp(l.beta1), m, B, w.Vb, w.Vs); }
+      DL_CUDA(cudaGetLastError());
+      if ((rc = launch_nt<NPASS>(sw.cZ, w.cZs, d, w.Vb, w.Vs, m, B, l.ss1.ptr, l.gW, m, st))) return rc;
+    }
+    {
+      umma::UEpiBG2<FAM, NPASS, PS> epi;
+      epi.Lp = s.Lin(k); epi.Tk = s.Tslab(k);
+      epi.b1 = make_bp(l.beta1); epi.ss1 = make_bp(l.ss1);
+      epi.cLin = sw.cL; epi.cEin = sw.cE;
+      epi.has_prev = k > 0;
+      const int j = k > 0 ? k - 1 : 0;
+      const dladmm_layer& lj = p->layers[j];
+      epi.Ek = s.Eout(j); epi.Ep = s.Ein(j); epi.Lpp = s.Lin(j); epi.maskE = s.mE(j);
+      epi.gE = g->gE ? g->gE + s.ms * j : nullptr;
+      epi.gL = g->gL ? g->gL + s.ms * j : nullptr;
+      epi.gT = g->gT ? g->gT + s.ms * (j + 1) : nullptr;
+      epi.bL = make_bp(betaL(p, lj)); epi.b2 = make_bp(lj.beta2); epi.ss2 = make_bp(lj.ss2); epi.ss2_2 = make_bp(lj.ss2_2);
+      epi.th2 = make_bp(lj.theta2);
+      epi.dR = sw.dR; epi.dRs = w.dRs; epi.cE = sw.cE; epi.cL = sw.cL;
+      epi.ro = ro; epi.B = B;
+      if ((rc = launch_umma<umma::UEpiBG2<FAM, NPASS, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, w.cZs, d, w.Wtb + wi * w.m256 * w.dp,
+                                                                  w.Wts + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
+        return rc;
+    }
+    ReduceJobs jobs; jobs.n = 0;
+    add_job(jobs, SL_TH1, l.theta1, d);
+    add_job(jobs, SL_B1, l.beta1, m);
+    add_job(jobs, SL_SS1, l.ss1, m);
+    if (k > 0) add_m1_jobs(p, jobs, p->layers[k - 1]);
+    if (jobs.n) {
+      int ncol = ro.ngroups, prow = ro.prow;
+      if (PS) {
+        for (int i = 0; i < jobs.n; ++i) jobs.j[i].rows = 1;
+        ncol = ro.nentries; prow = 1;
+      }
+      int maxrows = 1;
+      for (int i = 0; i < jobs.n; ++i)
+        if (!jobs.j[i].scalar) maxrows = std::max(maxrows, jobs.j[i].rows);
+      dim3 rg((maxrows + 7) / 8, jobs.n);
+      { LaunchScope ls(DLADMM_KIND_BWD_REDUCE, st); reduce_partials_kernel<<<rg, 256, 0, st>>>(jobs, w.part, ncol, prow); }
+      DL_CUDA(cudaGetLastError());
+    }
+  }
+  return DLADMM_OK;
+}
+
+static bool all_params_scalar(const dladmm_problem* p) {
   bool ps = true;
   for (int k = 0; k < p->K; ++k) {
     const dladmm_layer& l = p->layers[k];
     const dladmm_bparam* all[8] = {&l.beta1, &l.beta2, &l.beta3, &l.ss1, &l.ss2, &l.ss2_2, &l.theta1, &l.theta2};
     for (int i = 0; i < 8; ++i) ps = ps && (all[i]->ptr == nullptr || (all[i]->row_stride == 0 && all[i]->col_period == 0));
   }
+  return ps;
+}
+
+static int umma_backward(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& sw, void* ws_base, cudaStream_t st) {
+  char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
+  UBwdWorkspace w = ucarve_bwd(p, base);
+  const bool x3 = p->precision == DLADMM_PREC_TF32X3;
+  const bool ps = all_params_scalar(p);
+#define DL_BWD(F)                                                                                                   \
+  (x3 ? (ps ? backward_umma<F, 3, true>(p, g, sw, w, st) : backward_umma<F, 3, false>(p, g, sw, w, st))              \
+      : (ps ? backward_umma<F, 1, true>(p, g, sw, w, st) : backward_umma<F, 1, false>(p, g, sw, w, st)))
+  switch (p->family) {
+    case DLADMM_FAMILY_A: return DL_BWD(DLADMM_FAMILY_A);
+    case DLADMM_FAMILY_B: return DL_BWD(DLADMM_FAMILY_B);
+    default: return DL_BWD(DLADMM_FAMILY_C);
+  }
+#undef DL_BWD
+}
+
+static int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {
+  char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
+  UWorkspace w = ucarve(p, base);
+  const bool x3 = p->precision == DLADMM_PREC_TF32X3;
+  const bool ps = all_params_scalar(p);
 #define DL_FWD(F)                                                                                       \
   (x3 ? (ps ? forward_umma<F, 3, true>(p, w, st) : forward_umma<F, 3, false>(p, w, st))                  \
       : (ps ? forward_umma<F, 1, true>(p, w, st) : forward_umma<F, 1, false>(p, w, st)))

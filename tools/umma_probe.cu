@@ -19,11 +19,12 @@ using namespace dladmm;
 using namespace dladmm::umma;
 
 struct EpiStore {
+  static constexpr int CHUNK = CH;
   struct State {};
   struct In {};
   float* C; i64 B;
   __device__ void begin(State&) const {}
-  __device__ void end(State&) const {}
+  __device__ void end(State&, int, int) const {}
   __device__ void load(In&, int, i64, bool, int) const {}
   __device__ void apply(State&, const In&, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat, i64) const {
     if (!valid) return;
