@@ -175,6 +175,8 @@ def run_ours(args):
     from dladmm_b200 import _lib
 
     rank, world, local = _dist_env()
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local)
@@ -289,7 +291,11 @@ def run_ours(args):
         t1.record()
         barrier()
         ms_train = t0.elapsed_time(t1)
-        train = {"columns_per_gpu": Bt, "ms_per_step": ms_train / nst}
+        _lib.profile_start()
+        step_train()
+        tprof = _lib.profile_stop()
+        train = {"columns_per_gpu": Bt, "ms_per_step": ms_train / nst,
+                 "kernel_ms_per_step": {k: v[0] for k, v in tprof.items() if v[1] > 0}}
 
     # ---- max over ranks -------------------------------------------------------------------------------
     stats = torch.tensor([ms_total, ms_e2e, train["ms_per_step"] if train else 0.0], device=dev, dtype=torch.float64)
@@ -364,6 +370,7 @@ def run_ours(args):
         if train:
             line["train"] = {"metric": "dladmm_train_samples_per_sec", "value": world * train["columns_per_gpu"] / (ms_train_step * 1e-3),
                              "unit": "samples/s", "columns_per_gpu": train["columns_per_gpu"], "ms_per_step": ms_train_step,
+                             "library_kernel_ms_per_step": train["kernel_ms_per_step"],
                              "what": "forward + backward + parameter gradients%s, scalar K=15" % (" + NCCL allreduce" if world > 1 else "")}
         if world == 1 and not args.no_cpu_baseline:
             times, threads = cpu_forward_rate(8192, 3)
