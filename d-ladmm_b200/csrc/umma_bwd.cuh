@@ -41,14 +41,14 @@ __device__ __forceinline__ void red_finish(const RedOut& ro, const int (&slots)[
   }
 }
 
-// dZ_k = gZ_k + carried + A^T dR ; dx1 = dZ_k * (m+ + m-) ; dtheta1 ; dx1 is written as (raw, small) = next operand
-template <int NPASS, bool PS>
+// dZ_k = gZ_k + carried + A^T dR ; dx1 = dZ_k * (m+ + m-) ; dtheta1 ; dx1 is the operand of the next two products
+template <bool PS>
 struct UEpiBG1 {
   static constexpr int CHUNK = CH;
   struct State { float red[1]; int lane; };
   struct In { float gz[CH], cz[CH]; unsigned mk[CH]; };
   const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
-  BP th1; float* dx1; float* __restrict__ dx1s; RedOut ro; i64 B;
+  BP th1; float* dx1; RedOut ro; i64 B;
   __device__ __forceinline__ void begin(State& st) const { st.red[0] = 0.f; st.lane = threadIdx.x & 31; }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[1] = {SL_TH1};
@@ -76,17 +76,14 @@ struct UEpiBG1 {
       const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_contrib<PS>(th1, ro, SL_TH1, st.red[0], row, b, group, ok, dz * (mn - mp), st.lane);
-      if (ok) {
-        dx1[off] = o;
-        if (NPASS == 3) dx1s[off] = o - tf32_trunc(o);
-      }
+      if (ok) dx1[off] = o;
     }
   }
 };
 
 // dV = -s1 * W^T dx1 ; dbeta1, dss1 ; carried dL, dT ; then the elementwise cotangent flow of layer k-1 (m1):
-// writes dR (raw, small) for the next A^T dR product, carried dE and dL.
-template <int FAM, int NPASS, bool PS>
+// writes dR for the next A^T dR product, carried dE and dL.
+template <int FAM, bool PS>
 struct UEpiBG2 {
   static constexpr int CHUNK = 8;
   static constexpr int C8 = 8;
@@ -99,7 +96,7 @@ struct UEpiBG2 {
   const float* __restrict__ Ek; const float* __restrict__ Ep; const float* __restrict__ Lpp; const uint8_t* __restrict__ maskE;
   const float* __restrict__ gE; const float* __restrict__ gL; const float* __restrict__ gT;
   BP bL, b2, ss2, ss2_2, th2;
-  float* __restrict__ dR; float* __restrict__ dRs; float* cE; float* cL;
+  float* __restrict__ dR; float* cE; float* cL;
   RedOut ro; i64 B;
   __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
@@ -187,7 +184,6 @@ struct UEpiBG2 {
       }
       if (ok) {
         dR[off] = dRv;
-        if (NPASS == 3) dRs[off] = dRv - tf32_trunc(dRv);
         cE[off] = nE;
         cL[off] = nL;
       }
@@ -203,7 +199,8 @@ struct NtPlan {
   static constexpr int NOPS = NPASS == 3 ? 2 : 1;
   static constexpr int A_BYTES = 128 * KC * 4;
   static constexpr int B_BYTES = TILE_N * KC * 4;
-  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [P raw | Q raw] [P small | Q small]
+  static constexpr int RAW_BYTES = A_BYTES + B_BYTES;                 // what TMA delivers
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
 };
@@ -217,8 +214,7 @@ struct NtShape {
 
 template <int NPASS, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constant__ CUtensorMap tmP_small,
-               const __grid_constant__ CUtensorMap tmQ_big, const __grid_constant__ CUtensorMap tmQ_small, NtShape ns,
+umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, NtShape ns,
                const float* __restrict__ s1ptr, float sign, float* __restrict__ C) {
   using Plan = NtPlan<NPASS, KC>;
   constexpr int STAGES = Plan::STAGES;
@@ -230,7 +226,8 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constan
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 2);
+  uint64_t* ready = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 128;
   const int n0 = blockIdx.z * TILE_N;                 // tile of Q rows (columns of dW)
@@ -240,8 +237,8 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constan
   const int k_chunks = b_end > b_begin ? (int)((b_end - b_begin + KC - 1) / KC) : 0;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmP_big); prefetch_tmap(&tmQ_big);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    prefetch_tmap(&tmP); prefetch_tmap(&tmQ);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
@@ -258,13 +255,10 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constan
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Plan::STAGE_BYTES);
+          mbar_expect_tx(&full[s], Plan::RAW_BYTES);
           const int bc = (int)(b_begin + (i64)kc * KC);
-#pragma unroll
-          for (int op = 0; op < Plan::NOPS; ++op) {
-            tma_load_2d(st + op * Plan::A_BYTES, op == 0 ? &tmP_big : &tmP_small, &full[s], bc, i0);
-            tma_load_2d(st + Plan::NOPS * Plan::A_BYTES + op * Plan::B_BYTES, op == 0 ? &tmQ_big : &tmQ_small, &full[s], bc, n0);
-          }
+          tma_load_2d(st, &tmP, &full[s], bc, i0);
+          tma_load_2d(st + Plan::A_BYTES, &tmQ, &full[s], bc, n0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -274,10 +268,11 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constan
         int s = 0; uint32_t ph = 0;
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(&full[s], ph);
+          if (NPASS == 3) mbar_wait(&ready[s], ph);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + s * Plan::STAGE_BYTES);
-          const uint32_t a_big = st, a_small = st + Plan::A_BYTES;
-          const uint32_t b_big = st + Plan::NOPS * Plan::A_BYTES, b_small = b_big + Plan::B_BYTES;
+          const uint32_t a_big = st, b_big = st + Plan::A_BYTES;
+          const uint32_t a_small = st + Plan::RAW_BYTES, b_small = a_small + Plan::A_BYTES;
 #pragma unroll
           for (int ks = 0; ks < KC / UMMA_K; ++ks) {
             const uint64_t da = make_sdesc(a_big + ks * 32, 16, SBO, LAYOUT);
@@ -295,6 +290,20 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP_big, const __grid_constan
           }
           umma_commit(&empty[s]);
           if (kc == k_chunks - 1) umma_commit(tfull);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp >= SPLIT_WARP0) {
+      if (NPASS == 3) {       // split both operand tiles (they sit next to each other) in shared memory
+        const int tid = threadIdx.x - SPLIT_WARP0 * 32;
+        int s = 0; uint32_t ph = 0;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(&full[s], ph);
+          uint8_t* st = smem + s * Plan::STAGE_BYTES;
+          split_tile(st, st + Plan::RAW_BYTES, Plan::RAW_BYTES, tid, SPLIT_WARPS * 32);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }

@@ -1,8 +1,8 @@
 // Fused epilogues for the tcgen05 kernels.  In the TMEM accumulator a thread owns ONE batch column and walks
 // over feature rows (CH per tcgen05.ld), so every global access below is a coalesced 128-byte segment per warp
 // and per-row parameters are warp-uniform.  The arithmetic is the reference's, op by op (see epilogues.cuh for
-// the file:line map); only the operand-split outputs (V_big/V_small, Z_small) are extra: they are the pre-split
-// MMA operands of the NEXT product (x = big + small, big representable in tf32).
+// the file:line map).  The only extra output is V_{k+1} = L_k + beta1_{k+1} T_{k+1}, the operand of the next W V
+// product; the 3xTF32 operand split (x = trunc_tf32(x) + small) happens in shared memory inside the consumer.
 //
 // Each functor is used in two phases per CH-row chunk so that the global loads of the chunk are all in flight
 // before the accumulator is read:  load(in, ...) -> tcgen05.ld -> apply(in, acc, ...).
@@ -38,27 +38,14 @@ struct PV {
   }
 };
 
-__device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }
-
-template <int NPASS>
-__device__ __forceinline__ void store_split_rna(float* __restrict__ big, float* __restrict__ small, i64 off, float x) {
-  if (NPASS == 3) {
-    float b = tf32_rna(x);
-    big[off] = b;
-    small[off] = x - b;
-  } else {
-    big[off] = x;
-  }
-}
-
 // T_0 = A Z0 + E0 - X, and V_0 = L0 + beta1_0 * T_0 for the first Z-step
-template <int NPASS, bool PSCALAR>
+template <bool PSCALAR>
 struct UEpiT0 {
   static constexpr int CHUNK = CH;
   struct State { PV<PSCALAR> b1; };
   struct In { float e0[CH], x[CH], l0[CH]; };
   const float* __restrict__ E0; const float* __restrict__ X; const float* __restrict__ L0; float* __restrict__ T0;
-  BP b1; float* __restrict__ Vb; float* __restrict__ Vs; i64 B;
+  BP b1; float* __restrict__ V; i64 B;
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
@@ -80,19 +67,18 @@ struct UEpiT0 {
       const i64 off = (i64)row * B + b;
       const float t = fsub(fadd(v[i], in.e0[i]), in.x[i]);
       T0[off] = t;
-      const float var = fadd(in.l0[i], fmul(st.b1.at(row, b), t));
-      store_split_rna<NPASS>(Vb, Vs, off, var);
+      V[off] = fadd(in.l0[i], fmul(st.b1.at(row, b), t));
     }
   }
 };
 
-// Z_k = act(Z_{k-1} - [ss1*] acc, theta1); Z_small = Z - trunc_tf32(Z) is the second operand part of A Z_k
-template <int NPASS, bool PSCALAR>
+// Z_k = act(Z_{k-1} - [ss1*] acc, theta1)
+template <bool PSCALAR>
 struct UEpiZ {
   static constexpr int CHUNK = CH;
   struct State { PV<PSCALAR> th1; float s1; };
   struct In { float zp[CH]; };
-  const float* __restrict__ Zp; float* __restrict__ Zk; float* __restrict__ Zs; uint8_t* __restrict__ maskZ;
+  const float* __restrict__ Zp; float* __restrict__ Zk; uint8_t* __restrict__ maskZ;
   BP th1; BP ss1; i64 B;
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; }
   __device__ __forceinline__ void end(State&, int, int) const {}
@@ -114,14 +100,13 @@ struct UEpiZ {
       unsigned bits;
       const float z = soft_act(fsub(in.zp[i], wv), st.th1.at(row, b), bits);
       Zk[off] = z;
-      if (NPASS == 3) Zs[off] = z - tf32_trunc(z);
       if (maskZ) maskZ[off] = (uint8_t)bits;
     }
   }
 };
 
-// E_k, T_{k+1}, L_k from acc = A Z_k; then V_{k+1} = L_k + beta1_{k+1} * T_{k+1} (split) unless this is the last layer
-template <int FAM, int NPASS, bool PSCALAR>
+// E_k, T_{k+1}, L_k from acc = A Z_k; then V_{k+1} = L_k + beta1_{k+1} * T_{k+1} unless this is the last layer
+template <int FAM, bool PSCALAR>
 struct UEpiELT {
   static constexpr int CHUNK = CH;
   struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; };
@@ -129,7 +114,7 @@ struct UEpiELT {
   const float* __restrict__ X; const float* __restrict__ Ep; const float* __restrict__ Lp;
   float* __restrict__ Ek; float* __restrict__ Lk; float* __restrict__ Tn; uint8_t* __restrict__ maskE;
   BP b2, ss2, ss2_2, th2, bL;
-  int has_next; BP b1n; float* __restrict__ Vb; float* __restrict__ Vs;
+  int has_next; BP b1n; float* __restrict__ V;
   i64 B;
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
@@ -172,10 +157,7 @@ struct UEpiELT {
       const float l = fadd(lp, fmul(st.bL.at(row, b), t));
       Ek[off] = e; Tn[off] = t; Lk[off] = l;
       if (FAM != DLADMM_FAMILY_C && maskE) maskE[off] = (uint8_t)bits;
-      if (has_next) {
-        const float var = fadd(l, fmul(st.b1n.at(row, b), t));
-        store_split_rna<NPASS>(Vb, Vs, off, var);
-      }
+      if (has_next) V[off] = fadd(l, fmul(st.b1n.at(row, b), t));
     }
   }
 };

@@ -11,11 +11,15 @@
 // every global access of the fused epilogue is a coalesced 128-byte row segment, and per-row parameters are
 // warp-uniform.
 //
-// 3xTF32: operands are pre-split as x = big + small; three MMAs per k-step accumulate
-// big*big + big*small + small*big in the same TMEM accumulator (fp32-level products).
+// 3xTF32: x = big + small with big = the tf32 the tensor core sees; three MMAs per k-step accumulate
+// small*big + big*small + big*big in the same TMEM accumulator (fp32-level products).  Weights are split once per call
+// (round-to-nearest) by the host-side prep kernel.  Activations arrive as plain fp32 through TMA and are split IN SHARED
+// MEMORY by four splitter warps (big = the raw word, which the tensor core truncates to tf32; small = x - trunc(x) written
+// next to it), so no split copy of an activation ever exists in HBM.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; two warps per quadrant split the feature rows).  Persistent over (batch tile, feature tile) pairs,
+// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; two warps per quadrant split the feature rows),
+// warps 10..13 = operand splitters (3xTF32 only).  Persistent over (batch tile, feature tile) pairs,
 // two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -28,7 +32,9 @@ constexpr int TILE_B = 128;      // batch columns per tile (UMMA M)
 constexpr int TILE_N = 256;      // feature rows per tile (UMMA N)
 constexpr int UMMA_K = 8;        // tf32
 constexpr int EPI_WARPS = 8;          // two per TMEM lane quadrant, each owning half of the tile's feature rows
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SPLIT_WARPS = 4;        // shared-memory tf32 splitters (3-pass mode)
+constexpr int SPLIT_WARP0 = 2 + EPI_WARPS;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * SPLIT_WARPS;
 constexpr int EPI_WARP0 = 2;
 constexpr int CH = 16;            // feature rows per epilogue step (one tcgen05.ld.32x32b.x16)
 
@@ -40,6 +46,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -75,6 +82,16 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ float tf32_small(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// small = x - trunc_tf32(x) for `bytes` of an operand tile (any layout: the transform is elementwise)
+__device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* small, int bytes, int tid, int nthreads) {
+  const float4* src = reinterpret_cast<const float4*>(raw);
+  float4* dst = reinterpret_cast<float4*>(small);
+  for (int i = tid; i < bytes / 16; i += nthreads) {
+    const float4 v = src[i];
+    dst[i] = make_float4(tf32_small(v.x), tf32_small(v.y), tf32_small(v.z), tf32_small(v.w));
+  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -173,7 +190,8 @@ struct SmemPlan {
   static constexpr int NOPS = NPASS == 3 ? 2 : 1;                    // big (+ small)
   static constexpr int A_BYTES = TILE_B * KC * 4;                    // one operand part
   static constexpr int B_BYTES = TILE_N * KC * 4;
-  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | A small] [B big | B small]
+  static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
@@ -184,9 +202,8 @@ struct SmemPlan {
 //   epi.apply(state, in, row0, b, valid, acc[CH], n_feat, column_group)
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_constant__ CUtensorMap tmA_small,
-                 const __grid_constant__ CUtensorMap tmB_big, const __grid_constant__ CUtensorMap tmB_small,
-                 GemmShape gs, Epi epi) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_big,
+                 const __grid_constant__ CUtensorMap tmB_small, GemmShape gs, Epi epi) {
   using Plan = SmemPlan<NPASS, KC>;
   constexpr int STAGES = Plan::STAGES;
   constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
@@ -198,15 +215,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
   uint64_t* empty = bars + STAGES;         // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;     // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  uint64_t* ready = bars + 2 * STAGES + 4;   // [STAGES] activation split done (3-pass mode)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 ntiles = gs.n_btiles * gs.n_ntiles;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA_big); prefetch_tmap(&tmB_big);
-    if (NPASS == 3) { prefetch_tmap(&tmA_small); prefetch_tmap(&tmB_small); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB_big);
+    if (NPASS == 3) prefetch_tmap(&tmB_small);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -231,19 +249,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
         for (int kc = 0; kc < gs.k_chunks; ++kc) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Plan::STAGE_BYTES);
+          mbar_expect_tx(&full[s], Plan::TX_BYTES);
+          // activation (raw fp32): 4 boxes of (32 batch columns x KC rows), 128 B per row
 #pragma unroll
-          for (int op = 0; op < Plan::NOPS; ++op) {
-            const CUtensorMap* ma = op == 0 ? &tmA_big : &tmA_small;
-            const CUtensorMap* mb = op == 0 ? &tmB_big : &tmB_small;
-            uint8_t* a_dst = st + op * Plan::A_BYTES;
-            uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES + op * Plan::B_BYTES;
-            // activation: 4 boxes of (32 batch columns x KC rows), 128 B per row
-#pragma unroll
-            for (int g = 0; g < TILE_B / 32; ++g) tma_load_2d(a_dst + g * (KC * 128), ma, &full[s], b0 + g * 32, kc * KC);
-            // weights: one box of (KC k x 256 rows)
-            tma_load_2d(b_dst, mb, &full[s], kc * KC, j0);
-          }
+          for (int g = 0; g < TILE_B / 32; ++g) tma_load_2d(st + g * (KC * 128), &tmA, &full[s], b0 + g * 32, kc * KC);
+          // weights: one box of (KC k x 256 rows) per part
+          uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES;
+          tma_load_2d(b_dst, &tmB_big, &full[s], kc * KC, j0);
+          if (NPASS == 3) tma_load_2d(b_dst + Plan::B_BYTES, &tmB_small, &full[s], kc * KC, j0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -260,6 +273,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
         const uint32_t d_tmem = tmem_base + acc * TILE_N;
         for (int kc = 0; kc < gs.k_chunks; ++kc) {
           mbar_wait(&full[s], ph);
+          if (NPASS == 3) mbar_wait(&ready[s], ph);      // small part of the activation tile written by the splitters
           tc_fence_after();
           const uint32_t st = smem_u32(smem + s * Plan::STAGE_BYTES);
           const uint32_t a_big = st, a_small = st + Plan::A_BYTES;
@@ -287,6 +301,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_big, const __grid_const
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= SPLIT_WARP0) {
+    // ===== operand splitters (3-pass mode): small = x - trunc_tf32(x) of the activation tile, in shared memory =====
+    if (NPASS == 3) {
+      const int tid = threadIdx.x - SPLIT_WARP0 * 32;
+      int s = 0; uint32_t ph = 0;
+      for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kc = 0; kc < gs.k_chunks; ++kc) {
+          mbar_wait(&full[s], ph);                       // TMA bytes landed; the stage was free (producer waited on empty)
+          uint8_t* st = smem + s * Plan::STAGE_BYTES;
+          split_tile(st, st + Plan::A_BYTES, Plan::A_BYTES, tid, SPLIT_WARPS * 32);
+          fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else {

@@ -10,11 +10,12 @@
 
 namespace dladmm {
 
+static int device_sm_count();
+
 struct UWorkspace {
   float *Ab, *As;      // A  (m256 x dp): features of the A Z product on the N side, K = d
   float *Wb, *Ws;      // nW x (d256 x mp): features of the W V product on the N side, K = m
-  float *Vb, *Vs;      // (m x B) split operand V_k = L_{k-1} + beta1_k T_k
-  float *Zs;           // (d x B) small part of Z_k (or of Z0)
+  float *V;            // (m x B) operand V_k = L_{k-1} + beta1_k T_k of the next W V product
   size_t bytes;
   int m256, d256, mp, dp, nW;
 };
@@ -37,9 +38,7 @@ static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   w.As = take((size_t)w.m256 * w.dp);
   w.Wb = take((size_t)w.nW * w.d256 * w.mp);
   w.Ws = take((size_t)w.nW * w.d256 * w.mp);
-  w.Vb = take((size_t)p->m * p->B);
-  w.Vs = take((size_t)p->m * p->B);
-  w.Zs = take((size_t)p->d * p->B);
+  w.V = take((size_t)p->m * p->B);
   w.bytes = off;
   return w;
 }
@@ -52,9 +51,7 @@ static inline bool umma_eligible(const dladmm_problem* p) {
 struct UBwdWorkspace {
   float *Atb, *Ats;    // A^T (d256 x mp): features of A^T dR on the N side, K = m
   float *Wtb, *Wts;    // nW x (m256 x dp): W^T, features of W^T dx1 on the N side, K = d
-  float *cZs;          // (d x B) small part of dx1
-  float *dRs;          // (m x B) small part of dR
-  float *Vb, *Vs;      // (m x B) V_k recomputed per layer
+  float *V;            // (m x B) V_k recomputed per layer
   float *part;         // parameter-gradient partial sums of the tcgen05 epilogues
   size_t bytes;
   int m256, d256, mp, dp, nW, ngroups, prow, nentries;
@@ -81,10 +78,7 @@ static UBwdWorkspace ucarve_bwd(const dladmm_problem* p, char* base) {
   w.Ats = take((size_t)w.d256 * w.mp);
   w.Wtb = take((size_t)w.nW * w.m256 * w.dp);
   w.Wts = take((size_t)w.nW * w.m256 * w.dp);
-  w.cZs = take((size_t)p->d * p->B);
-  w.dRs = take((size_t)p->m * p->B);
-  w.Vb = take((size_t)p->m * p->B);
-  w.Vs = take((size_t)p->m * p->B);
+  w.V = take((size_t)p->m * p->B);
   w.part = take(std::max((size_t)SL_COUNT * w.ngroups * w.prow, (size_t)SL_COUNT * w.nentries));
   w.bytes = off;
   return w;
@@ -116,18 +110,6 @@ static __global__ void __launch_bounds__(256) prep_split_kernel(SplitJobs jobs, 
     } else {
       jb.big[(i64)r * Cpad + c] = v;
     }
-  }
-}
-
-static __global__ void __launch_bounds__(256) split_trunc_kernel(const float* __restrict__ src, float* __restrict__ small, i64 n) {
-  i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) * 4;
-  if (i + 3 < n) {
-    float4 v = *reinterpret_cast<const float4*>(src + i);
-    float4 s = make_float4(v.x - umma::tf32_trunc(v.x), v.y - umma::tf32_trunc(v.y), v.z - umma::tf32_trunc(v.z),
-                           v.w - umma::tf32_trunc(v.w));
-    *reinterpret_cast<float4*>(small + i) = s;
-  } else {
-    for (; i < n; ++i) small[i] = src[i] - umma::tf32_trunc(src[i]);
   }
 }
 
@@ -184,10 +166,9 @@ static __global__ void __launch_bounds__(256) prep_split_t_kernel(SplitJobs jobs
   }
 }
 
-// V_k = L_{k-1} + beta1_k * T_k as split MMA operand (backward recomputation)
-template <int NPASS>
+// V_k = L_{k-1} + beta1_k * T_k (backward recomputation of the dW operand)
 static __global__ void __launch_bounds__(256) make_v_kernel(const float* __restrict__ L, const float* __restrict__ T, BP b1, int rows,
-                                                            i64 B, float* __restrict__ Vb, float* __restrict__ Vs) {
+                                                            i64 B, float* __restrict__ V) {
   const i64 quads = (B + 3) / 4;
   const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
   if (idx >= quads * rows) return;
@@ -199,14 +180,10 @@ static __global__ void __launch_bounds__(256) make_v_kernel(const float* __restr
   const i64 off = (i64)row * B + col;
   Quad l = load4(L, off, nv, vec), t = load4(T, off, nv, vec);
   float b[4]; bp_at4(b1, row, col, b);
-  float vb[4], vs[4];
+  float v[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float v = fadd(l.v[j], fmul(b[j], t.v[j]));
-    if (NPASS == 3) { vb[j] = umma::tf32_rna(v); vs[j] = v - vb[j]; } else { vb[j] = v; vs[j] = 0.f; }
-  }
-  store4(Vb, off, vb, nv, vec);
-  if (NPASS == 3) store4(Vs, off, vs, nv, vec);
+  for (int j = 0; j < 4; ++j) v[j] = fadd(l.v[j], fmul(b[j], t.v[j]));
+  store4(V, off, v, nv, vec);
 }
 
 static int device_sm_count() {
@@ -223,20 +200,19 @@ static int device_sm_count() {
 // C[j,b] = sum_k Wt[j,k] Act[k,b] with a fused epilogue.  act_* are (Kdim x B) batch-contiguous; w_* are prepared
 // (n_pad x k_pad) K-major arrays.
 template <class Epi, int NPASS>
-static int launch_umma(int kind, const float* act_big, const float* act_small, int Kdim, const float* w_big, const float* w_small,
+static int launch_umma(int kind, const float* act, int Kdim, const float* w_big, const float* w_small,
                        int n_pad, int k_pad, int n_feat, i64 B, const Epi& epi, cudaStream_t st, int grid_override = 0) {
   constexpr int KC = NPASS == 3 ? 16 : 32;
   using Plan = umma::SmemPlan<NPASS, KC>;
-  CUtensorMap tAb, tAs, tBb, tBs;
+  CUtensorMap tA, tBb, tBs;
   int rc;
-  if ((rc = umma::make_tmap_2d(&tAb, act_big, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = umma::make_tmap_2d(&tA, act, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if ((rc = umma::make_tmap_2d(&tBb, w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
   if (NPASS == 3) {
-    if ((rc = umma::make_tmap_2d(&tAs, act_small, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     if ((rc = umma::make_tmap_2d(&tBs, w_small, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
   } else {
-    tAs = tAb; tBs = tBb;
+    tBs = tBb;
   }
   umma::GemmShape gs;
   gs.n_feat = n_feat;
@@ -254,7 +230,7 @@ static int launch_umma(int kind, const float* act_big, const float* act_small, i
   const int grid = grid_override > 0 ? grid_override : (int)std::min<i64>(ntiles, device_sm_count());
   {
     LaunchScope ls(kind, st);
-    kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tAb, tAs, tBb, tBs, gs, epi);
+    kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tA, tBb, tBs, gs, epi);
   }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
@@ -269,35 +245,28 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   if ((rc = uprepare_weights<NPASS>(p, w, st))) return rc;
   // T_0 = A Z0 + E0 - X (+ V_0)
   {
-    if (NPASS == 3) {
-      i64 n = (i64)d * B;
-      { LaunchScope ls(DLADMM_KIND_PREP, st); split_trunc_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(p->Z0, w.Zs, n); }
-      DL_CUDA(cudaGetLastError());
-    }
-    umma::UEpiT0<NPASS, PS> epi{p->E0, p->X, p->L0, s.Tslab(0), make_bp(p->layers[0].beta1), w.Vb, w.Vs, B};
-    if ((rc = launch_umma<umma::UEpiT0<NPASS, PS>, NPASS>(DLADMM_KIND_GEMM_T0, p->Z0, w.Zs, d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st)))
-      return rc;
+    umma::UEpiT0<PS> epi{p->E0, p->X, p->L0, s.Tslab(0), make_bp(p->layers[0].beta1), w.V, B};
+    if ((rc = launch_umma<umma::UEpiT0<PS>, NPASS>(DLADMM_KIND_GEMM_T0, p->Z0, d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st))) return rc;
   }
   for (int k = 0; k < p->K; ++k) {
     const dladmm_layer& l = p->layers[k];
     const size_t wi = (size_t)weight_index(p, k);
     {
-      umma::UEpiZ<NPASS, PS> epi{s.Zin(k), s.Zout(k), w.Zs, s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
-      if ((rc = launch_umma<umma::UEpiZ<NPASS, PS>, NPASS>(DLADMM_KIND_GEMM_Z, w.Vb, w.Vs, m, w.Wb + wi * w.d256 * w.mp,
-                                                       w.Ws + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st)))
+      umma::UEpiZ<PS> epi{s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
+      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, w.V, m, w.Wb + wi * w.d256 * w.mp, w.Ws + wi * w.d256 * w.mp,
+                                                    w.d256, w.mp, d, B, epi, st)))
         return rc;
     }
     {
-      umma::UEpiELT<FAM, NPASS, PS> epi;
+      umma::UEpiELT<FAM, PS> epi;
       epi.X = p->X; epi.Ep = s.Ein(k); epi.Lp = s.Lin(k);
       epi.Ek = s.Eout(k); epi.Lk = s.Lout(k); epi.Tn = s.Tslab(k + 1); epi.maskE = s.mE(k);
       epi.b2 = make_bp(l.beta2); epi.ss2 = make_bp(l.ss2); epi.ss2_2 = make_bp(l.ss2_2); epi.th2 = make_bp(l.theta2);
       epi.bL = make_bp(betaL(p, l));
       epi.has_next = k + 1 < p->K;
       epi.b1n = make_bp(p->layers[k + 1 < p->K ? k + 1 : k].beta1);
-      epi.Vb = w.Vb; epi.Vs = w.Vs; epi.B = B;
-      if ((rc = launch_umma<umma::UEpiELT<FAM, NPASS, PS>, NPASS>(DLADMM_KIND_GEMM_ELT, s.Zout(k), w.Zs, d, w.Ab, w.As, w.m256, w.dp, m, B,
-                                                              epi, st)))
+      epi.V = w.V; epi.B = B;
+      if ((rc = launch_umma<umma::UEpiELT<FAM, PS>, NPASS>(DLADMM_KIND_GEMM_ELT, s.Zout(k), d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st)))
         return rc;
     }
   }
@@ -305,21 +274,14 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
 }
 
 template <int NPASS>
-static int launch_nt(const float* P, const float* Ps, int M, const float* Q, const float* Qs, int N, i64 B, const float* s1ptr,
-                     float* C, int ldc, cudaStream_t st) {
+static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const float* s1ptr, float* C, int ldc, cudaStream_t st) {
   constexpr int KC = NPASS == 3 ? 16 : 32;
   using Plan = umma::NtPlan<NPASS, KC>;
   const CUtensorMapSwizzle sw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUtensorMap tP, tPs, tQ, tQs;
+  CUtensorMap tP, tQ;
   int rc;
   if ((rc = umma::make_tmap_2d(&tP, P, M, B, B, KC, 128, sw))) return rc;
   if ((rc = umma::make_tmap_2d(&tQ, Q, N, B, B, KC, umma::TILE_N, sw))) return rc;
-  if (NPASS == 3) {
-    if ((rc = umma::make_tmap_2d(&tPs, Ps, M, B, B, KC, 128, sw))) return rc;
-    if ((rc = umma::make_tmap_2d(&tQs, Qs, N, B, B, KC, umma::TILE_N, sw))) return rc;
-  } else {
-    tPs = tP; tQs = tQ;
-  }
   const int mt = (M + 127) / 128, nt = (N + umma::TILE_N - 1) / umma::TILE_N;
   int split = std::max(1, device_sm_count() / (mt * nt));
   i64 chunk = round_up64((B + split - 1) / split, KC);
@@ -334,7 +296,7 @@ static int launch_nt(const float* P, const float* Ps, int M, const float* Q, con
   }
   {
     LaunchScope ls(DLADMM_KIND_BWD_GEMM_DW, st);
-    kern<<<dim3(mt, split, nt), umma::NUM_THREADS, Plan::TOTAL, st>>>(tP, tPs, tQ, tQs, ns, s1ptr, -1.f, C);
+    kern<<<dim3(mt, split, nt), umma::NUM_THREADS, Plan::TOTAL, st>>>(tP, tQ, ns, s1ptr, -1.f, C);
   }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
@@ -377,11 +339,6 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
     ReduceJobs jobs; jobs.n = 0;
     add_m1_jobs(p, jobs, p->layers[K - 1]);
     if ((rc = launch_reduce(jobs, sw, st))) return rc;
-    if (NPASS == 3) {
-      i64 n = (i64)m * B;
-      { LaunchScope ls(DLADMM_KIND_PREP, st); split_trunc_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(sw.dR, w.dRs, n); }
-      DL_CUDA(cudaGetLastError());
-    }
   }
   // one grid for both activation-side products so that the per-warp partial entries line up
   const i64 nbt = (B + umma::TILE_B - 1) / umma::TILE_B;
@@ -393,25 +350,24 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
     const dladmm_layer& l = p->layers[k];
     const size_t wi = (size_t)weight_index(p, k);
     {
-      umma::UEpiBG1<NPASS, PS> epi;
+      umma::UEpiBG1<PS> epi;
       epi.gZ = g->gZ ? g->gZ + s.zs * k : nullptr;
       epi.cZin = k == K - 1 ? nullptr : sw.cZ;
       epi.maskZ = s.mZ(k);
       epi.th1 = make_bp(l.theta1);
-      epi.dx1 = sw.cZ; epi.dx1s = w.cZs; epi.ro = ro; epi.B = B;
-      if ((rc = launch_umma<umma::UEpiBG1<NPASS, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DZ, sw.dR, w.dRs, m, w.Atb, w.Ats, w.d256, w.mp, d, B,
-                                                             epi, st, grid)))
+      epi.dx1 = sw.cZ; epi.ro = ro; epi.B = B;
+      if ((rc = launch_umma<umma::UEpiBG1<PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DZ, sw.dR, m, w.Atb, w.Ats, w.d256, w.mp, d, B, epi, st, grid)))
         return rc;
     }
     if (l.gW) {
       const i64 quads = (B + 3) / 4;
       { LaunchScope ls(DLADMM_KIND_PREP, st);
-        make_v_kernel<NPASS><<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(s.Lin(k), s.Tslab(k), make_bp(l.beta1), m, B, w.Vb, w.Vs); }
+        make_v_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(s.Lin(k), s.Tslab(k), make_bp(l.beta1), m, B, w.V); }
       DL_CUDA(cudaGetLastError());
-      if ((rc = launch_nt<NPASS>(sw.cZ, w.cZs, d, w.Vb, w.Vs, m, B, l.ss1.ptr, l.gW, m, st))) return rc;
+      if ((rc = launch_nt<NPASS>(sw.cZ, d, w.V, m, B, l.ss1.ptr, l.gW, m, st))) return rc;
     }
     {
-      umma::UEpiBG2<FAM, NPASS, PS> epi;
+      umma::UEpiBG2<FAM, PS> epi;
       epi.Lp = s.Lin(k); epi.Tk = s.Tslab(k);
       epi.b1 = make_bp(l.beta1); epi.ss1 = make_bp(l.ss1);
       epi.cLin = sw.cL; epi.cEin = sw.cE;
@@ -424,10 +380,10 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       epi.gT = g->gT ? g->gT + s.ms * (j + 1) : nullptr;
       epi.bL = make_bp(betaL(p, lj)); epi.b2 = make_bp(lj.beta2); epi.ss2 = make_bp(lj.ss2); epi.ss2_2 = make_bp(lj.ss2_2);
       epi.th2 = make_bp(lj.theta2);
-      epi.dR = sw.dR; epi.dRs = w.dRs; epi.cE = sw.cE; epi.cL = sw.cL;
+      epi.dR = sw.dR; epi.cE = sw.cE; epi.cL = sw.cL;
       epi.ro = ro; epi.B = B;
-      if ((rc = launch_umma<umma::UEpiBG2<FAM, NPASS, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, w.cZs, d, w.Wtb + wi * w.m256 * w.dp,
-                                                                  w.Wts + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
+      if ((rc = launch_umma<umma::UEpiBG2<FAM, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, d, w.Wtb + wi * w.m256 * w.dp,
+                                                           w.Wts + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
         return rc;
     }
     ReduceJobs jobs; jobs.n = 0;

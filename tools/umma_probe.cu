@@ -60,10 +60,9 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   CK(cudaMemcpy(dA, Act.data(), Act.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dAs, As.data(), As.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xFF, (size_t)n_feat * B * 4));
-  CUtensorMap tAb, tAs, tBb, tBs;
+  CUtensorMap tAb, tBb, tBs;
   int rc = 0;
   rc |= make_tmap_2d(&tAb, dA, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  rc |= make_tmap_2d(&tAs, dAs, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   rc |= make_tmap_2d(&tBb, dWb, npad, kpad, kpad, KC, TILE_N, wsw);
   rc |= make_tmap_2d(&tBs, dWs, npad, kpad, kpad, KC, TILE_N, wsw);
@@ -78,7 +77,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
   i64 ntiles = gs.n_btiles * gs.n_ntiles;
   int grid = (int)(ntiles < nsm ? ntiles : nsm);
-  kern<<<grid, NUM_THREADS, smem>>>(tAb, tAs, tBb, tBs, gs, epi);
+  kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, gs, epi);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> C((size_t)n_feat * B);
@@ -94,7 +93,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   if (reps > 0) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) kern<<<grid, NUM_THREADS, smem>>>(tAb, tAs, tBb, tBs, gs, epi);
+    for (int r = 0; r < reps; ++r) kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, gs, epi);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
   }
