@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdladmm.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
@@ -35,7 +35,9 @@ class Problem(C.Structure):
 
 
 class Cotangents(C.Structure):
-    _fields_ = [("gZ", C.c_void_p), ("gE", C.c_void_p), ("gL", C.c_void_p), ("gT", C.c_void_p)]
+    _fields_ = [("gZ", C.c_void_p), ("gE", C.c_void_p), ("gL", C.c_void_p), ("gT", C.c_void_p),
+                ("loss_kind", C.c_int32), ("loss_alpha", C.c_float), ("loss_layer_weight", C.POINTER(C.c_float)),
+                ("loss_scale", C.c_void_p)]
 
 
 class Caps(C.Structure):

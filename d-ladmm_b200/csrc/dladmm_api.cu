@@ -303,6 +303,8 @@ static M1Args make_m1(const dladmm_problem* p, const dladmm_cotangents* g, const
   a.th2 = make_bp(l.theta2);
   a.dR = w.dR; a.cE = w.cE; a.cL = w.cL;
   a.B = p->B;
+  a.lw = 0.f; a.lscale = nullptr;
+  if (g->loss_kind == 1 && g->loss_scale && g->loss_layer_weight) { a.lw = g->loss_layer_weight[j]; a.lscale = g->loss_scale; }
   return a;
 }
 
@@ -328,7 +330,9 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
     // BG1: dZ_k = gZ_k + carried + A^T dR ; dx1 -> cZ
     {
       BPlain bl{w.dR, B};
-      EpiBG1 epi{g->gZ ? g->gZ + s.zs * k : nullptr, k == K - 1 ? nullptr : w.cZ, s.mZ(k), make_bp(l.theta1), w.cZ, B};
+      const bool lossz = g->loss_kind == 1 && g->loss_scale && g->loss_layer_weight;
+      EpiBG1 epi{g->gZ ? g->gZ + s.zs * k : nullptr, k == K - 1 ? nullptr : w.cZ, s.mZ(k), make_bp(l.theta1), w.cZ, B,
+                 s.Zout(k), lossz ? g->loss_alpha * g->loss_layer_weight[k] : 0.f, lossz ? g->loss_scale : nullptr};
       if ((rc = launch_simt(DLADMM_KIND_BWD_GEMM_DZ, d, B, m, w.Atp, w.mp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
     }
     // BG3: gW -= s1 * dx1 * V_k^T
@@ -482,6 +486,11 @@ int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* s
   int rc = validate(p, 1);
   if (rc) return rc;
   if (!g) { set_error("cotangents is NULL"); return DLADMM_ERR_INVALID; }
+  if (g->loss_kind != 0 && g->loss_kind != 1) { set_error("unknown loss_kind %d", g->loss_kind); return DLADMM_ERR_INVALID; }
+  if (g->loss_kind == 1 && (!g->loss_layer_weight || !g->loss_scale)) {
+    set_error("loss_kind 1 needs loss_layer_weight (host) and loss_scale (device)");
+    return DLADMM_ERR_INVALID;
+  }
   if (p->B == 0) return DLADMM_OK;
   if ((rc = check_device())) return rc;
   cudaStream_t st = (cudaStream_t)stream;

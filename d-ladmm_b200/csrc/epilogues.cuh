@@ -20,6 +20,8 @@ enum { SL_BL = 0, SL_TH2 = 1, SL_SS2 = 2, SL_B2 = 3, SL_B1 = 4, SL_SS1 = 5, SL_T
 
 // accumulate a parameter-gradient contribution: row-reduced params go to `red`, per-slot params
 // (main_lena.py:35-36, (m x bs)) go straight to their gradient with an atomic.
+__device__ __forceinline__ float sgn(float x) { return (x > 0.f ? 1.f : 0.f) - (x < 0.f ? 1.f : 0.f); }
+
 __device__ __forceinline__ void pgrad(const BP& q, int row, i64 col, float val, float& red) {
   if (q.g == nullptr) return;
   if (q.period) atomicAdd(q.g + (i64)row * q.rs + col % q.period, val);
@@ -127,6 +129,7 @@ struct M1Args {
   BP bL, b2, ss2, ss2_2, th2;
   float* dR; float* cE; float* cL;   // outputs (m,B)
   i64 B;
+  float lw; const float* lscale;     // fused L1-L1 loss: cotangent lw*scale*sign(E_j - T_{j+1}) on E_j, minus that on T_{j+1}
 };
 
 template <int FAM>
@@ -144,6 +147,11 @@ __device__ __forceinline__ void m1_quad(const M1Args& a, int row, i64 col, float
     for (int j = 0; j < 4; ++j) dT[j] += g.v[j]; }
   Quad tn = load4(a.Tn, off, nvalid, vec), lp = load4(a.Lp, off, nvalid, vec);
   Quad ek = load4(a.Ek, off, nvalid, vec);
+  if (a.lscale) {
+    const float sc = a.lw * __ldg(a.lscale);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float s = sc * sgn(ek.v[j] - tn.v[j]); dE[j] += s; dT[j] -= s; }
+  }
   float vbL[4]; bp_at4(a.bL, row, col, vbL);
   float dR[4], nE[4], nL[4];
   unsigned bits[4] = {0, 0, 0, 0};
@@ -217,9 +225,13 @@ struct EpiBG1 {
   BP th1;
   float* dx1;             // out (d,B): dZ_k * (m+ + m-), also the carried dZ_{k-1}
   i64 B;
+  const float* Zk; float lz; const float* lscale;   // fused L1-L1 loss: cotangent lz*scale*sign(Z_k) on Z_k
   __device__ __forceinline__ void operator()(int row, i64 col, const float (&acc)[4], int nvalid, bool vec, float* red) const {
     i64 off = (i64)row * B + col;
     float dz[4] = {acc[0], acc[1], acc[2], acc[3]};
+    if (lscale) { Quad z = load4(Zk, off, nvalid, vec); const float sc = lz * __ldg(lscale);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dz[j] += sc * sgn(z.v[j]); }
     if (gZ) { Quad g = load4(gZ, off, nvalid, vec);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dz[j] += g.v[j]; }

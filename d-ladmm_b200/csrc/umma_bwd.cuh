@@ -45,11 +45,15 @@ __device__ __forceinline__ void red_finish(const RedOut& ro, const int (&slots)[
 template <bool PS>
 struct UEpiBG1 {
   static constexpr int CHUNK = CH;
-  struct State { float red[1]; int lane; };
-  struct In { float gz[CH], cz[CH]; unsigned mk[CH]; };
+  struct State { float red[1]; int lane; float lsc; };
+  struct In { float gz[CH], cz[CH], zk[CH]; unsigned mk[CH]; };
   const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
   BP th1; float* dx1; RedOut ro; i64 B;
-  __device__ __forceinline__ void begin(State& st) const { st.red[0] = 0.f; st.lane = threadIdx.x & 31; }
+  const float* __restrict__ Zk; float lz; const float* __restrict__ lscale;   // fused L1-L1 loss cotangent on Z_k
+  __device__ __forceinline__ void begin(State& st) const {
+    st.red[0] = 0.f; st.lane = threadIdx.x & 31;
+    st.lsc = lscale ? lz * __ldg(lscale) : 0.f;
+  }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[1] = {SL_TH1};
     if (th1.g && th1.period == 0) red_finish<PS, 1>(ro, slots, st.red, entry, lane);
@@ -60,6 +64,7 @@ struct UEpiBG1 {
       const bool ok = valid && row0 + i < n_feat;
       const i64 off = (i64)(row0 + i) * B + b;
       in.gz[i] = (ok && gZ) ? __ldg(gZ + off) : 0.f;
+      in.zk[i] = (ok && lscale) ? __ldg(Zk + off) : 0.f;   // raw value only: nothing may consume a load in this phase
       in.cz[i] = (ok && cZin) ? cZin[off] : 0.f;
       in.mk[i] = ok ? (unsigned)__ldg(maskZ + off) : 0u;
     }
@@ -72,7 +77,8 @@ struct UEpiBG1 {
       if (row >= n_feat) continue;                  // warp-uniform
       const bool ok = valid;
       const i64 off = (i64)row * B + b;
-      const float dz = v[i] + in.gz[i] + in.cz[i];
+      float dz = v[i] + in.gz[i] + in.cz[i];
+      if (lscale) dz += st.lsc * sgn(in.zk[i]);
       const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_contrib<PS>(th1, ro, SL_TH1, st.red[0], row, b, group, ok, dz * (mn - mp), st.lane);
@@ -85,9 +91,9 @@ struct UEpiBG1 {
 // writes dR for the next A^T dR product, carried dE and dL.
 template <int FAM, bool PS>
 struct UEpiBG2 {
-  static constexpr int CHUNK = 8;
-  static constexpr int C8 = 8;
-  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; };
+  static constexpr int CHUNK = 4;     // 11 input arrays per element: keep the register footprint of a chunk small
+  static constexpr int C8 = 4;
+  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; };
   struct In { float lp[C8], tk[C8], cl[C8], ce[C8], ek[C8], ep[C8], lpp[C8], gl[C8], ge[C8], gt[C8]; unsigned mk[C8]; };
   // layer k
   const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
@@ -98,12 +104,14 @@ struct UEpiBG2 {
   BP bL, b2, ss2, ss2_2, th2;
   float* __restrict__ dR; float* cE; float* cL;
   RedOut ro; i64 B;
+  float lw; const float* __restrict__ lscale;       // fused L1-L1 loss cotangents on E_{k-1} / T_k
   __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
     for (int r = 0; r < 6; ++r) st.red[r] = 0.f;
     st.b1.init(b1); st.bL.init(bL); st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2);
     st.s1 = ss1.p ? __ldg(ss1.p) : 1.f;
     st.lane = threadIdx.x & 31;
+    st.lsc = lscale ? lw * __ldg(lscale) : 0.f;
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
@@ -151,6 +159,7 @@ struct UEpiBG2 {
       float dE = in.ce[i] + in.ge[i];
       dT += in.gt[i];
       const float tn = tk, ek = in.ek[i], lpp = in.lpp[i];
+      if (lscale) { const float sl = st.lsc * sgn(ek - tn); dE += sl; dT -= sl; }
       const float vbL = st.bL.at(row, b);
       red_contrib<PS>(bL, ro, SL_BL, st.red[0], row, b, group, ok, dL * tn, st.lane);
       const float dTt = dT + vbL * dL;

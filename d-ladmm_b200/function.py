@@ -177,3 +177,58 @@ class UnrolledLADMM(torch.autograd.Function):
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
         return (None, None, None, None, None, None) + tuple(grads)
+
+
+class UnrolledLADMML1L1(torch.autograd.Function):
+    """forward(spec, alpha, weights, A, X, Z0, E0, L0, *params) -> (loss, Z, E, L, T) with
+
+        loss = (1/B) * sum_k weights[k] * sum_b ( alpha*||Z_k[:,b]||_1 + ||x[:,b] - A Z_k[:,b]||_1 )
+
+    the reference's training objective (main_syn_l1l1_scalar.py:289-299).  The loss cotangents are generated
+    inside the backward kernels (dladmm_cotangents.loss_kind = 1): no per-layer A@Z products, no (K,d,B)/(K,m,B)
+    gradient stacks, no elementwise autograd graph.  The returned iterates are not differentiable."""
+
+    @staticmethod
+    def forward(ctx, spec, alpha, weights, A, X, Z0, E0, L0, *params):
+        from .objective import l1l1_objective
+        Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True)
+        B = X.shape[1]
+        obj = l1l1_objective(Z, E, T, alpha)
+        w = torch.tensor([float(v) for v in weights], dtype=torch.float32, device=X.device)
+        loss = (obj * w).sum() / float(max(B, 1))
+        ctx.spec, ctx.alpha, ctx.weights, ctx.B = spec, float(alpha), [float(v) for v in weights], B
+        ctx.has_maskE = maskE is not None
+        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ] + ([maskE] if maskE is not None else []) + list(params)
+        ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(Z, E, L, T)
+        return loss, Z, E, L, T
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        lib = _lib.load()
+        spec = ctx.spec
+        saved = ctx.saved_tensors
+        A, X, Z0, E0, L0, Z, E, L, T, maskZ = saved[:10]
+        off = 10
+        maskE = None
+        if ctx.has_maskE:
+            maskE = saved[10]
+            off = 11
+        params = [t.contiguous() for t in saved[off:]]
+        needs = ctx.needs_input_grad[8:]
+        grads = [torch.zeros_like(t) if needs[i] else None for i, t in enumerate(params)]
+        scale = (gloss.detach().to(torch.float32) / float(max(ctx.B, 1))).reshape(1).contiguous()
+        cot = _lib.Cotangents()
+        cot.loss_kind = 1
+        cot.loss_alpha = ctx.alpha
+        warr = (C.c_float * spec.K)(*ctx.weights)
+        cot.loss_layer_weight = C.cast(warr, C.POINTER(C.c_float))
+        cot.loss_scale = scale.data_ptr()
+        layers = _build_layers(spec, params, grads)
+        dev = X.device
+        with torch.cuda.device(dev):
+            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True)
+            _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
+            ws.record_stream(torch.cuda.current_stream(dev))
+            scale.record_stream(torch.cuda.current_stream(dev))
+        return (None,) * 8 + tuple(grads)

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .function import LayerSpec, UnrolledLADMM, run_forward
+from .function import LayerSpec, UnrolledLADMM, UnrolledLADMML1L1, run_forward
 
 _FAMILY = {"lena": _lib.FAMILY_A, "ltheta": _lib.FAMILY_A, "scalar": _lib.FAMILY_B, "full": _lib.FAMILY_B,
            "tied": _lib.FAMILY_B, "lasso": _lib.FAMILY_C}
@@ -201,6 +201,28 @@ class DLADMMNet(nn.Module):
         if _RETURNS_T[self.variant]:
             return Zl, El, Ll, Tl
         return Zl, El, Ll
+
+
+    def _as_lists(self, Z, E, L, T):
+        Zl, El, Ll, Tl = list(Z.unbind(0)), list(E.unbind(0)), list(L.unbind(0)), list(T.unbind(0))
+        return (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)
+
+    def l1l1_loss(self, x, alpha, layer_weights=None):
+        """Fused training objective of the reference drivers (main_syn_l1l1_scalar.py:289-299):
+
+            loss = sum_k w_k * ( alpha * mean_b ||Z_k[:,b]||_1 + mean_b ||x[:,b] - A Z_k[:,b]||_1 )
+
+        with w_k = layer_weights[k] (the scripts use 0.6**epoch for k < K-1 and 1 for the last layer).
+        Returns (loss, outputs) where `outputs` is what forward(x) returns, detached.  loss.backward() runs
+        the library's backward with the loss cotangents generated inside the kernels."""
+        if not x.is_cuda:
+            raise RuntimeError("DLADMMNet.l1l1_loss needs a CUDA tensor: d-ladmm_b200 has no CPU path")
+        spec, params = self._spec_and_params()
+        w = [1.0] * self.layers if layer_weights is None else [float(v) for v in layer_weights]
+        if len(w) != self.layers:
+            raise ValueError("layer_weights must have one entry per layer")
+        loss, Z, E, L, T = UnrolledLADMML1L1.apply(spec, float(alpha), w, self.A, x, self.Z0, self.E0, self.L0, *params)
+        return loss, self._as_lists(Z, E, L, T)
 
 
 class DLADMMNetScalar(DLADMMNet):

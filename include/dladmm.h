@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLADMM_ABI_VERSION 1
+#define DLADMM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DLADMM_API __attribute__((visibility("default")))
@@ -119,6 +119,14 @@ typedef struct dladmm_cotangents {
   const float* gE;        /* (K,m,B)   */
   const float* gL;        /* (K,m,B)   */
   const float* gT;        /* (K+1,m,B) */
+  /* Optional fused training loss (adds its cotangents inside the backward kernels, nothing is materialised):
+   *   loss = scale0 * sum_k w_k * sum_b ( alpha*||Z_k[:,b]||_1 + ||X[:,b] - A Z_k[:,b]||_1 )
+   * i.e. the per-layer L1-L1 objective of main_syn_l1l1_scalar.py:289-299 with X - A Z_k taken as E_k - T_{k+1}.
+   * loss_scale points to ONE device float = d(final loss)/d(loss) * scale0 (e.g. upstream gradient / B). */
+  int32_t loss_kind;                /* 0: none, 1: L1-L1 objective */
+  float loss_alpha;
+  const float* loss_layer_weight;   /* HOST array of K floats w_k */
+  const float* loss_scale;          /* DEVICE pointer to one float */
 } dladmm_cotangents;
 
 typedef struct dladmm_caps {

@@ -156,3 +156,36 @@ def test_learned_forward_equals_classical_ladmm_on_gpu(precision):
     for k in range(K):
         assert (Z[k].cpu().double() - Zk[k]).abs().max() < tol * max(1.0, Zk[k].abs().max().item())
         assert (E[k].cpu().double() - Ek[k]).abs().max() < tol * max(1.0, Ek[k].abs().max().item())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("variant", ["scalar", "full", "tied", "lasso", "ltheta"])
+def test_fused_l1l1_loss_matches_reference_training_objective(variant, precision):
+    """model.l1l1_loss: loss value and every parameter gradient against autograd of the reference's own
+    training loss (main_syn_l1l1_scalar.py:289-299, with its separate A @ Z_k products) in fp64."""
+    _skip_if_unavailable(precision)
+    m, d, B, K = 60, 100, 64, 5
+    A, X = syn(m, d, B, seed=33)
+    gen = torch.Generator().manual_seed(5)
+    Z0 = torch.rand(d, B, generator=gen) / d
+    E0 = torch.zeros(m, B); L0 = torch.zeros(m, B)
+    model = dl.VARIANT_CLASSES[variant](m, 1, d, B, A, Z0, E0, L0, K, precision=precision)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    alpha, decay = 0.001, 0.6 ** 3
+    w = [decay] * (K - 1) + [1.0]
+    loss, outs = model.l1l1_loss(X.cuda(), alpha, w)
+    (2.0 * loss).backward()                                   # non-unit upstream gradient
+    assert not outs[0][0].requires_grad and len(outs[0]) == K
+    d64 = lambda t: t.double()
+    sd64 = {k: d64(v) for k, v in sd.items()}
+    lref, gref = orc.autograd_grads(variant, sd64, d64(A), d64(X), d64(Z0), d64(E0), d64(L0), K,
+                                    lambda Z, E, L, T: orc.l1l1_loss(Z, E, L, T, d64(A), d64(X), alpha=alpha, decay=decay))
+    assert abs(loss.item() - lref.item()) < (1e-4 if precision != "tf32" else 2e-2) * abs(lref.item())
+    for n, p in model.named_parameters():
+        if precision == "tf32":
+            assert torch.isfinite(p.grad).all(), n
+            continue
+        # (1,1) parameters: the gradient is a sum over all (rows x B) entries with cancellation, so hold it to an
+        # absolute floor instead of a relative error on a number that may be ~0
+        floor = 2e-3 if p.numel() == 1 else 1e-5
+        assert rel_l2(p.grad.cpu(), 2.0 * gref[n], floor=floor) < 5 * GRAD_TOL[precision], n
