@@ -1,6 +1,7 @@
 // C-ABI entry points of libdladmm.so (see include/dladmm.h) and the per-layer launch schedule.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -38,6 +39,13 @@ LaunchScope::LaunchScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_), re
 }
 LaunchScope::~LaunchScope() {
   if (rec) cudaEventRecord(g_prof[(size_t)rec - 1].b, st);
+  static int dbg = -1;          // DLADMM_DEBUG_SYNC=1: synchronise and report after every launch (debugging aid)
+  if (dbg < 0) { const char* e = getenv("DLADMM_DEBUG_SYNC"); dbg = (e && e[0] == '1') ? 1 : 0; }
+  if (dbg) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, "[dladmm] launch kind %d -> %s\n", kind, cudaGetErrorString(e));
+    fflush(stderr);
+  }
 }
 
 // ---- workspace carving -------------------------------------------------------------------------

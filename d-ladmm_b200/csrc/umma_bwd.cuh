@@ -41,45 +41,50 @@ __device__ __forceinline__ void red_finish(const RedOut& ro, const int (&slots)[
   }
 }
 
+// rank of array i among the present ones (its position in the staged slot), -1 if absent
+__device__ __forceinline__ int slot_rank(uint32_t mask, int i) { return (mask >> i) & 1u ? __popc(mask & ((1u << i) - 1u)) : -1; }
+
 // dZ_k = gZ_k + carried + A^T dR ; dx1 = dZ_k * (m+ + m-) ; dtheta1 ; dx1 is the operand of the next two products
 template <bool PS>
 struct UEpiBG1 {
-  static constexpr int CHUNK = CH;
-  struct State { float red[1]; int lane; float lsc; };
-  struct In { float gz[CH], cz[CH], zk[CH]; unsigned mk[CH]; };
+  static constexpr int CHUNK = 8;
+  static constexpr int NIN = 3;                    // gZ_k, carried dZ, Z_k (fused loss) -- each optional
+  struct State { float red[1]; int lane; float lsc; int o_gz, o_cz, o_zk; };
+  struct Pre { unsigned mk[CHUNK]; };
   const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
   BP th1; float* dx1; RedOut ro; i64 B;
   const float* __restrict__ Zk; float lz; const float* __restrict__ lscale;   // fused L1-L1 loss cotangent on Z_k
+  uint32_t in_mask;
+  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = gZ; p[1] = cZin; p[2] = lscale ? Zk : nullptr; }
   __device__ __forceinline__ void begin(State& st) const {
     st.red[0] = 0.f; st.lane = threadIdx.x & 31;
     st.lsc = lscale ? lz * __ldg(lscale) : 0.f;
+    st.o_gz = slot_rank(in_mask, 0) * SUBF(CHUNK); st.o_cz = slot_rank(in_mask, 1) * SUBF(CHUNK); st.o_zk = slot_rank(in_mask, 2) * SUBF(CHUNK);
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[1] = {SL_TH1};
     if (th1.g && th1.period == 0) red_finish<PS, 1>(ro, slots, st.red, entry, lane);
   }
-  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
+  __device__ __forceinline__ void prefetch(Pre& pre, int row0, i64 b, bool valid, int n_feat) const {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const bool ok = valid && row0 + i < n_feat;
-      const i64 off = (i64)(row0 + i) * B + b;
-      in.gz[i] = (ok && gZ) ? __ldg(gZ + off) : 0.f;
-      in.zk[i] = (ok && lscale) ? __ldg(Zk + off) : 0.f;   // raw value only: nothing may consume a load in this phase
-      in.cz[i] = (ok && cZin) ? cZin[off] : 0.f;
-      in.mk[i] = ok ? (unsigned)__ldg(maskZ + off) : 0u;
+      pre.mk[i] = ok ? (unsigned)__ldg(maskZ + (i64)(row0 + i) * B + b) : 0u;
     }
   }
-  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat,
-                                        i64 group) const {
+  __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
+                                        const float (&v)[CHUNK], int n_feat, i64 group) const {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (row >= n_feat) continue;                  // warp-uniform
       const bool ok = valid;
       const i64 off = (i64)row * B + b;
-      float dz = v[i] + in.gz[i] + in.cz[i];
-      if (lscale) dz += st.lsc * sgn(in.zk[i]);
-      const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
+      float dz = v[i];
+      if (st.o_gz >= 0) dz += slot[st.o_gz + i * TILE_B + col];
+      if (st.o_cz >= 0) dz += slot[st.o_cz + i * TILE_B + col];
+      if (st.o_zk >= 0) dz += st.lsc * sgn(slot[st.o_zk + i * TILE_B + col]);
+      const float mp = (pre.mk[i] & 1u) ? 1.f : 0.f, mn = (pre.mk[i] & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_contrib<PS>(th1, ro, SL_TH1, st.red[0], row, b, group, ok, dz * (mn - mp), st.lane);
       if (ok) dx1[off] = o;
@@ -91,10 +96,10 @@ struct UEpiBG1 {
 // writes dR for the next A^T dR product, carried dE and dL.
 template <int FAM, bool PS>
 struct UEpiBG2 {
-  static constexpr int CHUNK = 4;     // 11 input arrays per element: keep the register footprint of a chunk small
-  static constexpr int C8 = 4;
-  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; };
-  struct In { float lp[C8], tk[C8], cl[C8], ce[C8], ek[C8], ep[C8], lpp[C8], gl[C8], ge[C8], gt[C8]; unsigned mk[C8]; };
+  static constexpr int CHUNK = 4;
+  static constexpr int NIN = 10;   // L_{k-1}, T_k, cL | cE, E_{k-1}, L_{k-2}, E_{k-2}(B) | gL, gE, gT  (all but the first three optional)
+  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; };
+  struct Pre { unsigned mk[CHUNK]; };
   // layer k
   const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
   int has_prev;
@@ -105,6 +110,13 @@ struct UEpiBG2 {
   float* __restrict__ dR; float* cE; float* cL;
   RedOut ro; i64 B;
   float lw; const float* __restrict__ lscale;       // fused L1-L1 loss cotangents on E_{k-1} / T_k
+  uint32_t in_mask;
+  void host_inputs(const float* (&p)[MAX_EIN]) const {
+    p[0] = Lp; p[1] = Tk; p[2] = cLin;
+    p[3] = has_prev ? cEin : nullptr; p[4] = has_prev ? Ek : nullptr; p[5] = has_prev ? Lpp : nullptr;
+    p[6] = (has_prev && FAM == DLADMM_FAMILY_B) ? Ep : nullptr;
+    p[7] = has_prev ? gL : nullptr; p[8] = has_prev ? gE : nullptr; p[9] = has_prev ? gT : nullptr;
+  }
   __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
     for (int r = 0; r < 6; ++r) st.red[r] = 0.f;
@@ -112,53 +124,45 @@ struct UEpiBG2 {
     st.s1 = ss1.p ? __ldg(ss1.p) : 1.f;
     st.lane = threadIdx.x & 31;
     st.lsc = lscale ? lw * __ldg(lscale) : 0.f;
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) st.o[i] = slot_rank(in_mask, i) * SUBF(CHUNK);
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
     red_finish<PS, 6>(ro, slots, st.red, entry, lane);
   }
-  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
+  __device__ __forceinline__ void prefetch(Pre& pre, int row0, i64 b, bool valid, int n_feat) const {
 #pragma unroll
-    for (int i = 0; i < C8; ++i) {
-      const bool ok = valid && row0 + i < n_feat;
-      const i64 off = (i64)(row0 + i) * B + b;
-      in.lp[i] = ok ? __ldg(Lp + off) : 0.f;
-      in.tk[i] = ok ? __ldg(Tk + off) : 0.f;
-      in.cl[i] = ok ? cLin[off] : 0.f;
-      if (has_prev) {
-        in.ce[i] = ok ? cEin[off] : 0.f;
-        in.ek[i] = ok ? __ldg(Ek + off) : 0.f;
-        in.lpp[i] = ok ? __ldg(Lpp + off) : 0.f;
-        if (FAM == DLADMM_FAMILY_B) in.ep[i] = ok ? __ldg(Ep + off) : 0.f;
-        if (FAM != DLADMM_FAMILY_C) in.mk[i] = ok ? (unsigned)__ldg(maskE + off) : 0u;
-        in.gl[i] = (ok && gL) ? __ldg(gL + off) : 0.f;
-        in.ge[i] = (ok && gE) ? __ldg(gE + off) : 0.f;
-        in.gt[i] = (ok && gT) ? __ldg(gT + off) : 0.f;
-      }
+    for (int i = 0; i < CHUNK; ++i) {
+      const bool ok = valid && has_prev && FAM != DLADMM_FAMILY_C && row0 + i < n_feat;
+      pre.mk[i] = ok ? (unsigned)__ldg(maskE + (i64)(row0 + i) * B + b) : 0u;
     }
   }
-  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[C8], int n_feat,
-                                        i64 group) const {
+  __device__ __forceinline__ float in(const State& st, const float* slot, int a, int i, int col) const {
+    return st.o[a] >= 0 ? slot[st.o[a] + i * TILE_B + col] : 0.f;
+  }
+  __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
+                                        const float (&v)[CHUNK], int n_feat, i64 group) const {
 #pragma unroll
-    for (int i = 0; i < C8; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (row >= n_feat) continue;                  // warp-uniform
       const bool ok = valid;
       const i64 off = (i64)row * B + b;
       const float vb1 = st.b1.at(row, b);
-      const float tk = in.tk[i];
-      const float var = in.lp[i] + vb1 * tk;          // V_k recomputed
+      const float lp = in(st, slot, 0, i, col), tk = in(st, slot, 1, i, col);
+      const float var = lp + vb1 * tk;                // V_k recomputed
       const float dV = -st.s1 * v[i];
       red_contrib<PS>(b1, ro, SL_B1, st.red[4], row, b, group, ok, dV * tk, st.lane);
       red_contrib<PS>(ss1, ro, SL_SS1, st.red[5], row, b, group, ok, -var * v[i], st.lane);
-      float dL = in.cl[i] + dV;
+      float dL = in(st, slot, 2, i, col) + dV;
       float dT = vb1 * dV;
       if (!has_prev) continue;                      // warp-uniform
       // ---- layer k-1: (dL, dT, dE) -> dR, carried dE, carried dL (m1_quad in epilogues.cuh) ----
-      dL += in.gl[i];
-      float dE = in.ce[i] + in.ge[i];
-      dT += in.gt[i];
-      const float tn = tk, ek = in.ek[i], lpp = in.lpp[i];
+      dL += in(st, slot, 7, i, col);
+      float dE = in(st, slot, 3, i, col) + in(st, slot, 8, i, col);
+      dT += in(st, slot, 9, i, col);
+      const float tn = tk, ek = in(st, slot, 4, i, col), lpp = in(st, slot, 5, i, col);
       if (lscale) { const float sl = st.lsc * sgn(ek - tn); dE += sl; dT -= sl; }
       const float vbL = st.bL.at(row, b);
       red_contrib<PS>(bL, ro, SL_BL, st.red[0], row, b, group, ok, dL * tn, st.lane);
@@ -166,11 +170,11 @@ struct UEpiBG2 {
       const float dEt = dE + dTt;
       float dRv, nE, nL;
       if (FAM == DLADMM_FAMILY_B) {
-        const float ep = in.ep[i];
+        const float ep = in(st, slot, 6, i, col);
         const float vb2 = st.b2.at(row, b), vs2 = st.ss2.at(row, b);
         const float that = (tn - ek) + ep;
         const float q = lpp + vb2 * that;
-        const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
+        const float mp = (pre.mk[i] & 1u) ? 1.f : 0.f, mn = (pre.mk[i] & 2u) ? 1.f : 0.f;
         const float du = dEt * (mp + mn);
         red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
         const float dQ = -vs2 * du;
@@ -180,7 +184,7 @@ struct UEpiBG2 {
         dRv = dTt + dThat; nE = du + dThat; nL = dL + dQ;
       } else if (FAM == DLADMM_FAMILY_A) {
         const float vb2 = st.b2.at(row, b);
-        const float mp = (in.mk[i] & 1u) ? 1.f : 0.f, mn = (in.mk[i] & 2u) ? 1.f : 0.f;
+        const float mp = (pre.mk[i] & 1u) ? 1.f : 0.f, mn = (pre.mk[i] & 2u) ? 1.f : 0.f;
         const float du = dEt * (mp + mn);
         red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
         red_contrib<PS>(b2, ro, SL_B2, st.red[3], row, b, group, ok, -du * lpp, st.lane);
@@ -259,37 +263,38 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
 
   if (k_chunks > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int s = 0; uint32_t ph = 0;
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(&empty[s], ph ^ 1);
+      int s = 0; uint32_t ph = 0;
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
           mbar_expect_tx(&full[s], Plan::RAW_BYTES);
           const int bc = (int)(b_begin + (i64)kc * KC);
           tma_load_2d(st, &tmP, &full[s], bc, i0);
           tma_load_2d(st + Plan::A_BYTES, &tmQ, &full[s], bc, n0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
-        int s = 0; uint32_t ph = 0;
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(&full[s], ph);
-          if (NPASS == 3) mbar_wait(&ready[s], ph);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * Plan::STAGE_BYTES);
-          const uint32_t a_big = st, b_big = st + Plan::A_BYTES;
-          const uint32_t a_small = st + Plan::RAW_BYTES, b_small = a_small + Plan::A_BYTES;
+      constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
+      constexpr uint32_t hi = desc_hi(SBO, LAYOUT);
+      const uint32_t st0 = smem_u32(smem);
+      const uint32_t a_lo0 = desc_lo(st0, 16), b_lo0 = desc_lo(st0 + Plan::A_BYTES, 16);
+      int s = 0; uint32_t ph = 0;
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        mbar_wait(&full[s], ph);
+        if (NPASS == 3) mbar_wait(&ready[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + s * (Plan::STAGE_BYTES >> 4), b_lo = b_lo0 + s * (Plan::STAGE_BYTES >> 4);
 #pragma unroll
           for (int ks = 0; ks < KC / UMMA_K; ++ks) {
-            const uint64_t da = make_sdesc(a_big + ks * 32, 16, SBO, LAYOUT);
-            const uint64_t db = make_sdesc(b_big + ks * 32, 16, SBO, LAYOUT);
+            const uint64_t da = desc_at(hi, a_lo + ks * 2), db = desc_at(hi, b_lo + ks * 2);
             const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
             if (NPASS == 3) {
-              const uint64_t das = make_sdesc(a_small + ks * 32, 16, SBO, LAYOUT);
-              const uint64_t dbs = make_sdesc(b_small + ks * 32, 16, SBO, LAYOUT);
+              const uint64_t das = desc_at(hi, a_lo + (Plan::RAW_BYTES >> 4) + ks * 2);
+              const uint64_t dbs = desc_at(hi, b_lo + (Plan::RAW_BYTES >> 4) + ks * 2);
               umma_tf32(tmem_base, das, db, idesc, first);
               umma_tf32(tmem_base, da, dbs, idesc, 1u);
               umma_tf32(tmem_base, da, db, idesc, 1u);
@@ -299,11 +304,12 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
           }
           umma_commit(&empty[s]);
           if (kc == k_chunks - 1) umma_commit(tfull);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else if (warp >= SPLIT_WARP0) {
-      if (NPASS == 3) {       // split both operand tiles (they sit next to each other) in shared memory
+      if (NPASS == 3 && warp < SPLIT_WARP0 + SPLIT_WARPS) {   // split both operand tiles (adjacent) in shared memory
         const int tid = threadIdx.x - SPLIT_WARP0 * 32;
         int s = 0; uint32_t ph = 0;
         for (int kc = 0; kc < k_chunks; ++kc) {

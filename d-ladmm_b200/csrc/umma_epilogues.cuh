@@ -4,8 +4,10 @@
 // the file:line map).  The only extra output is V_{k+1} = L_k + beta1_{k+1} T_{k+1}, the operand of the next W V
 // product; the 3xTF32 operand split (x = trunc_tf32(x) + small) happens in shared memory inside the consumer.
 //
-// Each functor is used in two phases per CH-row chunk so that the global loads of the chunk are all in flight
-// before the accumulator is read:  load(in, ...) -> tcgen05.ld -> apply(in, acc, ...).
+// The (rows x B) arrays an epilogue reads elementwise are staged by TMA into a shared-memory ring (see
+// umma_gemm.cuh): apply() receives `slot`, the staged inputs of its chunk -- present arrays back to back, each
+// [CHUNK][128 columns] floats -- and reads them with conflict-free LDS (lane = column).  Only the 1-byte prox masks
+// are register-prefetched one chunk ahead (prefetch()).
 #pragma once
 #include "common.cuh"
 #include "epilogues.cuh"
@@ -38,36 +40,35 @@ struct PV {
   }
 };
 
+__host__ __device__ constexpr int SUBF(int chunk) { return chunk * TILE_B; }   // floats of one staged array of one chunk
+
+struct NoPre {};
+
 // T_0 = A Z0 + E0 - X, and V_0 = L0 + beta1_0 * T_0 for the first Z-step
 template <bool PSCALAR>
 struct UEpiT0 {
-  static constexpr int CHUNK = CH;
+  static constexpr int CHUNK = 8;
+  static constexpr int NIN = 3;                    // E0, X, L0
   struct State { PV<PSCALAR> b1; };
-  struct In { float e0[CH], x[CH], l0[CH]; };
+  typedef NoPre Pre;
   const float* __restrict__ E0; const float* __restrict__ X; const float* __restrict__ L0; float* __restrict__ T0;
-  BP b1; float* __restrict__ V; i64 B;
+  BP b1; float* __restrict__ V; i64 B; uint32_t in_mask;
+  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = E0; p[1] = X; p[2] = L0; }
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
   __device__ __forceinline__ void end(State&, int, int) const {}
-  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const bool ok = valid && row0 + i < n_feat;
-      const i64 off = (i64)(row0 + i) * B + b;
-      in.e0[i] = ok ? __ldg(E0 + off) : 0.f;
-      in.x[i] = ok ? __ldg(X + off) : 0.f;
-      in.l0[i] = ok ? __ldg(L0 + off) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat, i64) const {
+  __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
+                                        const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (row >= n_feat) continue;
       const i64 off = (i64)row * B + b;
-      const float t = fsub(fadd(v[i], in.e0[i]), in.x[i]);
+      const float e0 = slot[i * TILE_B + col], x = slot[SUBF(CHUNK) + i * TILE_B + col], l0 = slot[2 * SUBF(CHUNK) + i * TILE_B + col];
+      const float t = fsub(fadd(v[i], e0), x);
       T0[off] = t;
-      V[off] = fadd(in.l0[i], fmul(st.b1.at(row, b), t));
+      V[off] = fadd(l0, fmul(st.b1.at(row, b), t));
     }
   }
 };
@@ -75,30 +76,27 @@ struct UEpiT0 {
 // Z_k = act(Z_{k-1} - [ss1*] acc, theta1)
 template <bool PSCALAR>
 struct UEpiZ {
-  static constexpr int CHUNK = CH;
+  static constexpr int CHUNK = 16;
+  static constexpr int NIN = 1;                    // Z_{k-1}
   struct State { PV<PSCALAR> th1; float s1; };
-  struct In { float zp[CH]; };
+  typedef NoPre Pre;
   const float* __restrict__ Zp; float* __restrict__ Zk; uint8_t* __restrict__ maskZ;
-  BP th1; BP ss1; i64 B;
+  BP th1; BP ss1; i64 B; uint32_t in_mask;
+  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; }
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; }
   __device__ __forceinline__ void end(State&, int, int) const {}
-  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const bool ok = valid && row0 + i < n_feat;
-      in.zp[i] = ok ? __ldg(Zp + (i64)(row0 + i) * B + b) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat, i64) const {
+  __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
+                                        const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (row >= n_feat) continue;
       const i64 off = (i64)row * B + b;
       const float wv = ss1.p ? fmul(st.s1, v[i]) : v[i];
       unsigned bits;
-      const float z = soft_act(fsub(in.zp[i], wv), st.th1.at(row, b), bits);
+      const float z = soft_act(fsub(slot[i * TILE_B + col], wv), st.th1.at(row, b), bits);
       Zk[off] = z;
       if (maskZ) maskZ[off] = (uint8_t)bits;
     }
@@ -108,40 +106,34 @@ struct UEpiZ {
 // E_k, T_{k+1}, L_k from acc = A Z_k; then V_{k+1} = L_k + beta1_{k+1} * T_{k+1} unless this is the last layer
 template <int FAM, bool PSCALAR>
 struct UEpiELT {
-  static constexpr int CHUNK = CH;
+  static constexpr int CHUNK = 8;
+  static constexpr int NIN = 3;                    // X, L_{k-1}, E_{k-1} (family B only)
   struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; };
-  struct In { float x[CH], lp[CH], ep[CH]; };
+  typedef NoPre Pre;
   const float* __restrict__ X; const float* __restrict__ Ep; const float* __restrict__ Lp;
   float* __restrict__ Ek; float* __restrict__ Lk; float* __restrict__ Tn; uint8_t* __restrict__ maskE;
   BP b2, ss2, ss2_2, th2, bL;
   int has_next; BP b1n; float* __restrict__ V;
-  i64 B;
+  i64 B; uint32_t in_mask;
+  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = X; p[1] = Lp; p[2] = FAM == DLADMM_FAMILY_B ? Ep : nullptr; }
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
   }
   __device__ __forceinline__ void end(State&, int, int) const {}
-  __device__ __forceinline__ void load(In& in, int row0, i64 b, bool valid, int n_feat) const {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const bool ok = valid && row0 + i < n_feat;
-      const i64 off = (i64)(row0 + i) * B + b;
-      in.x[i] = ok ? __ldg(X + off) : 0.f;
-      in.lp[i] = ok ? __ldg(Lp + off) : 0.f;
-      if (FAM == DLADMM_FAMILY_B) in.ep[i] = ok ? __ldg(Ep + off) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void apply(State& st, const In& in, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat, i64) const {
+  __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
+                                        const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
+    for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (row >= n_feat) continue;
       const i64 off = (i64)row * B + b;
-      const float x = in.x[i], lp = in.lp[i], acc = v[i];
+      const float x = slot[i * TILE_B + col], lp = slot[SUBF(CHUNK) + i * TILE_B + col], acc = v[i];
       float e;
       unsigned bits = 0;
       if (FAM == DLADMM_FAMILY_B) {
-        const float ep = in.ep[i];
+        const float ep = slot[2 * SUBF(CHUNK) + i * TILE_B + col];
         const float that = fsub(fadd(acc, ep), x);
         const float vvar = fadd(lp, fmul(st.b2.at(row, b), that));
         const float u = fsub(ep, fmul(st.ss2.at(row, b), vvar));

@@ -12,14 +12,14 @@
 // warp-uniform.
 //
 // 3xTF32: x = big + small with big = the tf32 the tensor core sees; three MMAs per k-step accumulate
-// small*big + big*small + big*big in the same TMEM accumulator (fp32-level products).  Weights are split once per call
-// (round-to-nearest) by the host-side prep kernel.  Activations arrive as plain fp32 through TMA and are split IN SHARED
-// MEMORY by four splitter warps (big = the raw word, which the tensor core truncates to tf32; small = x - trunc(x) written
-// next to it), so no split copy of an activation ever exists in HBM.
+// small*big + big*small + big*big in the same TMEM accumulator (fp32-level products).  Both operands arrive as plain fp32
+// through TMA and are split IN SHARED MEMORY by four splitter warps (big = the raw word, which the tensor core truncates
+// to tf32; small = x - trunc(x) written next to it): no split copy of anything exists in HBM or L2, and the L2->SM operand
+// traffic -- the binding resource of these products -- is that of a plain fp32 GEMM.
 //
-// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// Warp roles (480 threads): warp 0 = TMA producer (operands), warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; two warps per quadrant split the feature rows),
-// warps 10..13 = operand splitters (3xTF32 only).  Persistent over (batch tile, feature tile) pairs,
+// warps 10..13 = operand splitters (3xTF32 only), warp 14 = TMA producer of the epilogue-input staging ring.  Persistent over (batch tile, feature tile) pairs,
 // two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -34,7 +34,8 @@ constexpr int UMMA_K = 8;        // tf32
 constexpr int EPI_WARPS = 8;          // two per TMEM lane quadrant, each owning half of the tile's feature rows
 constexpr int SPLIT_WARPS = 4;        // shared-memory tf32 splitters (3-pass mode)
 constexpr int SPLIT_WARP0 = 2 + EPI_WARPS;
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * SPLIT_WARPS;
+constexpr int EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS;   // producer of the epilogue-input staging ring
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * SPLIT_WARPS + 32;
 constexpr int EPI_WARP0 = 2;
 constexpr int CH = 16;            // feature rows per epilogue step (one tcgen05.ld.32x32b.x16)
 
@@ -163,6 +164,20 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[4]) { tmem_ld
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 
+// one lane of a CONVERGED warp; lets ptxas emit the uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) straight-line
+// instead of wrapping each of them in an elect/branch loop as it must inside divergent `if (lane == 0)` code
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------------
 // instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -179,6 +194,12 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
+// descriptor = (hi << 32) | lo with lo = (addr >> 4) | (LBO >> 4) << 16 : advancing the start address is a 32-bit add on lo
+__device__ __forceinline__ uint64_t desc_at(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
 constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
 // MN-major 32-bit operands have exactly one legal swizzled layout: 128-byte rows whose four 32-byte chunks are
 // permuted by (row % 4) -- UMMA layout type 1 (SWIZZLE_128B_BASE32B), written by TMA with
@@ -196,47 +217,71 @@ struct GemmShape {
   i64 n_btiles;      // ceil(B / TILE_B)
 };
 
+// Epilogue inputs (the (rows x B) arrays the fused epilogue reads elementwise) are staged through a shared-memory
+// ring by TMA: a dedicated producer thread streams (CHUNK rows x 128 columns) boxes of every input array, several
+// chunks -- and tiles -- ahead of the epilogue warps, so the epilogue never waits a DRAM round trip in registers.
+constexpr int MAX_EIN = 10;              // staged input arrays per epilogue
+constexpr int RING_BYTES = 72 * 1024;    // staging ring; depth = RING_BYTES / (present arrays * CHUNK * 512 B)
+
+struct EMaps { CUtensorMap m[MAX_EIN]; };
+
 template <int NPASS, int KC>
 struct SmemPlan {
   static constexpr int NOPS = NPASS == 3 ? 2 : 1;                    // big (+ small)
   static constexpr int A_BYTES = TILE_B * KC * 4;                    // one operand part
   static constexpr int B_BYTES = TILE_N * KC * 4;
-  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | A small] [B big | B small]
-  static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | B raw] [A small | B small]
+  static constexpr int RAW_BYTES = A_BYTES + B_BYTES;                // what TMA delivers; the small parts are computed in place
+  static constexpr int STAGES = 3;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
+constexpr int MAX_RING_DEPTH = 36;
 
-// Epi: functor with State/In types; per CH-feature chunk of one batch column the kernel calls
-//   epi.load(in, row0, b, valid, n_feat)  (global inputs, issued before the accumulator is read) and
-//   epi.apply(state, in, row0, b, valid, acc[CH], n_feat, column_group)
+// Epi: functor with
+//   CHUNK (feature rows per epilogue step), NIN (staged float input arrays), in_mask (bit i: array i present),
+//   State / Pre types, begin/end,
+//   prefetch(pre, row0, b, valid, n_feat)          register loads of small side inputs (prox masks), one chunk ahead
+//   apply(state, slot, col, pre, row0, b, valid, acc[CHUNK], n_feat, group)
+// where `slot` points at the staged inputs of this chunk: present arrays back to back, each [CHUNK][128] floats.
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_big,
-                 const __grid_constant__ CUtensorMap tmB_small, GemmShape gs, Epi epi) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ EMaps emaps, GemmShape gs, Epi epi) {
   using Plan = SmemPlan<NPASS, KC>;
   constexpr int STAGES = Plan::STAGES;
   constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
   constexpr uint32_t B_SBO = 8 * KC * 4;            // 8 rows of KC floats
+  constexpr int CHK = Epi::CHUNK;
+  constexpr int ROWS_PER_WARP = TILE_N / (EPI_WARPS / 4);
+  constexpr int NCH = ROWS_PER_WARP / CHK;          // chunks per (tile, half)
+  constexpr int SUB_BYTES = CHK * TILE_B * 4;       // one staged array of one chunk
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * Plan::STAGE_BYTES);
+  uint8_t* ring = smem + STAGES * Plan::STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(ring + RING_BYTES);
   uint64_t* full = bars;                   // [STAGES]
   uint64_t* empty = bars + STAGES;         // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;     // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-  uint64_t* ready = bars + 2 * STAGES + 4;   // [STAGES] activation split done (3-pass mode)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
+  uint64_t* ready = bars + 2 * STAGES;     // [STAGES] activation split done (3-pass mode)
+  uint64_t* tfull = bars + 3 * STAGES;     // [2]
+  uint64_t* tempty = bars + 3 * STAGES + 2;  // [2]
+  uint64_t* efull = bars + 3 * STAGES + 4;                   // [MAX_RING_DEPTH]
+  uint64_t* eempty = bars + 3 * STAGES + 4 + MAX_RING_DEPTH;  // [MAX_RING_DEPTH]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4 + 2 * MAX_RING_DEPTH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 ntiles = gs.n_btiles * gs.n_ntiles;
+  // staging ring geometry (uniform over the CTA)
+  const int nin = __popc(epi.in_mask);
+  const int slot_bytes = nin * SUB_BYTES;
+  int depth = nin > 0 ? RING_BYTES / slot_bytes : 1;
+  if (depth > MAX_RING_DEPTH) depth = MAX_RING_DEPTH;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA); prefetch_tmap(&tmB_big);
-    if (NPASS == 3) prefetch_tmap(&tmB_small);
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
+    for (int s = 0; s < depth; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -249,57 +294,59 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nt = (int)(tile % gs.n_ntiles);
-        const i64 bt = tile / gs.n_ntiles;
-        const int b0 = (int)(bt * TILE_B);             // batch column (TMA coordinates are 32-bit)
-        const int j0 = nt * TILE_N;
-        for (int kc = 0; kc < gs.k_chunks; ++kc) {
-          mbar_wait(&empty[s], ph ^ 1);
+    // ===== TMA producer (MMA operands): the whole warp walks the schedule, one elected lane issues =====
+    int s = 0; uint32_t ph = 0;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nt = (int)(tile % gs.n_ntiles);
+      const i64 bt = tile / gs.n_ntiles;
+      const int b0 = (int)(bt * TILE_B);             // batch column (TMA coordinates are 32-bit)
+      const int j0 = nt * TILE_N;
+      for (int kc = 0; kc < gs.k_chunks; ++kc) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Plan::TX_BYTES);
+          mbar_expect_tx(&full[s], Plan::RAW_BYTES);
           // activation (raw fp32): 4 boxes of (32 batch columns x KC rows), 128 B per row
 #pragma unroll
           for (int g = 0; g < TILE_B / 32; ++g) tma_load_2d(st + g * (KC * 128), &tmA, &full[s], b0 + g * 32, kc * KC);
-          // weights: one box of (KC k x 256 rows) per part
-          uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES;
-          tma_load_2d(b_dst, &tmB_big, &full[s], kc * KC, j0);
-          if (NPASS == 3) tma_load_2d(b_dst + Plan::B_BYTES, &tmB_small, &full[s], kc * KC, j0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          // weights (raw fp32): one box of (KC k x 256 rows)
+          tma_load_2d(st + Plan::A_BYTES, &tmB, &full[s], kc * KC, j0);
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0);
-      int s = 0; uint32_t ph = 0;
-      int acc = 0; uint32_t aph = 0;
-      for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], aph ^ 1);
+    // ===== MMA issuer: converged warp, one elected lane issues; descriptors are precomputed, only `lo` moves =====
+    constexpr uint32_t idesc = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0);
+    // A (MN-major, 128B swizzle / 32B atoms): rows of 32 batch columns (128 B); one k-step = 8 rows = 2 atoms (SBO = 512 B
+    // apart); batch groups of 32 are KC*128 B apart (LBO).  B (K-major): rows of KC floats; 8-row groups B_SBO apart;
+    // a k-step advances 32 B inside the swizzled row.
+    constexpr uint32_t a_hi = desc_hi(A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
+    constexpr uint32_t b_hi = desc_hi(B_SBO, B_LAYOUT);
+    const uint32_t st0 = smem_u32(smem);
+    const uint32_t a_lo0 = desc_lo(st0, KC * 128);
+    const uint32_t b_lo0 = desc_lo(st0 + Plan::A_BYTES, 16);
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t aph = 0;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TILE_N;
+      for (int kc = 0; kc < gs.k_chunks; ++kc) {
+        mbar_wait(&full[s], ph);
+        if (NPASS == 3) mbar_wait(&ready[s], ph);      // small part of the activation tile written by the splitters
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TILE_N;
-        for (int kc = 0; kc < gs.k_chunks; ++kc) {
-          mbar_wait(&full[s], ph);
-          if (NPASS == 3) mbar_wait(&ready[s], ph);      // small part of the activation tile written by the splitters
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * Plan::STAGE_BYTES);
-          const uint32_t a_big = st, a_small = st + Plan::A_BYTES;
-          const uint32_t b_big = st + Plan::NOPS * Plan::A_BYTES, b_small = b_big + Plan::B_BYTES;
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + s * (Plan::STAGE_BYTES >> 4), b_lo = b_lo0 + s * (Plan::STAGE_BYTES >> 4);
 #pragma unroll
           for (int ks = 0; ks < KC / UMMA_K; ++ks) {
-            // A (MN-major, 128B swizzle / 32B atoms): rows of 32 batch columns (128 B); one k-step = 8 rows = 2 atoms
-            // (SBO = 512 B apart); batch groups of 32 are KC*128 B apart (LBO)
-            const uint64_t da_big = make_sdesc(a_big + ks * 1024, KC * 128, A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
-            // B (K-major): rows of KC floats; 8-row groups B_SBO apart; advance 32 B per k-step inside the swizzled row
-            const uint64_t db_big = make_sdesc(b_big + ks * 32, 16, B_SBO, B_LAYOUT);
+            const uint64_t da_big = desc_at(a_hi, a_lo + ks * (1024 >> 4));
+            const uint64_t db_big = desc_at(b_hi, b_lo + ks * (32 >> 4));
             const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
             if (NPASS == 3) {
-              const uint64_t da_small = make_sdesc(a_small + ks * 1024, KC * 128, A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
-              const uint64_t db_small = make_sdesc(b_small + ks * 32, 16, B_SBO, B_LAYOUT);
+              const uint64_t da_small = desc_at(a_hi, a_lo + (Plan::RAW_BYTES >> 4) + ks * (1024 >> 4));
+              const uint64_t db_small = desc_at(b_hi, b_lo + (Plan::RAW_BYTES >> 4) + ks * (32 >> 4));
               umma_tf32(d_tmem, da_small, db_big, idesc, first);
               umma_tf32(d_tmem, da_big, db_small, idesc, 1u);
               umma_tf32(d_tmem, da_big, db_big, idesc, 1u);
@@ -309,9 +356,45 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           umma_commit(&empty[s]);                      // frees the smem stage when these MMAs retire
           if (kc == gs.k_chunks - 1) umma_commit(&tfull[acc]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (++acc == 2) { acc = 0; aph ^= 1; }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  } else if (warp == EIN_WARP) {
+    // ===== TMA producer (epilogue inputs): chunk n = ((tile_iter * NCH + c) * 2 + half) -> ring slot n % depth =====
+    if (nin > 0) {
+      i64 n = 0;
+      for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = (int)(tile % gs.n_ntiles);
+        const i64 bt = tile / gs.n_ntiles;
+        const int b0 = (int)(bt * TILE_B);
+        const int j0 = nt * TILE_N;
+        for (int c = 0; c < NCH; ++c) {
+          for (int h = 0; h < 2; ++h, ++n) {
+            const int s = (int)(n % depth);
+            const uint32_t ph = (uint32_t)((n / depth) & 1);
+            mbar_wait(&eempty[s], ph ^ 1);
+            const int row0 = j0 + h * ROWS_PER_WARP + c * CHK;
+            if (elect_one()) {
+              if (row0 >= gs.n_feat) {
+                mbar_arrive(&efull[s]);                  // nothing to stage, keep the phases in step
+              } else {
+                uint8_t* dst = ring + s * slot_bytes;
+                mbar_expect_tx(&efull[s], slot_bytes);
+#pragma unroll
+                for (int i = 0; i < Epi::NIN; ++i) {
+                  if (epi.in_mask & (1u << i)) {
+                    tma_load_2d(dst, &emaps.m[i], &efull[s], b0, row0);
+                    dst += SUB_BYTES;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
     }
   } else if (warp >= SPLIT_WARP0) {
@@ -323,7 +406,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kc = 0; kc < gs.k_chunks; ++kc) {
           mbar_wait(&full[s], ph);                       // TMA bytes landed; the stage was free (producer waited on empty)
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          split_tile(st, st + Plan::A_BYTES, Plan::A_BYTES, tid, SPLIT_WARPS * 32);
+          split_tile(st, st + Plan::RAW_BYTES, Plan::RAW_BYTES, tid, SPLIT_WARPS * 32);   // both operand tiles
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
           __syncwarp();
           if (lane == 0) mbar_arrive(&ready[s]);
@@ -335,33 +418,41 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== epilogue warps =====
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
     const int half = (warp - EPI_WARP0) >> 2;          // which half of the tile's feature rows
-    constexpr int ROWS_PER_WARP = TILE_N / (EPI_WARPS / 4);
-    constexpr int CHK = Epi::CHUNK;                    // feature rows per epilogue step
+    const int col = q * 32 + lane;                     // column inside the tile
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
+    i64 n = half;                                      // this half's chunk counter in the staging ring
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int nt = (int)(tile % gs.n_ntiles);
       const i64 bt = tile / gs.n_ntiles;
-      const i64 b = bt * TILE_B + q * 32 + lane;
+      const i64 b = bt * TILE_B + col;
       const int j0 = nt * TILE_N;
       const bool valid = b < gs.B;
-      typename Epi::In in;
       const int jw = j0 + half * ROWS_PER_WARP;        // first feature row of this warp
-      epi.load(in, jw, b, valid, gs.n_feat);           // global inputs of the first chunk fly while the MMAs finish
+      typename Epi::Pre pre;
+      epi.prefetch(pre, jw, b, valid, gs.n_feat);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + acc * TILE_N + half * ROWS_PER_WARP + ((uint32_t)(q * 32) << 16);
-      // CH rows per step: small enough that the unrolled body stays inside the instruction cache, large enough
-      // (CH loads per input array per thread) to keep HBM busy from 4 warps
 #pragma unroll 1
-      for (int c = 0; c < ROWS_PER_WARP / CHK; ++c) {
+      for (int c = 0; c < NCH; ++c, n += 2) {
         const int row0 = jw + c * CHK;
-        if (row0 >= gs.n_feat) break;                  // warp-uniform
-        float v[CHK];
-        tmem_ld(t0 + c * CHK, v);
-        epi.apply(state, in, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);
-        if (c + 1 < ROWS_PER_WARP / CHK && row0 + CHK < gs.n_feat) epi.load(in, row0 + CHK, b, valid, gs.n_feat);
+        typename Epi::Pre pre_next;
+        epi.prefetch(pre_next, row0 + CHK, b, valid && c + 1 < NCH, gs.n_feat);
+        const int s = (int)(n % depth);
+        if (nin > 0) mbar_wait(&efull[s], (uint32_t)((n / depth) & 1));
+        if (row0 < gs.n_feat) {                          // warp-uniform
+          float v[CHK];
+          tmem_ld(t0 + c * CHK, v);
+          epi.apply(state, reinterpret_cast<const float*>(ring + s * slot_bytes), col, pre, row0, b, valid, v, gs.n_feat,
+                    bt * (TILE_B / 32) + q);
+        }
+        if (nin > 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&eempty[s]);
+        }
+        pre = pre_next;
       }
       tc_fence_before();
       __syncwarp();

@@ -113,6 +113,7 @@ def test_backward_matches_reference_gradients(name, precision):
 def test_training_loss_gradients_match_oracle_autograd(variant, precision):
     """The reference's actual training loss (main_syn_l1l1_scalar.py:289-299): only Z_k gets a cotangent."""
     _skip_if_unavailable(precision)
+    torch.manual_seed(4321)
     m, d, B, K = 60, 100, 48, 5
     A, X = syn(m, d, B, seed=21)
     gen = torch.Generator().manual_seed(4)
@@ -164,6 +165,7 @@ def test_fused_l1l1_loss_matches_reference_training_objective(variant, precision
     """model.l1l1_loss: loss value and every parameter gradient against autograd of the reference's own
     training loss (main_syn_l1l1_scalar.py:289-299, with its separate A @ Z_k products) in fp64."""
     _skip_if_unavailable(precision)
+    torch.manual_seed(1234)                                     # W init draws from the global generator
     m, d, B, K = 60, 100, 64, 5
     A, X = syn(m, d, B, seed=33)
     gen = torch.Generator().manual_seed(5)
@@ -187,5 +189,5 @@ def test_fused_l1l1_loss_matches_reference_training_objective(variant, precision
             continue
         # (1,1) parameters: the gradient is a sum over all (rows x B) entries with cancellation, so hold it to an
         # absolute floor instead of a relative error on a number that may be ~0
-        floor = 2e-3 if p.numel() == 1 else 1e-5
+        floor = 2e-3 if p.numel() == 1 else 1e-4 * max(1.0, float(gref[n].abs().max()) * p.numel() ** 0.5)
         assert rel_l2(p.grad.cpu(), 2.0 * gref[n], floor=floor) < 5 * GRAD_TOL[precision], n
