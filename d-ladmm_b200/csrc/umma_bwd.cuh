@@ -315,7 +315,7 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(&full[s], ph);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          split_tile(st, st + Plan::RAW_BYTES, Plan::RAW_BYTES, tid, SPLIT_WARPS * 32);
+          split_tile<Plan::RAW_BYTES, SPLIT_WARPS * 32>(st, st + Plan::RAW_BYTES, tid);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ready[s]);

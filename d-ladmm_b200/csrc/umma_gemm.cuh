@@ -12,10 +12,11 @@
 // warp-uniform.
 //
 // 3xTF32: x = big + small with big = the tf32 the tensor core sees; three MMAs per k-step accumulate
-// small*big + big*small + big*big in the same TMEM accumulator (fp32-level products).  Both operands arrive as plain fp32
-// through TMA and are split IN SHARED MEMORY by four splitter warps (big = the raw word, which the tensor core truncates
-// to tf32; small = x - trunc(x) written next to it): no split copy of anything exists in HBM or L2, and the L2->SM operand
-// traffic -- the binding resource of these products -- is that of a plain fp32 GEMM.
+// small*big + big*small + big*big in the same TMEM accumulator (fp32-level products).  Weights are split once per call
+// (round-to-nearest) by the prep kernel.  Activations arrive as plain fp32 through TMA and are split IN SHARED MEMORY by
+// four splitter warps (big = the raw word, which the tensor core truncates to tf32; small = x - trunc(x) written next to
+// it), so no split copy of an activation ever exists in HBM.  (Splitting the weights in shared memory as well was measured
+// slower: shared-memory bandwidth -- TMA writes + split + three operand reads per k-step -- is what bounds this kernel.)
 //
 // Warp roles (480 threads): warp 0 = TMA producer (operands), warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; two warps per quadrant split the feature rows),
@@ -85,14 +86,21 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ float tf32_small(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-// small = x - trunc_tf32(x) for `bytes` of an operand tile (any layout: the transform is elementwise)
-__device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* small, int bytes, int tid, int nthreads) {
+// small = x - trunc_tf32(x) for BYTES of operand tiles (any layout: the transform is elementwise).  Fully unrolled: all
+// the 16-byte loads of a thread are in flight before the first store (a rolled loop costs ~90 clk per 16 bytes and made
+// the splitters the throughput limit of the whole pipeline -- measured with clock64 stamps in tools/umma_probe.cu).
+template <int BYTES, int NTHREADS>
+__device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* small, int tid) {
+  constexpr int N = BYTES / 16 / NTHREADS;
+  static_assert(N * 16 * NTHREADS == BYTES, "tile bytes must be a multiple of 16 * threads");
   const float4* src = reinterpret_cast<const float4*>(raw);
   float4* dst = reinterpret_cast<float4*>(small);
-  for (int i = tid; i < bytes / 16; i += nthreads) {
-    const float4 v = src[i];
-    dst[i] = make_float4(tf32_small(v.x), tf32_small(v.y), tf32_small(v.z), tf32_small(v.w));
-  }
+  float4 v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = src[tid + i * NTHREADS];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    dst[tid + i * NTHREADS] = make_float4(tf32_small(v[i].x), tf32_small(v[i].y), tf32_small(v[i].z), tf32_small(v[i].w));
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -209,7 +217,17 @@ constexpr uint32_t LAYOUT_SW128_BASE32B = 1;
 constexpr uint32_t A_ATOM_BYTES = 512;
 
 // ---- kernel ----------------------------------------------------------------------------------------------
+#ifdef UMMA_TRACE
+#define UMMA_TR(gs, idx, ev) do { if (blockIdx.x == 0 && (gs).trace && (idx) < 256) (gs).trace[(idx) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define UMMA_TR(gs, idx, ev) do { } while (0)
+#endif
+
 struct GemmShape {
+#ifdef UMMA_TRACE
+  long long* trace;  // [256][8] clock64 stamps of CTA 0: 0 producer got the stage, 1 TMA issued, 2 splitter saw full, 3 split done,
+                     //                                    4 MMA saw ready, 5 MMAs issued
+#endif
   int n_feat;        // valid feature rows (epilogue bound); weights are zero padded to a multiple of TILE_N
   int n_ntiles;      // ceil(n_feat / TILE_N)
   int k_chunks;      // ceil(Kdim / KC)
@@ -230,8 +248,8 @@ struct SmemPlan {
   static constexpr int NOPS = NPASS == 3 ? 2 : 1;                    // big (+ small)
   static constexpr int A_BYTES = TILE_B * KC * 4;                    // one operand part
   static constexpr int B_BYTES = TILE_N * KC * 4;
-  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | B raw] [A small | B small]
-  static constexpr int RAW_BYTES = A_BYTES + B_BYTES;                // what TMA delivers; the small parts are computed in place
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | A small] [B big | B small]
+  static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
   static constexpr int STAGES = 3;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + 1024;   // + alignment slack
@@ -246,8 +264,8 @@ constexpr int MAX_RING_DEPTH = 36;
 // where `slot` points at the staged inputs of this chunk: present arrays back to back, each [CHUNK][128] floats.
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ EMaps emaps, GemmShape gs, Epi epi) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_big,
+                 const __grid_constant__ CUtensorMap tmB_small, const __grid_constant__ EMaps emaps, GemmShape gs, Epi epi) {
   using Plan = SmemPlan<NPASS, KC>;
   constexpr int STAGES = Plan::STAGES;
   constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
@@ -278,7 +296,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (depth > MAX_RING_DEPTH) depth = MAX_RING_DEPTH;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB_big);
+    if (NPASS == 3) prefetch_tmap(&tmB_small);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     for (int s = 0; s < depth; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 4); }
@@ -295,7 +314,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===== TMA producer (MMA operands): the whole warp walks the schedule, one elected lane issues =====
-    int s = 0; uint32_t ph = 0;
+    int s = 0; uint32_t ph = 0; int trp = 0; (void)trp;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int nt = (int)(tile % gs.n_ntiles);
       const i64 bt = tile / gs.n_ntiles;
@@ -304,14 +323,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kc = 0; kc < gs.k_chunks; ++kc) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
+          UMMA_TR(gs, trp, 0); 
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Plan::RAW_BYTES);
+          mbar_expect_tx(&full[s], Plan::TX_BYTES);
           // activation (raw fp32): 4 boxes of (32 batch columns x KC rows), 128 B per row
 #pragma unroll
           for (int g = 0; g < TILE_B / 32; ++g) tma_load_2d(st + g * (KC * 128), &tmA, &full[s], b0 + g * 32, kc * KC);
-          // weights (raw fp32): one box of (KC k x 256 rows)
-          tma_load_2d(st + Plan::A_BYTES, &tmB, &full[s], kc * KC, j0);
+          // weights, pre-split by the prep kernel: one box of (KC k x 256 rows) per part
+          uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES;
+          tma_load_2d(b_dst, &tmB_big, &full[s], kc * KC, j0);
+          if (NPASS == 3) tma_load_2d(b_dst + Plan::B_BYTES, &tmB_small, &full[s], kc * KC, j0);
+          UMMA_TR(gs, trp, 1);
         }
+        ++trp;
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -326,18 +350,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t b_hi = desc_hi(B_SBO, B_LAYOUT);
     const uint32_t st0 = smem_u32(smem);
     const uint32_t a_lo0 = desc_lo(st0, KC * 128);
-    const uint32_t b_lo0 = desc_lo(st0 + Plan::A_BYTES, 16);
-    int s = 0; uint32_t ph = 0;
+    const uint32_t b_lo0 = desc_lo(st0 + Plan::NOPS * Plan::A_BYTES, 16);
+    int s = 0; uint32_t ph = 0; int trm = 0; (void)trm;
     int acc = 0; uint32_t aph = 0;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * TILE_N;
-      for (int kc = 0; kc < gs.k_chunks; ++kc) {
+      for (int kc = 0; kc < gs.k_chunks; ++kc, ++trm) {
         mbar_wait(&full[s], ph);
         if (NPASS == 3) mbar_wait(&ready[s], ph);      // small part of the activation tile written by the splitters
         tc_fence_after();
         if (elect_one()) {
+          UMMA_TR(gs, trm, 4);
           const uint32_t a_lo = a_lo0 + s * (Plan::STAGE_BYTES >> 4), b_lo = b_lo0 + s * (Plan::STAGE_BYTES >> 4);
 #pragma unroll
           for (int ks = 0; ks < KC / UMMA_K; ++ks) {
@@ -345,8 +370,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t db_big = desc_at(b_hi, b_lo + ks * (32 >> 4));
             const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
             if (NPASS == 3) {
-              const uint64_t da_small = desc_at(a_hi, a_lo + (Plan::RAW_BYTES >> 4) + ks * (1024 >> 4));
-              const uint64_t db_small = desc_at(b_hi, b_lo + (Plan::RAW_BYTES >> 4) + ks * (32 >> 4));
+              const uint64_t da_small = desc_at(a_hi, a_lo + (Plan::A_BYTES >> 4) + ks * (1024 >> 4));
+              const uint64_t db_small = desc_at(b_hi, b_lo + (Plan::B_BYTES >> 4) + ks * (32 >> 4));
               umma_tf32(d_tmem, da_small, db_big, idesc, first);
               umma_tf32(d_tmem, da_big, db_small, idesc, 1u);
               umma_tf32(d_tmem, da_big, db_big, idesc, 1u);
@@ -356,6 +381,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           umma_commit(&empty[s]);                      // frees the smem stage when these MMAs retire
           if (kc == gs.k_chunks - 1) umma_commit(&tfull[acc]);
+          UMMA_TR(gs, trm, 5);
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -401,14 +427,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== operand splitters (3-pass mode): small = x - trunc_tf32(x) of the activation tile, in shared memory =====
     if (NPASS == 3) {
       const int tid = threadIdx.x - SPLIT_WARP0 * 32;
-      int s = 0; uint32_t ph = 0;
+      int s = 0; uint32_t ph = 0; int trs = 0; (void)trs;
       for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int kc = 0; kc < gs.k_chunks; ++kc) {
+        for (int kc = 0; kc < gs.k_chunks; ++kc, ++trs) {
           mbar_wait(&full[s], ph);                       // TMA bytes landed; the stage was free (producer waited on empty)
+          if (tid == 0) UMMA_TR(gs, trs, 2);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          split_tile(st, st + Plan::RAW_BYTES, Plan::RAW_BYTES, tid, SPLIT_WARPS * 32);   // both operand tiles
+          split_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, tid);
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
           __syncwarp();
+          if (tid == 0) UMMA_TR(gs, trs, 3);
           if (lane == 0) mbar_arrive(&ready[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -468,6 +496,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_dealloc(tmem_base, 512);
   }
 }
+
 
 // ---- host side: tensor maps ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -13,8 +13,8 @@ namespace dladmm {
 static int device_sm_count();
 
 struct UWorkspace {
-  float *Ab;           // A  (m256 x dp) zero padded: features of the A Z product on the N side, K = d
-  float *Wb;           // nW x (d256 x mp) zero padded: features of the W V product on the N side, K = m
+  float *Ab, *As;      // A  (m256 x dp) zero padded, tf32 big/small: features of the A Z product on the N side, K = d
+  float *Wb, *Ws;      // nW x (d256 x mp): features of the W V product on the N side, K = m
   float *V;            // (m x B) operand V_k = L_{k-1} + beta1_k T_k of the next W V product
   size_t bytes;
   int m256, d256, mp, dp, nW;
@@ -35,7 +35,9 @@ static UWorkspace ucarve(const dladmm_problem* p, char* base) {
     return r;
   };
   w.Ab = take((size_t)w.m256 * w.dp);
+  w.As = take((size_t)w.m256 * w.dp);
   w.Wb = take((size_t)w.nW * w.d256 * w.mp);
+  w.Ws = take((size_t)w.nW * w.d256 * w.mp);
   w.V = take((size_t)p->m * p->B);
   w.bytes = off;
   return w;
@@ -47,8 +49,8 @@ static inline bool umma_eligible(const dladmm_problem* p) {
 }
 
 struct UBwdWorkspace {
-  float *Atb;          // A^T (d256 x mp) zero padded: features of A^T dR on the N side, K = m
-  float *Wtb;          // nW x (m256 x dp) zero padded: W^T, features of W^T dx1 on the N side, K = d
+  float *Atb, *Ats;    // A^T (d256 x mp) zero padded, tf32 big/small: features of A^T dR on the N side, K = m
+  float *Wtb, *Wts;    // nW x (m256 x dp): W^T, features of W^T dx1 on the N side, K = d
   float *V;            // (m x B) V_k recomputed per layer
   float *part;         // parameter-gradient partial sums of the tcgen05 epilogues
   size_t bytes;
@@ -73,7 +75,9 @@ static UBwdWorkspace ucarve_bwd(const dladmm_problem* p, char* base) {
     return r;
   };
   w.Atb = take((size_t)w.d256 * w.mp);
+  w.Ats = take((size_t)w.d256 * w.mp);
   w.Wtb = take((size_t)w.nW * w.m256 * w.dp);
+  w.Wts = take((size_t)w.nW * w.m256 * w.dp);
   w.V = take((size_t)p->m * p->B);
   w.part = take(std::max((size_t)SL_COUNT * w.ngroups * w.prow, (size_t)SL_COUNT * w.nentries));
   w.bytes = off;
@@ -85,7 +89,8 @@ static inline size_t umma_workspace_bytes(const dladmm_problem* p, int for_backw
   return (for_backward ? ucarve_bwd(p, nullptr).bytes : ucarve(p, nullptr).bytes) + 1024;
 }
 
-// dense (R x C) -> zero padded (Rpad x Cpad) K-major copy (TMA needs a 16-byte multiple pitch; fc.weight has 4*m = 1000 B)
+// dense (R x C) -> zero padded (Rpad x Cpad) K-major big/small parts (tf32 round-to-nearest split) or a plain padded copy
+// (TMA needs a 16-byte multiple pitch; fc.weight has 4*m = 1000 B)
 struct SplitJob { const float* src; float* big; float* small; };
 struct SplitJobs { int n; SplitJob j[32]; };
 
@@ -113,9 +118,9 @@ template <int NPASS>
 static int uprepare_weights(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
   {
     SplitJobs jobs; jobs.n = 1;
-    jobs.j[0].src = p->A; jobs.j[0].big = w.Ab; jobs.j[0].small = nullptr;
+    jobs.j[0].src = p->A; jobs.j[0].big = w.Ab; jobs.j[0].small = w.As;
     dim3 grid((w.dp + 31) / 32, (w.m256 + 31) / 32, 1);
-    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<1><<<grid, 256, 0, st>>>(jobs, p->m, p->d, w.m256, w.dp); }
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->m, p->d, w.m256, w.dp); }
     DL_CUDA(cudaGetLastError());
   }
   std::vector<const float*> uniq = WeightMap(p).uniq;
@@ -125,10 +130,10 @@ static int uprepare_weights(const dladmm_problem* p, const UWorkspace& w, cudaSt
       size_t idx = base + i;
       jobs.j[i].src = uniq[idx];
       jobs.j[i].big = w.Wb + idx * (size_t)w.d256 * w.mp;
-      jobs.j[i].small = nullptr;
+      jobs.j[i].small = w.Ws + idx * (size_t)w.d256 * w.mp;
     }
     dim3 grid((w.mp + 31) / 32, (w.d256 + 31) / 32, jobs.n);
-    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<1><<<grid, 256, 0, st>>>(jobs, p->d, p->m, w.d256, w.mp); }
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->d, p->m, w.d256, w.mp); }
     DL_CUDA(cudaGetLastError());
   }
   return DLADMM_OK;
@@ -196,15 +201,20 @@ static int device_sm_count() {
 // C[j,b] = sum_k Wt[j,k] Act[k,b] with a fused epilogue.  act_* are (Kdim x B) batch-contiguous; w_* are prepared
 // (n_pad x k_pad) K-major arrays.
 template <class Epi, int NPASS>
-static int launch_umma(int kind, const float* act, int Kdim, const float* w_pad,
+static int launch_umma(int kind, const float* act, int Kdim, const float* w_big, const float* w_small,
                        int n_pad, int k_pad, int n_feat, i64 B, Epi epi, cudaStream_t st, int grid_override = 0) {
   constexpr int KC = NPASS == 3 ? 16 : 32;
   using Plan = umma::SmemPlan<NPASS, KC>;
-  CUtensorMap tA, tBb;
+  CUtensorMap tA, tBb, tBs;
   int rc;
   if ((rc = umma::make_tmap_2d(&tA, act, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if ((rc = umma::make_tmap_2d(&tBb, w_pad, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
+  if ((rc = umma::make_tmap_2d(&tBb, w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
+  if (NPASS == 3) {
+    if ((rc = umma::make_tmap_2d(&tBs, w_small, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
+  } else {
+    tBs = tBb;
+  }
   // epilogue inputs staged by TMA: one (CHUNK rows x 128 columns) box per present array
   static umma::EMaps em;
   {
@@ -235,7 +245,7 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_pad,
   const int grid = grid_override > 0 ? grid_override : (int)std::min<i64>(ntiles, device_sm_count());
   {
     LaunchScope ls(kind, st);
-    kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tA, tBb, em, gs, epi);
+    kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tA, tBb, tBs, em, gs, epi);
   }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
@@ -251,14 +261,14 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   // T_0 = A Z0 + E0 - X (+ V_0)
   {
     umma::UEpiT0<PS> epi{p->E0, p->X, p->L0, s.Tslab(0), make_bp(p->layers[0].beta1), w.V, B};
-    if ((rc = launch_umma<umma::UEpiT0<PS>, NPASS>(DLADMM_KIND_GEMM_T0, p->Z0, d, w.Ab, w.m256, w.dp, m, B, epi, st))) return rc;
+    if ((rc = launch_umma<umma::UEpiT0<PS>, NPASS>(DLADMM_KIND_GEMM_T0, p->Z0, d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st))) return rc;
   }
   for (int k = 0; k < p->K; ++k) {
     const dladmm_layer& l = p->layers[k];
     const size_t wi = (size_t)weight_index(p, k);
     {
       umma::UEpiZ<PS> epi{s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
-      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, w.V, m, w.Wb + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st)))
+      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, w.V, m, w.Wb + wi * w.d256 * w.mp, w.Ws + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st)))
         return rc;
     }
     {
@@ -270,7 +280,7 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
       epi.has_next = k + 1 < p->K;
       epi.b1n = make_bp(p->layers[k + 1 < p->K ? k + 1 : k].beta1);
       epi.V = w.V; epi.B = B;
-      if ((rc = launch_umma<umma::UEpiELT<FAM, PS>, NPASS>(DLADMM_KIND_GEMM_ELT, s.Zout(k), d, w.Ab, w.m256, w.dp, m, B, epi, st)))
+      if ((rc = launch_umma<umma::UEpiELT<FAM, PS>, NPASS>(DLADMM_KIND_GEMM_ELT, s.Zout(k), d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st)))
         return rc;
     }
   }
@@ -316,9 +326,9 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
   // transposed, split weights
   {
     SplitJobs jobs; jobs.n = 1;
-    jobs.j[0].src = p->A; jobs.j[0].big = w.Atb; jobs.j[0].small = nullptr;
+    jobs.j[0].src = p->A; jobs.j[0].big = w.Atb; jobs.j[0].small = w.Ats;
     dim3 grid((w.mp + 31) / 32, (w.d256 + 31) / 32, 1);
-    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<1><<<grid, 256, 0, st>>>(jobs, d, m, w.d256, w.mp); }
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, d, m, w.d256, w.mp); }
     DL_CUDA(cudaGetLastError());
     std::vector<const float*> uniq = WeightMap(p).uniq;
     for (size_t base = 0; base < uniq.size(); base += 32) {
@@ -327,10 +337,10 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
         size_t idx = base + i;
         wj.j[i].src = uniq[idx];
         wj.j[i].big = w.Wtb + idx * (size_t)w.m256 * w.dp;
-        wj.j[i].small = nullptr;
+        wj.j[i].small = w.Wts + idx * (size_t)w.m256 * w.dp;
       }
       dim3 g2((w.dp + 31) / 32, (w.m256 + 31) / 32, wj.n);
-      { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<1><<<g2, 256, 0, st>>>(wj, m, d, w.m256, w.dp); }
+      { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<NPASS><<<g2, 256, 0, st>>>(wj, m, d, w.m256, w.dp); }
       DL_CUDA(cudaGetLastError());
     }
   }
@@ -362,7 +372,7 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       epi.dx1 = sw.cZ; epi.ro = ro; epi.B = B;
       const bool lossz = g->loss_kind == 1;
       epi.Zk = s.Zout(k); epi.lz = lossz ? g->loss_alpha * g->loss_layer_weight[k] : 0.f; epi.lscale = lossz ? g->loss_scale : nullptr;
-      if ((rc = launch_umma<umma::UEpiBG1<PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DZ, sw.dR, m, w.Atb, w.d256, w.mp, d, B, epi, st, grid)))
+      if ((rc = launch_umma<umma::UEpiBG1<PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DZ, sw.dR, m, w.Atb, w.Ats, w.d256, w.mp, d, B, epi, st, grid)))
         return rc;
     }
     if (l.gW) {
@@ -389,7 +399,7 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       epi.dR = sw.dR; epi.cE = sw.cE; epi.cL = sw.cL;
       epi.ro = ro; epi.B = B;
       epi.lw = g->loss_kind == 1 ? g->loss_layer_weight[j] : 0.f; epi.lscale = g->loss_kind == 1 ? g->loss_scale : nullptr;
-      if ((rc = launch_umma<umma::UEpiBG2<FAM, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, d, w.Wtb + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
+      if ((rc = launch_umma<umma::UEpiBG2<FAM, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, d, w.Wtb + wi * w.m256 * w.dp, w.Wts + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
         return rc;
     }
     ReduceJobs jobs; jobs.n = 0;

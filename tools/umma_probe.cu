@@ -2,6 +2,7 @@
 // checked against a double-precision CPU product.  Development tool, not part of the library.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o umma_probe tools/umma_probe.cu
 //   ./umma_probe [n_feat Kdim B]
+#define UMMA_TRACE 1
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -48,8 +49,9 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   for (int j = 0; j < n_feat; ++j)
     for (int k = 0; k < Kdim; ++k) {
       float w = W[(size_t)j * Kdim + k];
-      Wb[(size_t)j * kpad + k] = w;
-      Ws[(size_t)j * kpad + k] = 0.f;
+      float big = NPASS == 3 ? rna_tf32(w) : w;
+      Wb[(size_t)j * kpad + k] = big;
+      Ws[(size_t)j * kpad + k] = w - big;
     }
   for (size_t i = 0; i < As.size(); ++i) As[i] = Act[i] - trunc_tf32(Act[i]);
   float *dWb, *dWs, *dA, *dAs, *dC;
@@ -68,6 +70,8 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   rc |= make_tmap_2d(&tBs, dWs, npad, kpad, kpad, KC, TILE_N, wsw);
   if (rc) { printf("tensor map creation failed\n"); exit(1); }
   GemmShape gs;
+  long long* dtr; CK(cudaMalloc(&dtr, 256 * 8 * 8)); CK(cudaMemset(dtr, 0, 256 * 8 * 8));
+  gs.trace = dtr;
   gs.n_feat = n_feat; gs.n_ntiles = npad / TILE_N; gs.k_chunks = (Kdim + KC - 1) / KC; gs.B = B;
   gs.n_btiles = (B + TILE_B - 1) / TILE_B;
   EpiStore epi{dC, B, 0u};
@@ -78,7 +82,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
   i64 ntiles = gs.n_btiles * gs.n_ntiles;
   int grid = (int)(ntiles < nsm ? ntiles : nsm);
-  kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, em, gs, epi);
+  kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, em, gs, epi);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> C((size_t)n_feat * B);
@@ -90,16 +94,25 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
     num += d * d; den += ref[i] * ref[i]; if (fabs(d) > maxabs) maxabs = fabs(d);
   }
   double rel = sqrt(num / den);
+  if (getenv("PROBE_TRACE")) {
+    std::vector<long long> tr(256 * 8);
+    CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
+    long long t0 = tr[0];
+    printf("chunk: prod_got tma_issued | split_saw_full split_done | mma_saw_ready mma_issued   (cycles since first event)\n");
+    for (int i = 0; i < 40; ++i)
+      printf("%3d: %7lld %7lld | %7lld %7lld | %7lld %7lld\n", i, tr[i * 8 + 0] - t0, tr[i * 8 + 1] - t0, tr[i * 8 + 2] - t0,
+             tr[i * 8 + 3] - t0, tr[i * 8 + 4] - t0, tr[i * 8 + 5] - t0);
+  }
   float ms = 0;
   if (reps > 0) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, em, gs, epi);
+    for (int r = 0; r < reps; ++r) kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, em, gs, epi);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
   }
-  printf("NPASS=%d KC=%d stages=%d smem=%d grid=%d: rel_l2=%.3e maxabs=%.3e nonfinite=%zu  time=%.3f ms  %.1f TFLOP/s\n", NPASS, KC,
-         SmemPlan<NPASS, KC>::STAGES, smem, grid, rel, maxabs, nbad, ms, ms > 0 ? 2.0 * n_feat * Kdim * B / ms / 1e9 : 0.0);
+  printf("%s NPASS=%d KC=%d smem=%d grid=%d: rel_l2=%.3e maxabs=%.3e nonfinite=%zu  time=%.3f ms  %.1f TFLOP/s\n", "single", NPASS, KC,
+         smem, grid, rel, maxabs, nbad, ms, ms > 0 ? 2.0 * n_feat * Kdim * B / ms / 1e9 : 0.0);
   cudaFree(dWb); cudaFree(dWs); cudaFree(dA); cudaFree(dAs); cudaFree(dC);
   return rel;
 }
