@@ -37,8 +37,8 @@ F_GEMM_PER_COL = 2.0 * M * D                      # one (d x m)(m x 1) or (m x d
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
-# (profiles/r01_ncu_full_summary.md), keyed by (precision, kernel kind)
-TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 463.263488e6 + 279.419136e6, ("tf32x3", "gemm_z"): 264.145920e6 + 213.329408e6}
+# (profiles/r01_ncu_full_summary_v4.md), keyed by (precision, kernel kind)
+TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 332.102144e6 + 216.018688e6, ("tf32x3", "gemm_z"): 197.864448e6 + 92.462848e6}
 
 
 def _peaks():
@@ -314,13 +314,13 @@ def run_ours(args):
         gemm_kinds = ("gemm_t0", "gemm_z", "gemm_elt")
         flops_per_launch = F_GEMM_PER_COL * B
         mma_passes = {"fp32": 1, "tf32": 1, "tf32x3": 3}[precision]
-        # algorithmic HBM bytes per launch of each fused product kernel: operands read +
-        # epilogue inputs read + outputs written; 3xTF32 carries the split operand arrays (V_big/V_small, Z_small)
-        x3 = precision == "tf32x3"
+        # algorithmic HBM bytes per launch of each fused product kernel: the activation
+        # operand + the epilogue inputs read + the outputs written (weights are L2-resident, 3xTF32 splits never
+        # leave shared memory, prox masks are not written in inference)
         bytes_per_launch = {
-            "gemm_t0": 4.0 * B * ((2 * D if x3 else D) + 3 * M + M + (2 * M if x3 else M)),
-            "gemm_z": 4.0 * B * ((2 * M if x3 else M) + D + (2 * D if x3 else D)),
-            "gemm_elt": 4.0 * B * ((2 * D if x3 else D) + 3 * M + 3 * M + (2 * M if x3 else M)),
+            "gemm_t0": 4.0 * B * (D + 3 * M + 2 * M),        # Z0 | E0, X, L0 | T0, V
+            "gemm_z": 4.0 * B * (M + D + D),                 # V | Z_{k-1} | Z_k
+            "gemm_elt": 4.0 * B * (D + 3 * M + 4 * M),       # Z_k | X, E_{k-1}, L_{k-1} | E_k, T_{k+1}, L_k, V
         }
         avg_ms = dom_ms / dom_n
         tensor_peak = peaks["tf32_tflops"] / mma_passes

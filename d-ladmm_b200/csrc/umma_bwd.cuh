@@ -49,23 +49,26 @@ template <bool PS>
 struct UEpiBG1 {
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 3;                    // gZ_k, carried dZ, Z_k (fused loss) -- each optional
-  struct State { float red[1]; int lane; float lsc; int o_gz, o_cz, o_zk; };
+  struct State { float red[1]; int lane; float lsc; int o_gz, o_cz, o_zk, o_mk; };
   struct Pre { unsigned mk[CHUNK]; };
   const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
   BP th1; float* dx1; RedOut ro; i64 B;
   const float* __restrict__ Zk; float lz; const float* __restrict__ lscale;   // fused L1-L1 loss cotangent on Z_k
   uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = gZ; p[1] = cZin; p[2] = lscale ? Zk : nullptr; }
+  const uint8_t* host_mask() const { return maskZ; }
   __device__ __forceinline__ void begin(State& st) const {
     st.red[0] = 0.f; st.lane = threadIdx.x & 31;
     st.lsc = lscale ? lz * __ldg(lscale) : 0.f;
     st.o_gz = slot_rank(in_mask, 0) * SUBF(CHUNK); st.o_cz = slot_rank(in_mask, 1) * SUBF(CHUNK); st.o_zk = slot_rank(in_mask, 2) * SUBF(CHUNK);
+    st.o_mk = (in_mask & EIN_MASK_BIT) ? __popc(in_mask & ~EIN_MASK_BIT) * SUBF(CHUNK) * 4 : -1;   // byte offset of the staged mask
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[1] = {SL_TH1};
     if (th1.g && th1.period == 0) red_finish<PS, 1>(ro, slots, st.red, entry, lane);
   }
   __device__ __forceinline__ void prefetch(Pre& pre, int row0, i64 b, bool valid, int n_feat) const {
+    if (in_mask & EIN_MASK_BIT) return;             // mask bytes come through the staging ring
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const bool ok = valid && row0 + i < n_feat;
@@ -84,7 +87,8 @@ struct UEpiBG1 {
       if (st.o_gz >= 0) dz += slot[st.o_gz + i * TILE_B + col];
       if (st.o_cz >= 0) dz += slot[st.o_cz + i * TILE_B + col];
       if (st.o_zk >= 0) dz += st.lsc * sgn(slot[st.o_zk + i * TILE_B + col]);
-      const float mp = (pre.mk[i] & 1u) ? 1.f : 0.f, mn = (pre.mk[i] & 2u) ? 1.f : 0.f;
+      const unsigned mk = st.o_mk >= 0 ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
+      const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_contrib<PS>(th1, ro, SL_TH1, st.red[0], row, b, group, ok, dz * (mn - mp), st.lane);
       if (ok) dx1[off] = o;
@@ -96,9 +100,9 @@ struct UEpiBG1 {
 // writes dR for the next A^T dR product, carried dE and dL.
 template <int FAM, bool PS>
 struct UEpiBG2 {
-  static constexpr int CHUNK = 4;
+  static constexpr int CHUNK = 4;     // up to 10 staged arrays + mask per element: keep one ring slot small
   static constexpr int NIN = 10;   // L_{k-1}, T_k, cL | cE, E_{k-1}, L_{k-2}, E_{k-2}(B) | gL, gE, gT  (all but the first three optional)
-  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; };
+  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };
   struct Pre { unsigned mk[CHUNK]; };
   // layer k
   const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
@@ -117,6 +121,7 @@ struct UEpiBG2 {
     p[6] = (has_prev && FAM == DLADMM_FAMILY_B) ? Ep : nullptr;
     p[7] = has_prev ? gL : nullptr; p[8] = has_prev ? gE : nullptr; p[9] = has_prev ? gT : nullptr;
   }
+  const uint8_t* host_mask() const { return (has_prev && FAM != DLADMM_FAMILY_C) ? maskE : nullptr; }
   __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
     for (int r = 0; r < 6; ++r) st.red[r] = 0.f;
@@ -126,12 +131,14 @@ struct UEpiBG2 {
     st.lsc = lscale ? lw * __ldg(lscale) : 0.f;
 #pragma unroll
     for (int i = 0; i < NIN; ++i) st.o[i] = slot_rank(in_mask, i) * SUBF(CHUNK);
+    st.o_mk = (in_mask & EIN_MASK_BIT) ? __popc(in_mask & ~EIN_MASK_BIT) * SUBF(CHUNK) * 4 : -1;
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
     red_finish<PS, 6>(ro, slots, st.red, entry, lane);
   }
   __device__ __forceinline__ void prefetch(Pre& pre, int row0, i64 b, bool valid, int n_feat) const {
+    if (in_mask & EIN_MASK_BIT) return;             // mask bytes come through the staging ring
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const bool ok = valid && has_prev && FAM != DLADMM_FAMILY_C && row0 + i < n_feat;
@@ -169,12 +176,13 @@ struct UEpiBG2 {
       const float dTt = dT + vbL * dL;
       const float dEt = dE + dTt;
       float dRv, nE, nL;
+      const unsigned mk = st.o_mk >= 0 ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
       if (FAM == DLADMM_FAMILY_B) {
         const float ep = in(st, slot, 6, i, col);
         const float vb2 = st.b2.at(row, b), vs2 = st.ss2.at(row, b);
         const float that = (tn - ek) + ep;
         const float q = lpp + vb2 * that;
-        const float mp = (pre.mk[i] & 1u) ? 1.f : 0.f, mn = (pre.mk[i] & 2u) ? 1.f : 0.f;
+        const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
         const float du = dEt * (mp + mn);
         red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
         const float dQ = -vs2 * du;
@@ -184,7 +192,7 @@ struct UEpiBG2 {
         dRv = dTt + dThat; nE = du + dThat; nL = dL + dQ;
       } else if (FAM == DLADMM_FAMILY_A) {
         const float vb2 = st.b2.at(row, b);
-        const float mp = (pre.mk[i] & 1u) ? 1.f : 0.f, mn = (pre.mk[i] & 2u) ? 1.f : 0.f;
+        const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
         const float du = dEt * (mp + mn);
         red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
         red_contrib<PS>(b2, ro, SL_B2, st.red[3], row, b, group, ok, -du * lpp, st.lane);

@@ -54,6 +54,7 @@ struct UEpiT0 {
   const float* __restrict__ E0; const float* __restrict__ X; const float* __restrict__ L0; float* __restrict__ T0;
   BP b1; float* __restrict__ V; i64 B; uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = E0; p[1] = X; p[2] = L0; }
+  const uint8_t* host_mask() const { return nullptr; }
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
@@ -83,6 +84,7 @@ struct UEpiZ {
   const float* __restrict__ Zp; float* __restrict__ Zk; uint8_t* __restrict__ maskZ;
   BP th1; BP ss1; i64 B; uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; }
+  const uint8_t* host_mask() const { return nullptr; }
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
@@ -116,6 +118,7 @@ struct UEpiELT {
   int has_next; BP b1n; float* __restrict__ V;
   i64 B; uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = X; p[1] = Lp; p[2] = FAM == DLADMM_FAMILY_B ? Ep : nullptr; }
+  const uint8_t* host_mask() const { return nullptr; }
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
   }

@@ -241,7 +241,8 @@ struct GemmShape {
 constexpr int MAX_EIN = 10;              // staged input arrays per epilogue
 constexpr int RING_BYTES = 72 * 1024;    // staging ring; depth = RING_BYTES / (present arrays * CHUNK * 512 B)
 
-struct EMaps { CUtensorMap m[MAX_EIN]; };
+struct EMaps { CUtensorMap m[MAX_EIN]; CUtensorMap mk; };   // float inputs + the 1-byte prox mask of the chunk
+constexpr uint32_t EIN_MASK_BIT = 1u << 31;                 // in_mask bit: the mask bytes are staged too
 
 template <int NPASS, int KC>
 struct SmemPlan {
@@ -290,8 +291,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 ntiles = gs.n_btiles * gs.n_ntiles;
   // staging ring geometry (uniform over the CTA)
-  const int nin = __popc(epi.in_mask);
-  const int slot_bytes = nin * SUB_BYTES;
+  const int nin = __popc(epi.in_mask & ~EIN_MASK_BIT);
+  const bool mk_staged = (epi.in_mask & EIN_MASK_BIT) != 0;
+  const int slot_bytes = nin * SUB_BYTES + (mk_staged ? CHK * TILE_B : 0);
   int depth = nin > 0 ? RING_BYTES / slot_bytes : 1;
   if (depth > MAX_RING_DEPTH) depth = MAX_RING_DEPTH;
 
@@ -416,6 +418,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     dst += SUB_BYTES;
                   }
                 }
+                if (mk_staged) tma_load_2d(dst, &emaps.mk, &efull[s], b0, row0);
               }
             }
             __syncwarp();
@@ -516,6 +519,23 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // 2D fp32 row-major matrix (rows x cols, pitch in elements); box = (box_cols x box_rows); OOB reads give zeros
+// 2D uint8 row-major matrix (prox masks), no swizzle
+inline int make_tmap_2d_u8(CUtensorMap* out, const uint8_t* base, i64 rows, i64 cols, i64 pitch, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DLADMM_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (u8) failed (%d) rows=%lld cols=%lld pitch=%lld", (int)r, rows, cols, pitch);
+    return DLADMM_ERR_CUDA;
+  }
+  return DLADMM_OK;
+}
+
 inline int make_tmap_2d(CUtensorMap* out, const float* base, i64 rows, i64 cols, i64 pitch, int box_cols, int box_rows,
                         CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();

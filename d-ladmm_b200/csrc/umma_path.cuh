@@ -228,6 +228,12 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
     }
     for (int i = 0; i < umma::MAX_EIN; ++i)
       if (!(epi.in_mask & (1u << i))) em.m[i] = tBb;       // placeholder, never dereferenced
+    em.mk = tBb;
+    // the 1-byte prox masks ride the same ring when TMA can address them (16-byte multiple pitch)
+    if (epi.host_mask() && epi.in_mask != 0 && (B % 16) == 0) {
+      if ((rc = umma::make_tmap_2d_u8(&em.mk, epi.host_mask(), n_feat, B, B, umma::TILE_B, Epi::CHUNK))) return rc;
+      epi.in_mask |= umma::EIN_MASK_BIT;
+    }
   }
   umma::GemmShape gs;
   gs.n_feat = n_feat;

@@ -75,7 +75,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   gs.n_feat = n_feat; gs.n_ntiles = npad / TILE_N; gs.k_chunks = (Kdim + KC - 1) / KC; gs.B = B;
   gs.n_btiles = (B + TILE_B - 1) / TILE_B;
   EpiStore epi{dC, B, 0u};
-  static EMaps em; for (int i = 0; i < MAX_EIN; ++i) em.m[i] = tBb;
+  static EMaps em; for (int i = 0; i < MAX_EIN; ++i) em.m[i] = tBb; em.mk = tBb;
   auto kern = umma_gemm_kernel<EpiStore, NPASS, KC>;
   const int smem = SmemPlan<NPASS, KC>::TOTAL;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
