@@ -183,3 +183,31 @@ def test_native_library_is_the_code_that_runs():
     assert "libdladmm.so" in maps
     caps = dl.query_device(0)
     assert caps["supported"] == 1 and caps["cc_major"] == 10 and caps["sm_count"] >= 100
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_config5_shape_multiple_feature_tiles(precision):
+    """BASELINE config 5 shape (m=1000, d=2000): several 256-row feature tiles per product, K-loop over 2000;
+    forward against the fp32 oracle and training gradients against fp64 autograd, at a batch the CPU finishes fast."""
+    torch.manual_seed(7)
+    m, d, B, K = 1000, 2000, 256, 3
+    A, X = syn(m, d, B, seed=77)
+    Z0 = torch.zeros(d, B); E0 = torch.zeros(m, B); L0 = torch.zeros(m, B)
+    model = dl.DLADMMNetScalar(m, 1, d, B, A, Z0, E0, L0, K, precision=precision)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    loss, outs = model.l1l1_loss(X.cuda(), 0.001, [0.5, 0.5, 1.0])
+    loss.backward()
+    Zo, Eo, Lo, To = orc.forward("scalar", sd, A, X, Z0, E0, L0, K)
+    tol = 5e-5 if precision == "tf32x3" else 1e-5
+    for k in range(K):
+        assert rel_l2(outs[0][k].cpu(), Zo[k], floor=1e-3) < tol, (k, rel_l2(outs[0][k].cpu(), Zo[k]))
+        assert rel_l2(outs[2][k].cpu(), Lo[k], floor=1e-2) < tol
+    d64 = lambda t: t.double()
+    lref, gref = orc.autograd_grads("scalar", {k: d64(v) for k, v in sd.items()}, d64(A), d64(X), d64(Z0), d64(E0), d64(L0), K,
+                                    lambda Z, E, L, T: orc.l1l1_loss(Z, E, L, T, d64(A), d64(X), alpha=0.001, decay=0.5))
+    assert abs(loss.item() - lref.item()) < 1e-4 * abs(lref.item())
+    for n, p in model.named_parameters():
+        floor = 2e-3 if p.numel() == 1 else 1e-4 * max(1.0, float(gref[n].abs().max()) * p.numel() ** 0.5)
+        # the L1 objective is non-smooth: sign(E_k - T_{k+1}) and the prox masks flip for entries within rounding of
+        # zero, and with only 256 columns a handful of flips moves dW by ~0.5 % in 3xTF32
+        assert rel_l2(p.grad.cpu(), gref[n], floor=floor) < (1e-2 if precision == "tf32x3" else 2e-3), n
