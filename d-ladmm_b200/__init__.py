@@ -11,12 +11,13 @@ from .net import (DLADMMNet, DLADMMNetFull, DLADMMNetLasso, DLADMMNetLena, DLADM
 from .function import UnrolledLADMM, LayerSpec, run_forward
 from .gen_syn import gen_syn_data, SynData
 from .objective import l1l1_objective
+from .mu_updater import mu_updater_dict
 from .sharding import column_shard, allreduce_gradients, ShardedTrainer
 
 __all__ = ["DLADMMNet", "DLADMMNetScalar", "DLADMMNetFull", "DLADMMNetTied", "DLADMMNetLasso", "DLADMMNetLena",
            "DLADMMNetLtheta", "VARIANT_CLASSES", "UnrolledLADMM", "LayerSpec", "run_forward", "gen_syn_data",
            "SynData", "l1l1_objective", "column_shard", "allreduce_gradients", "ShardedTrainer",
-           "default_precision", "library_path", "query_device"]
+           "default_precision", "library_path", "query_device", "mu_updater_dict"]
 
 
 def library_path():

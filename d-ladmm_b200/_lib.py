@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdladmm.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
@@ -31,7 +31,7 @@ class Problem(C.Structure):
                 ("layers", C.POINTER(Layer)),
                 ("Z", C.c_void_p), ("E", C.c_void_p), ("L", C.c_void_p), ("T", C.c_void_p),
                 ("maskZ", C.c_void_p), ("maskE", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("T_init", C.c_void_p)]
 
 
 class Cotangents(C.Structure):
@@ -54,7 +54,11 @@ class GenDesc(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
-EXPORTS = ["dladmm_workspace_bytes", "dladmm_forward", "dladmm_backward", "dladmm_gen_workspace_bytes",
+class SgPair(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int32)]
+
+
+EXPORTS = ["dladmm_sg_norm", "dladmm_sg_select", "dladmm_workspace_bytes", "dladmm_forward", "dladmm_backward", "dladmm_gen_workspace_bytes",
            "dladmm_gen_syn", "dladmm_objective", "dladmm_query", "dladmm_last_error", "dladmm_launch_count",
            "dladmm_profile_start", "dladmm_profile_stop"]
 
@@ -86,6 +90,12 @@ def load():
     lib.dladmm_gen_syn.argtypes = [C.POINTER(GenDesc), C.c_void_p]
     lib.dladmm_objective.restype = C.c_int
     lib.dladmm_objective.argtypes = [C.POINTER(Problem), C.c_float, C.c_void_p, C.c_void_p]
+    lib.dladmm_sg_norm.restype = C.c_int
+    lib.dladmm_sg_norm.argtypes = [C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    lib.dladmm_sg_select.restype = C.c_int
+    lib.dladmm_sg_select.argtypes = [C.c_int32, C.POINTER(SgPair), C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                     C.c_void_p]
     lib.dladmm_query.restype = C.c_int
     lib.dladmm_query.argtypes = [C.c_int, C.POINTER(Caps)]
     lib.dladmm_launch_count.restype = C.c_int64

@@ -232,8 +232,10 @@ static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_
   const int m = p->m, d = p->d;
   const i64 B = p->B;
   int rc;
-  // T_0 = A Z0 + E0 - X
-  {
+  // T_0 = A Z0 + E0 - X (or given by the caller)
+  if (p->T_init) {
+    DL_CUDA(cudaMemcpyAsync(s.Tslab(0), p->T_init, sizeof(float) * (size_t)m * B, cudaMemcpyDeviceToDevice, st));
+  } else {
     BPlain bl{p->Z0, B};
     EpiT0 epi{p->E0, p->X, s.Tslab(0), B};
     if ((rc = launch_simt(DLADMM_KIND_GEMM_T0, m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;

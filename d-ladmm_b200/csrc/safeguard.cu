@@ -1,0 +1,84 @@
+// Safeguarded-evaluation helpers (test_syn_l1l1_scalar.py:163-176, 238-274): the column norm of the safeguard
+// operator S and the per-column selection between the learned and the classical iterate.  The two matrix products
+// of every KM / learned step run through dladmm_forward with K = 1 and T_init.
+#include "common.cuh"
+
+namespace dladmm {
+
+// out[b] = || [ beta * Tn[:,b] ; c * (En[:,b] - 2 Ek[:,b] + Ep[:,b]) ] ||_2      (test_syn_l1l1_scalar.py:173, two_norm)
+static __global__ void __launch_bounds__(256) sg_norm_kernel(int m, i64 B, float beta, float c, const float* __restrict__ Tn,
+                                                             const float* __restrict__ En, const float* __restrict__ Ek,
+                                                             const float* __restrict__ Ep, float* __restrict__ out) {
+  const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int i = 0; i < m; ++i) {
+    const i64 off = (i64)i * B + b;
+    const float t = beta * Tn[off];
+    const float e = c * ((En[off] - 2.f * Ek[off]) + Ep[off]);
+    s += t * t + e * e;
+  }
+  out[b] = sqrtf(s);
+}
+
+// keep[b] = (snorm[b] < one_minus_delta * mu[b]) ; out = keep ? a : b, column-wise, for several (rows x B) arrays
+struct SelJob { const float* a; const float* b; float* out; int rows; };
+struct SelJobs { int n; SelJob j[6]; };
+
+static __global__ void __launch_bounds__(256) sg_keep_kernel(i64 B, const float* __restrict__ snorm, const float* __restrict__ mu,
+                                                             float one_minus_delta, float* __restrict__ keep) {
+  const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (b < B) keep[b] = snorm[b] < one_minus_delta * mu[b] ? 1.f : 0.f;
+}
+
+static __global__ void __launch_bounds__(256) sg_select_kernel(SelJobs jobs, i64 B, const float* __restrict__ keep) {
+  const SelJob jb = jobs.j[blockIdx.y];
+  const i64 n = (i64)jb.rows * B;
+  for (i64 idx = (i64)blockIdx.x * 256 + threadIdx.x; idx < n; idx += (i64)gridDim.x * 256) {
+    const i64 b = idx % B;
+    jb.out[idx] = keep[b] != 0.f ? jb.a[idx] : jb.b[idx];
+  }
+}
+
+}  // namespace dladmm
+
+using namespace dladmm;
+
+extern "C" {
+
+int dladmm_sg_norm(int32_t m, int64_t B, float beta, float c, const float* Tn, const float* En, const float* Ek, const float* Ep,
+                   float* out, void* stream) {
+  DL_REQUIRE(m > 0 && B >= 0 && Tn && En && Ek && Ep && out, "sg_norm: bad arguments");
+  if (B == 0) return DLADMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+    sg_norm_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, B, beta, c, Tn, En, Ek, Ep, out); }
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, const float* mu,
+                     float one_minus_delta, float* keep, void* stream) {
+  DL_REQUIRE(n_arrays >= 0 && n_arrays <= 6 && (n_arrays == 0 || pairs) && snorm && mu && keep, "sg_select: bad arguments");
+  if (B == 0) return DLADMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+    sg_keep_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, snorm, mu, one_minus_delta, keep); }
+  DL_CUDA(cudaGetLastError());
+  if (n_arrays == 0) return DLADMM_OK;
+  SelJobs jobs; jobs.n = n_arrays;
+  int maxrows = 1;
+  for (int i = 0; i < n_arrays; ++i) {
+    DL_REQUIRE(pairs[i].a && pairs[i].b && pairs[i].out && pairs[i].rows > 0, "sg_select: pair %d incomplete", i);
+    jobs.j[i].a = pairs[i].a; jobs.j[i].b = pairs[i].b; jobs.j[i].out = pairs[i].out; jobs.j[i].rows = pairs[i].rows;
+    maxrows = pairs[i].rows > maxrows ? pairs[i].rows : maxrows;
+  }
+  i64 blocks = ((i64)maxrows * B + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+    sg_select_kernel<<<dim3((unsigned)blocks, n_arrays), 256, 0, st>>>(jobs, B, keep); }
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+}  // extern "C"

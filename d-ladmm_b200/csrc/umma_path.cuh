@@ -264,8 +264,14 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   const i64 B = p->B;
   int rc;
   if ((rc = uprepare_weights<NPASS>(p, w, st))) return rc;
-  // T_0 = A Z0 + E0 - X (+ V_0)
-  {
+  // T_0 = A Z0 + E0 - X (+ V_0), or T_0 given by the caller
+  if (p->T_init) {
+    DL_CUDA(cudaMemcpyAsync(s.Tslab(0), p->T_init, sizeof(float) * (size_t)m * B, cudaMemcpyDeviceToDevice, st));
+    const i64 quads = (B + 3) / 4;
+    { LaunchScope ls(DLADMM_KIND_PREP, st);
+      make_v_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(p->L0, p->T_init, make_bp(p->layers[0].beta1), m, B, w.V); }
+    DL_CUDA(cudaGetLastError());
+  } else {
     umma::UEpiT0<PS> epi{p->E0, p->X, p->L0, s.Tslab(0), make_bp(p->layers[0].beta1), w.V, B};
     if ((rc = launch_umma<umma::UEpiT0<PS>, NPASS>(DLADMM_KIND_GEMM_T0, p->Z0, d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st))) return rc;
   }

@@ -69,7 +69,7 @@ def _build_layers(spec, params, grads):
     return arr
 
 
-def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, for_backward):
+def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, for_backward, T_init=None):
     lib = _lib.load()
     p = _lib.Problem()
     p.abi_version = _lib.ABI_VERSION
@@ -83,6 +83,7 @@ def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only
     p.Z, p.E, p.L, p.T = Z.data_ptr(), E.data_ptr(), L.data_ptr(), T.data_ptr()
     p.maskZ = maskZ.data_ptr() if maskZ is not None else None
     p.maskE = maskE.data_ptr() if maskE is not None else None
+    p.T_init = T_init.data_ptr() if T_init is not None else None
     nbytes = lib.dladmm_workspace_bytes(C.byref(p), 1 if for_backward else 0)
     ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=X.device)
     p.workspace = ws.data_ptr()
@@ -106,8 +107,9 @@ def _check_inputs(spec, A, X, Z0, E0, L0, params):
                            (B, tuple(Z0.shape), tuple(E0.shape), tuple(L0.shape)))
 
 
-def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False):
-    """Launch the K-layer forward.  Returns stacked (Z, E, L, T, maskZ, maskE)."""
+def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_init=None):
+    """Launch the K-layer forward.  Returns stacked (Z, E, L, T, maskZ, maskE).  `T_init` (m,B): T_0 supplied by the
+    caller instead of A Z0 + E0 - X (single-layer steps from an arbitrary state)."""
     lib = _lib.load()
     _check_inputs(spec, A, X, Z0, E0, L0, params)
     X = X.contiguous()
@@ -125,9 +127,14 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False):
         maskZ = torch.empty((K, d, B), dtype=torch.uint8, device=dev)
         if spec.family != _lib.FAMILY_C:
             maskE = torch.empty((K, m, B), dtype=torch.uint8, device=dev)
+    if T_init is not None:
+        _require_cuda_f32("T_init", T_init)
+        T_init = T_init.contiguous()
+        if tuple(T_init.shape) != (m, B):
+            raise RuntimeError("T_init must be (m, B)")
     layers = _build_layers(spec, params, None)
     with torch.cuda.device(dev):
-        p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, False)
+        p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, False, T_init)
         _lib.check(lib.dladmm_forward(C.byref(p), torch.cuda.current_stream(dev).cuda_stream))
         ws.record_stream(torch.cuda.current_stream(dev))
     return Z, E, L, T, maskZ, maskE

@@ -13,13 +13,16 @@ PyTorch-eager fallback -- calling ``forward`` without the library or without a C
     lena      main_lena.py:16-102                               Z, E, L
     ltheta    main_syn_l1l1_ltheta.py:16-108                    Z, E, L
 """
+import ctypes as C
 import os
+from math import sqrt
 
 import torch
 import torch.nn as nn
 
 from . import _lib
 from .function import LayerSpec, UnrolledLADMM, UnrolledLADMML1L1, run_forward
+from .mu_updater import mu_updater_dict
 
 _FAMILY = {"lena": _lib.FAMILY_A, "ltheta": _lib.FAMILY_A, "scalar": _lib.FAMILY_B, "full": _lib.FAMILY_B,
            "tied": _lib.FAMILY_B, "lasso": _lib.FAMILY_C}
@@ -223,6 +226,115 @@ class DLADMMNet(nn.Module):
             raise ValueError("layer_weights must have one entry per layer")
         loss, Z, E, L, T = UnrolledLADMML1L1.apply(spec, float(alpha), w, self.A, x, self.Z0, self.E0, self.L0, *params)
         return loss, self._as_lists(Z, E, L, T)
+
+
+    # ---- classical LADMM step, safeguard operator and safeguarded evaluation (family B) -------------------------------
+    def two_norm(self, z, dim=0):
+        """test_syn_l1l1_scalar.py:126-128"""
+        return (z ** 2).sum(dim=dim).sqrt()
+
+    def _one_layer(self, spec1, params, Zk, Ek, Lk, Tk, X):
+        Z, E, L, T, _, _ = run_forward(spec1, self.A, X, Zk, Ek, Lk, [p.detach() for p in params], want_masks=False, T_init=Tk)
+        return Z[0], E[0], L[0], T[1]
+
+    def _km_spec(self, beta, ss1, ss2, alpha):
+        key = (float(beta), float(ss1), float(ss2), float(alpha))
+        cache = self.__dict__.setdefault("_km_cache", {})
+        if key not in cache:
+            dev = self.A.device
+            s = lambda v: torch.full((1, 1), float(v), dtype=torch.float32, device=dev)
+            params = [self.A.t().contiguous(), s(beta), s(ss1), s(ss2), s(float(ss1) * float(alpha)), s(ss2)]
+            slots = {"beta1": 1, "beta2": 1, "beta3": 1, "ss1": 2, "ss2": 3, "theta1": 4, "theta2": 5}
+            spec = LayerSpec(_lib.FAMILY_B, self.m, self.d, 1, _lib.PRECISIONS[self.precision], [slots], [0])
+            cache.clear()
+            cache[key] = (spec, params)
+        return cache[key]
+
+    def KM(self, Zk, Ek, Lk, Tk, X, **kwargs):
+        """One classical LADMM iteration (test_syn_l1l1_scalar.py:131-160): the learned family-B layer with W = A^T scaled
+        by ss1, all betas = beta, thresholds ss1*alpha and ss2.  Returns (Varn, Zn, En, Tn, Ln)."""
+        if _FAMILY[self.variant] != _lib.FAMILY_B:
+            raise NotImplementedError("KM/S/safeguard are built for the family-B variants (scalar, full, tied)")
+        beta = float(kwargs.get("beta", 1.0))
+        ss1 = kwargs.get("ss1", None)
+        ss1 = 0.999 / self.L.item() if ss1 is None else float(ss1)
+        ss2 = float(kwargs.get("ss2", 0.3))
+        alpha = float(kwargs.get("alpha", 0.01))
+        spec1, params = self._km_spec(beta, ss1, ss2, alpha)
+        Zn, En, Ln, Tn = self._one_layer(spec1, params, Zk, Ek, Lk, Tk, X)
+        return Lk + beta * Tk, Zn, En, Tn, Ln
+
+    def S(self, Zk, Ek, Lk, Tk, X, Ep, **kwargs):
+        """Safeguard operator (test_syn_l1l1_scalar.py:163-176): [beta*T^{k+1} ; c*(E^{k+1} - 2 E^k + E^{k-1})]."""
+        beta, ss2 = 1.0, 0.3
+        _, _, En, Tn, _ = self.KM(Zk, Ek, Lk, Tk, X, beta=beta, ss2=ss2, alpha=kwargs.get("alpha", 0.01))
+        c1 = beta * ss2
+        c = sqrt(c1 / (1 - c1))
+        return torch.cat([beta * Tn, c * (En - 2 * Ek + Ep)])
+
+    def _s_norm(self, Zk, Ek, Lk, Tk, X, Ep, alpha):
+        beta, ss2 = 1.0, 0.3
+        _, _, En, Tn, _ = self.KM(Zk, Ek, Lk, Tk, X, beta=beta, ss2=ss2, alpha=alpha)
+        c1 = beta * ss2
+        out = torch.empty(X.shape[1], dtype=torch.float32, device=X.device)
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        _lib.check(_lib.load().dladmm_sg_norm(self.m, X.shape[1], beta, sqrt(c1 / (1 - c1)), Tn.data_ptr(), En.data_ptr(),
+                                              Ek.contiguous().data_ptr(), Ep.contiguous().data_ptr(), out.data_ptr(), stream))
+        return out
+
+    def forward_safeguarded(self, x, use_learned, use_safeguard, continued=False, K=None, num_iter=200, delta=-99.0,
+                            mu_k_method="None", mu_k_param=0.0, alpha=0.01):
+        """The evaluation forward of test_syn_l1l1_scalar.py:179-317: per layer the classical KM step, the learned step,
+        the safeguard test ||S(u_L2O)|| < (1-delta)*mu_k per column, the per-column selection and the mu_k update.
+        Returns (Z, E, L, T) lists, plus sg_count (columns that fell back to KM, per layer) when both flags are set."""
+        if _FAMILY[self.variant] != _lib.FAMILY_B:
+            raise NotImplementedError("forward_safeguarded is built for the family-B variants (scalar, full, tied)")
+        layers = self.layers
+        if K is None:
+            K = layers if (not continued and (use_learned or use_safeguard)) else num_iter
+        X = x.contiguous()
+        B = X.shape[1]
+        lib = _lib.load()
+        spec, params = self._spec_and_params()
+        with torch.no_grad():
+            T = [self.A.mm(self.Z0) + self.E0 - X]
+            Z, E, L = [], [], []
+            return_cnt = use_learned and use_safeguard
+            if return_cnt:
+                mu_k = self._s_norm(self.Z0, self.E0, self.L0, T[-1], X, self.E0, alpha)
+                updater = mu_updater_dict[mu_k_method](mu_k, mu_k_param)
+                sg_count = [0.0] * layers
+            for k in range(K):
+                if continued and k == layers:
+                    use_learned = use_safeguard = False
+                Zp, Ep_, Lp = (self.Z0, self.E0, self.L0) if k == 0 else (Z[-1], E[-1], L[-1])
+                _, Zn_KM, En_KM, Tn_KM, Ln_KM = self.KM(Zp, Ep_, Lp, T[-1], X, alpha=alpha)
+                if use_learned:
+                    spec1 = LayerSpec(spec.family, self.m, self.d, 1, spec.precision, [spec.slots[k]], [spec.weights[k]], spec.fixed)
+                    Zn, En, Ln, Tn = self._one_layer(spec1, params, Zp, Ep_, Lp, T[-1], X)
+                if use_safeguard:
+                    assert use_learned
+                    s_norm = self._s_norm(Zn, En, Ln, Tn, X, Ep_, alpha)
+                    keep = torch.empty(B, dtype=torch.float32, device=X.device)
+                    outs = [torch.empty_like(t) for t in (Zn, En, Tn, Ln)]
+                    pairs = (_lib.SgPair * 4)()
+                    for i, (a, b_, o) in enumerate(zip((Zn, En, Tn, Ln), (Zn_KM, En_KM, Tn_KM, Ln_KM), outs)):
+                        pairs[i].a, pairs[i].b, pairs[i].out, pairs[i].rows = a.data_ptr(), b_.data_ptr(), o.data_ptr(), a.shape[0]
+                    mu_vec = mu_k if isinstance(mu_k, torch.Tensor) else torch.full((B,), float(mu_k), device=X.device)
+                    _lib.check(lib.dladmm_sg_select(4, pairs, B, s_norm.data_ptr(), mu_vec.contiguous().data_ptr(),
+                                                    float(1.0 - delta), keep.data_ptr(),
+                                                    torch.cuda.current_stream(X.device).cuda_stream))
+                    mu_k = updater.step(s_norm, keep)
+                    Z.append(outs[0]); E.append(outs[1]); T.append(outs[2]); L.append(outs[3])
+                    if k < layers:
+                        sg_count[k] = float(B - keep.sum().item())
+                elif use_learned:
+                    Z.append(Zn); E.append(En); T.append(Tn); L.append(Ln)
+                else:
+                    Z.append(Zn_KM); E.append(En_KM); T.append(Tn_KM); L.append(Ln_KM)
+        if return_cnt:
+            return Z, E, L, T, sg_count
+        return Z, E, L, T
 
 
 class DLADMMNetScalar(DLADMMNet):

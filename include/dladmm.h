@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLADMM_ABI_VERSION 2
+#define DLADMM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DLADMM_API __attribute__((visibility("default")))
@@ -111,6 +111,9 @@ typedef struct dladmm_problem {
   uint8_t* maskE;         /* out (K,m,B) or NULL: same for the E prox (families A,B) */
   void* workspace;
   size_t workspace_bytes;
+  const float* T_init;    /* optional (m,B): T_0 supplied by the caller instead of A Z0 + E0 - X (it is copied to T[0]).
+                             Used to advance ONE layer from an arbitrary state (Z0,E0,L0,T_init), e.g. the classical KM
+                             step and the safeguard operator of test_syn_l1l1_scalar.py:131-176 */
 } dladmm_problem;
 
 /* Upstream cotangents for backward; each may be NULL (= zero).  Shapes as the forward outputs. */
@@ -174,6 +177,15 @@ DLADMM_API int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream);
  * k = 0..K-1, from the iterates a forward (last_only == 0) left in p->Z/E/T, using X - A Z_k = E_k - T_{k+1}
  * (no extra matrix product).  `out` is K floats on the device, overwritten. */
 DLADMM_API int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* stream);
+
+/* Safeguarded evaluation (test_syn_l1l1_scalar.py:163-176, 238-274).
+ * dladmm_sg_norm:   out[b] = || [ beta*Tn[:,b] ; c*(En[:,b] - 2 Ek[:,b] + Ep[:,b]) ] ||_2   (the norm of S(u), all (m,B))
+ * dladmm_sg_select: keep[b] = snorm[b] < one_minus_delta * mu[b]; out = keep ? a : b column-wise for each pair. */
+typedef struct dladmm_sg_pair { const float* a; const float* b; float* out; int32_t rows; } dladmm_sg_pair;
+DLADMM_API int dladmm_sg_norm(int32_t m, int64_t B, float beta, float c, const float* Tn, const float* En, const float* Ek,
+                              const float* Ep, float* out, void* stream);
+DLADMM_API int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, const float* mu,
+                                float one_minus_delta, float* keep, void* stream);
 
 DLADMM_API int dladmm_query(int device, dladmm_caps* caps);
 

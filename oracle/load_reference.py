@@ -80,3 +80,32 @@ def run(model, x):
         return out
     Z, E, L = out
     return Z, E, L, None
+
+
+def load_mu_updater_dict():
+    """The reference's own mu_updater.py (numpy-only import), loaded as a module object."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_mu_updater", os.path.join(REFERENCE_ROOT, "mu_updater.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.mu_updater_dict
+
+
+def load_eval_class(layers, alpha=0.01, delta=-99.0, mu_k_method="None", mu_k_param=0.0, continued=False, num_iter=200,
+                    use_learned=True, use_safeguard=True):
+    """The evaluation ``DLADMMNet`` of test_syn_l1l1_scalar.py:75-317 (KM, S, safeguarded forward), unmodified.
+
+    The class reads script-level globals (test_syn_l1l1_scalar.py:39-55: alpha, delta, mu_k_method, mu_k_param,
+    layers, K, args.continued, mu_updater_dict); they are supplied through the exec namespace."""
+    import types
+    path = os.path.join(REFERENCE_ROOT, "test_syn_l1l1_scalar.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    nodes = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DLADMMNet"]
+    K = layers if (not continued and (use_learned or use_safeguard)) else num_iter
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "sqrt": sqrt, "alpha": alpha, "delta": delta,
+          "mu_k_method": mu_k_method, "mu_k_param": mu_k_param, "layers": layers, "K": K,
+          "args": types.SimpleNamespace(continued=continued), "mu_updater_dict": load_mu_updater_dict(),
+          "__name__": "reference_eval_scalar"}
+    exec(compile(ast.Module(body=nodes, type_ignores=[]), path, "exec"), ns)
+    return ns["DLADMMNet"]

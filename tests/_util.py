@@ -6,7 +6,9 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+_ALL_NPZ = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN_NAMES = [n for n in _ALL_NPZ if not n.startswith("sg_")]
+SG_GOLDEN_NAMES = [n for n in _ALL_NPZ if n.startswith("sg_")]      # safeguarded evaluation fixtures
 SMALL_GOLDEN = [n for n in GOLDEN_NAMES if "shape" not in n]
 
 
@@ -51,3 +53,37 @@ def syn(m, d, B, seed, p=0.1, sigma=1.0):
     Z = (torch.rand(d, B, generator=gen) < p).float() * torch.randn(d, B, generator=gen) * sigma
     E = (torch.rand(m, B, generator=gen) < p).float() * torch.randn(m, B, generator=gen) * sigma
     return A, A.mm(Z) + E
+
+
+class SgGolden(object):
+    """A fixture written by oracle/make_golden_safeguard.py (reference test_syn_l1l1_scalar.py outputs)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        t = lambda k: torch.from_numpy(z[k].copy())
+        self.A, self.X = t("A"), t("X")
+        self.m, self.d = self.A.shape
+        self.B = self.X.shape[1]
+        self.lip, self.layers, self.alpha = float(z["lip"]), int(z["layers"]), float(z["alpha"])
+        self.use_learned, self.use_safeguard = bool(z["use_learned"]), bool(z["use_safeguard"])
+        self.continued, self.num_iter = bool(z["continued"]), int(z["num_iter"])
+        self.delta, self.method, self.param = float(z["delta"]), str(z["method"]), float(z["param"])
+        self.Z, self.E, self.L, self.T = t("Z"), t("E"), t("L"), t("T")
+        self.sg_count = z["sg_count"].tolist()
+        self.keys = [str(k) for k in z["keys"]]
+        self.sd = {k: t("sd/" + k) for k in self.keys}
+        self.Z0, self.E0, self.L0 = torch.zeros(self.d, self.B), torch.zeros(self.m, self.B), torch.zeros(self.m, self.B)
+        if "s_norm" in z.files:
+            s, thr = t("s_norm"), t("thr")
+            margin = ((s - thr).abs() / thr.abs().clamp_min(1e-9)).min(dim=0).values
+        else:
+            margin = torch.full((self.B,), float("inf"))
+        self.margin = margin        # per column: smallest relative distance of ||S|| from the threshold over the layers
+
+    def robust_columns(self, tol):
+        return self.margin > tol
+
+    def kwargs(self):
+        return dict(continued=self.continued, num_iter=self.num_iter, delta=self.delta, mu_k_method=self.method,
+                    mu_k_param=self.param, alpha=self.alpha)

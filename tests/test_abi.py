@@ -42,7 +42,8 @@ def _struct_fields(name):
 
 @pytest.mark.parametrize("cname,cls", [("dladmm_bparam", _lib.BParam), ("dladmm_layer", _lib.Layer),
                                        ("dladmm_problem", _lib.Problem), ("dladmm_cotangents", _lib.Cotangents),
-                                       ("dladmm_caps", _lib.Caps), ("dladmm_gen_desc", _lib.GenDesc)])
+                                       ("dladmm_caps", _lib.Caps), ("dladmm_gen_desc", _lib.GenDesc),
+                                       ("dladmm_sg_pair", _lib.SgPair)])
 def test_ctypes_structs_mirror_header(cname, cls):
     assert _struct_fields(cname) == [f[0] for f in cls._fields_]
 
