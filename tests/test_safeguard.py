@@ -90,10 +90,7 @@ def _model(g, precision):
     dev = torch.device("cuda:0")
     model = dl.DLADMMNetScalar(m=g.m, n=g.B, d=g.d, batch_size=g.B, A=g.A, Z0=g.Z0, E0=g.E0, L0=g.L0, layers=g.layers,
                                precision=precision, device=dev)
-    sd = dict(g.sd)
-    for k in range(g.layers):       # the evaluation script's class has no ss1: ss1 = 1 is the same map
-        sd.setdefault("ss1.%d" % k, torch.ones(1, 1))
-    model.load_state_dict(sd)
+    model.load_state_dict(g.sd)       # same keys as the evaluation script's class
     return model, dev
 
 
