@@ -18,17 +18,17 @@ struct RedOut { float* part; int nentries; int ngroups; int prow; };
 template <bool PS>
 __device__ __forceinline__ void red_contrib(const BP& q, const RedOut& ro, int slot, float& acc, int row, i64 col, i64 group,
                                             bool ok, float val, int lane) {
+  if (PS) {                                         // every parameter is a (1,1) scalar: register accumulation only
+    acc += ok ? val : 0.f;                          // (entries of parameters without a gradient are never read back)
+    return;
+  }
   if (q.g == nullptr) return;                       // warp-uniform
   if (q.period) {                                   // per-slot parameter (main_lena.py:35-36): direct accumulation
     if (ok) atomicAdd(q.g + (i64)row * q.rs + col % q.period, val);
     return;
   }
-  if (PS) {
-    acc += ok ? val : 0.f;
-  } else {
-    const float s = warp_sum(ok ? val : 0.f);
-    if (lane == 0) ro.part[((i64)slot * ro.ngroups + group) * ro.prow + row] = s;
-  }
+  const float s = warp_sum(ok ? val : 0.f);
+  if (lane == 0) ro.part[((i64)slot * ro.ngroups + group) * ro.prow + row] = s;
 }
 
 template <bool PS, int NRED>
@@ -242,7 +242,8 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
   constexpr uint32_t LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
   constexpr uint32_t SBO = 8 * KC * 4;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment as an offset from the __shared__ symbol: keeps the address space visible to the compiler (LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = (uint64_t*)(smem + STAGES * Plan::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;

@@ -276,7 +276,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int NCH = ROWS_PER_WARP / CHK;          // chunks per (tile, half)
   constexpr int SUB_BYTES = CHK * TILE_B * 4;       // one staged array of one chunk
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment as an offset from the __shared__ symbol: keeps the address space visible to the compiler (LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem + STAGES * Plan::STAGE_BYTES;
   uint64_t* bars = (uint64_t*)(ring + RING_BYTES);
   uint64_t* full = bars;                   // [STAGES]
