@@ -75,12 +75,13 @@ struct UEpiBG1 {
       pre.mk[i] = ok ? (unsigned)__ldg(maskZ + (i64)(row0 + i) * B + b) : 0u;
     }
   }
+  template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64 group) const {
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
-      if (row >= n_feat) continue;                  // warp-uniform
+      if (!FULL && row >= n_feat) continue;         // warp-uniform
       const bool ok = valid;
       const i64 off = (i64)row * B + b;
       float dz = v[i];
@@ -148,12 +149,21 @@ struct UEpiBG2 {
   __device__ __forceinline__ float in(const State& st, const float* slot, int a, int i, int col) const {
     return st.o[a] >= 0 ? slot[st.o[a] + i * TILE_B + col] : 0.f;
   }
+  template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64 group) const {
+    // the common case (all rows of the chunk exist, a layer below) gets a copy of the row loop without warp-uniform
+    // branches so that the rows of the chunk are scheduled together
+    if (FULL && has_prev) rows<true>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+    else rows<false>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void rows(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
+                                       const float (&v)[CHUNK], int n_feat, i64 group) const {
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
-      if (row >= n_feat) continue;                  // warp-uniform
+      if (!FAST && row >= n_feat) continue;         // warp-uniform
       const bool ok = valid;
       const i64 off = (i64)row * B + b;
       const float vb1 = st.b1.at(row, b);
@@ -164,7 +174,7 @@ struct UEpiBG2 {
       red_contrib<PS>(ss1, ro, SL_SS1, st.red[5], row, b, group, ok, -var * v[i], st.lane);
       float dL = in(st, slot, 2, i, col) + dV;
       float dT = vb1 * dV;
-      if (!has_prev) continue;                      // warp-uniform
+      if (!FAST && !has_prev) continue;             // warp-uniform
       // ---- layer k-1: (dL, dT, dE) -> dR, carried dE, carried dL (m1_quad in epilogues.cuh) ----
       dL += in(st, slot, 7, i, col);
       float dE = in(st, slot, 3, i, col) + in(st, slot, 8, i, col);

@@ -58,13 +58,14 @@ struct UEpiT0 {
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
-      if (row >= n_feat) continue;
+      if (!FULL && row >= n_feat) continue;
       const i64 off = (i64)row * B + b;
       const float e0 = slot[i * TILE_B + col], x = slot[SUBF(CHUNK) + i * TILE_B + col], l0 = slot[2 * SUBF(CHUNK) + i * TILE_B + col];
       const float t = fsub(fadd(v[i], e0), x);
@@ -88,13 +89,14 @@ struct UEpiZ {
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
-      if (row >= n_feat) continue;
+      if (!FULL && row >= n_feat) continue;
       const i64 off = (i64)row * B + b;
       const float wv = ss1.p ? fmul(st.s1, v[i]) : v[i];
       unsigned bits;
@@ -124,13 +126,14 @@ struct UEpiELT {
   }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
-      if (row >= n_feat) continue;
+      if (!FULL && row >= n_feat) continue;
       const i64 off = (i64)row * B + b;
       const float x = slot[i * TILE_B + col], lp = slot[SUBF(CHUNK) + i * TILE_B + col], acc = v[i];
       float e;

@@ -263,6 +263,16 @@ constexpr int MAX_RING_DEPTH = 36;
 //   prefetch(pre, row0, b, valid, n_feat)          register loads of small side inputs (prox masks), one chunk ahead
 //   apply(state, slot, col, pre, row0, b, valid, acc[CHUNK], n_feat, group)
 // where `slot` points at the staged inputs of this chunk: present arrays back to back, each [CHUNK][128] floats.
+// position in the epilogue-input staging ring: slot index and mbarrier phase, advanced without integer division
+struct RingPos {
+  int s; uint32_t ph;
+  __device__ __forceinline__ void init(int n, int depth) { s = 0; ph = 0; advance(n, depth); }
+  __device__ __forceinline__ void advance(int by, int depth) {
+    s += by;
+    while (s >= depth) { s -= depth; ph ^= 1u; }
+  }
+};
+
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_big,
@@ -394,17 +404,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == EIN_WARP) {
     // ===== TMA producer (epilogue inputs): chunk n = ((tile_iter * NCH + c) * 2 + half) -> ring slot n % depth =====
     if (nin > 0) {
-      i64 n = 0;
+      RingPos rp; rp.init(0, depth);
       for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nt = (int)(tile % gs.n_ntiles);
         const i64 bt = tile / gs.n_ntiles;
         const int b0 = (int)(bt * TILE_B);
         const int j0 = nt * TILE_N;
         for (int c = 0; c < NCH; ++c) {
-          for (int h = 0; h < 2; ++h, ++n) {
-            const int s = (int)(n % depth);
-            const uint32_t ph = (uint32_t)((n / depth) & 1);
-            mbar_wait(&eempty[s], ph ^ 1);
+          for (int h = 0; h < 2; ++h, rp.advance(1, depth)) {
+            const int s = rp.s;
+            mbar_wait(&eempty[s], rp.ph ^ 1);
             const int row0 = j0 + h * ROWS_PER_WARP + c * CHK;
             if (elect_one()) {
               if (row0 >= gs.n_feat) {
@@ -454,7 +463,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
-    i64 n = half;                                      // this half's chunk counter in the staging ring
+    RingPos rp; rp.init(half, depth);                  // this half's chunks are every other slot of the staging ring
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int nt = (int)(tile % gs.n_ntiles);
       const i64 bt = tile / gs.n_ntiles;
@@ -468,17 +477,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t0 = tmem_base + acc * TILE_N + half * ROWS_PER_WARP + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c, n += 2) {
+      for (int c = 0; c < NCH; ++c, rp.advance(2, depth)) {
         const int row0 = jw + c * CHK;
         typename Epi::Pre pre_next;
         epi.prefetch(pre_next, row0 + CHK, b, valid && c + 1 < NCH, gs.n_feat);
-        const int s = (int)(n % depth);
-        if (nin > 0) mbar_wait(&efull[s], (uint32_t)((n / depth) & 1));
+        const int s = rp.s;
+        if (nin > 0) mbar_wait(&efull[s], rp.ph);
         if (row0 < gs.n_feat) {                          // warp-uniform
           float v[CHK];
           tmem_ld(t0 + c * CHK, v);
-          epi.apply(state, reinterpret_cast<const float*>(ring + s * slot_bytes), col, pre, row0, b, valid, v, gs.n_feat,
-                    bt * (TILE_B / 32) + q);
+          const float* slot = reinterpret_cast<const float*>(ring + s * slot_bytes);
+          if (row0 + CHK <= gs.n_feat)                   // every row of the chunk exists: branch-free rows, interleaved by the compiler
+            epi.template apply<true>(state, slot, col, pre, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);
+          else
+            epi.template apply<false>(state, slot, col, pre, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);
         }
         if (nin > 0) {
           __syncwarp();
