@@ -303,22 +303,28 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
       int s = 0; uint32_t ph = 0;
       for (int kc = 0; kc < k_chunks; ++kc) {
         mbar_wait(&full[s], ph);
-        if (NPASS == 3) mbar_wait(&ready[s], ph);
         tc_fence_after();
+        const uint32_t a_lo = a_lo0 + s * (Plan::STAGE_BYTES >> 4), b_lo = b_lo0 + s * (Plan::STAGE_BYTES >> 4);
+        // raw * raw (big * big) needs no split: issued while the splitters work on the stage
         if (elect_one()) {
-          const uint32_t a_lo = a_lo0 + s * (Plan::STAGE_BYTES >> 4), b_lo = b_lo0 + s * (Plan::STAGE_BYTES >> 4);
 #pragma unroll
-          for (int ks = 0; ks < KC / UMMA_K; ++ks) {
-            const uint64_t da = desc_at(hi, a_lo + ks * 2), db = desc_at(hi, b_lo + ks * 2);
-            const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
-            if (NPASS == 3) {
+          for (int ks = 0; ks < KC / UMMA_K; ++ks)
+            umma_tf32(tmem_base, desc_at(hi, a_lo + ks * 2), desc_at(hi, b_lo + ks * 2), idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+        }
+        __syncwarp();
+        if (NPASS == 3) {
+          mbar_wait(&ready[s], ph);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          if (NPASS == 3) {
+#pragma unroll
+            for (int ks = 0; ks < KC / UMMA_K; ++ks) {
+              const uint64_t da = desc_at(hi, a_lo + ks * 2), db = desc_at(hi, b_lo + ks * 2);
               const uint64_t das = desc_at(hi, a_lo + (Plan::RAW_BYTES >> 4) + ks * 2);
               const uint64_t dbs = desc_at(hi, b_lo + (Plan::RAW_BYTES >> 4) + ks * 2);
-              umma_tf32(tmem_base, das, db, idesc, first);
+              umma_tf32(tmem_base, das, db, idesc, 1u);
               umma_tf32(tmem_base, da, dbs, idesc, 1u);
-              umma_tf32(tmem_base, da, db, idesc, 1u);
-            } else {
-              umma_tf32(tmem_base, da, db, idesc, first);
             }
           }
           umma_commit(&empty[s]);

@@ -28,6 +28,7 @@ struct EpiStore {
   __device__ void begin(State&) const {}
   __device__ void end(State&, int, int) const {}
   __device__ void prefetch(Pre&, int, i64, bool, int) const {}
+  template <bool FULL>
   __device__ void apply(State&, const float*, int, const Pre&, int row0, i64 b, bool valid, const float (&v)[CH], int n_feat, i64) const {
     if (!valid) return;
 #pragma unroll
