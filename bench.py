@@ -240,25 +240,23 @@ def run_ours(args):
 
     # ---- end to end: pinned host observations -> H2D -> forward -> objective -> D2H -------------------
     X_host = X.cpu().pin_memory()
-    x_dev = torch.empty_like(X)
     obj_host = torch.empty(K_LAYERS, dtype=torch.float32).pin_memory()
 
-    def step_e2e():
-        x_dev.copy_(X_host, non_blocking=True)
-        with torch.no_grad():
-            Z, E, L, T = model(x_dev)
-            obj = dl.l1l1_objective(Z, E, T, 0.001)
-        obj_host.copy_(obj, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return obj_host
+    def run_e2e(nsteps):
+        # dl.HostFeed uploads batch i+1 on a copy stream while batch i computes; every step still copies its own
+        # 65.5 MB of observations from pinned host memory and reads its per-layer objective back to the host
+        feed = dl.HostFeed((X_host for _ in range(nsteps)), dev)
+        for x_dev in feed:
+            obj, _outs = model.forward_objective(x_dev, 0.001)      # all K iterates returned + fused objective
+            obj_host.copy_(obj, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return feed.bytes_copied
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    run_e2e(max(2, args.warmup // 2))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    h2d_bytes = run_e2e(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -360,9 +358,11 @@ def run_ours(args):
                        "parallelism": "columns sharded, %d rank(s), no data-path collective" % world},
             "algorithmic_tflops": value * F_FWD / 1e12,
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(X_host.numel() * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes // args.steps),
                     "d2h_bytes_per_step": int(K_LAYERS * 4), "ms_per_step": ms_e2e / args.steps,
-                    "api": "DLADMMNet.forward(x) + l1l1_objective, x copied from pinned host memory each step"},
+                    "api": "for x in dl.HostFeed(pinned host batches): DLADMMNet.forward_objective(x, alpha) -> all K iterates "
+                           "+ per-layer objective read back to the host every step; the upload of batch i+1 overlaps the "
+                           "forward of batch i (double buffer), each batch is copied H2D once inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -13,11 +13,12 @@ from .gen_syn import gen_syn_data, SynData
 from .objective import l1l1_objective
 from .mu_updater import mu_updater_dict
 from .sharding import column_shard, allreduce_gradients, ShardedTrainer
+from .host_feed import HostFeed
 
 __all__ = ["DLADMMNet", "DLADMMNetScalar", "DLADMMNetFull", "DLADMMNetTied", "DLADMMNetLasso", "DLADMMNetLena",
            "DLADMMNetLtheta", "VARIANT_CLASSES", "UnrolledLADMM", "LayerSpec", "run_forward", "gen_syn_data",
            "SynData", "l1l1_objective", "column_shard", "allreduce_gradients", "ShardedTrainer",
-           "default_precision", "library_path", "query_device", "mu_updater_dict"]
+           "default_precision", "library_path", "query_device", "mu_updater_dict", "HostFeed"]
 
 
 def library_path():

@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdladmm.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
@@ -31,7 +31,8 @@ class Problem(C.Structure):
                 ("layers", C.POINTER(Layer)),
                 ("Z", C.c_void_p), ("E", C.c_void_p), ("L", C.c_void_p), ("T", C.c_void_p),
                 ("maskZ", C.c_void_p), ("maskE", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("T_init", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("T_init", C.c_void_p),
+                ("Vsave", C.c_void_p), ("objective", C.c_void_p), ("objective_alpha", C.c_float), ("reserved2", C.c_int32)]
 
 
 class Cotangents(C.Structure):

@@ -413,6 +413,8 @@ __global__ void __launch_bounds__(256) objective_kernel(const float* __restrict_
 
 using namespace dladmm;
 
+static int run_objective(const dladmm_problem* p, float alpha, float* out, cudaStream_t st);
+
 extern "C" {
 
 const char* dladmm_last_error(void) { return g_err; }
@@ -473,7 +475,10 @@ size_t dladmm_workspace_bytes(const dladmm_problem* p, int for_backward) {
 int dladmm_forward(const dladmm_problem* p, void* stream) {
   int rc = validate(p, 0);
   if (rc) return rc;
-  if (p->B == 0) return DLADMM_OK;
+  if (p->B == 0) {
+    if (p->objective) DL_CUDA(cudaMemsetAsync(p->objective, 0, sizeof(float) * p->K, (cudaStream_t)stream));
+    return DLADMM_OK;
+  }
   if (p->workspace_bytes < dladmm_workspace_bytes(p, 0)) {
     set_error("workspace too small: need %zu bytes, got %zu", dladmm_workspace_bytes(p, 0), p->workspace_bytes);
     return DLADMM_ERR_WORKSPACE;
@@ -484,12 +489,18 @@ int dladmm_forward(const dladmm_problem* p, void* stream) {
   // tensor-core precisions need a 16-byte pitch for TMA (B % 4 == 0); other batch sizes run the FFMA kernels,
   // which are fp32 throughout (never less accurate than the precision asked for)
   if (umma_eligible(p)) return umma_forward(p, (char*)p->workspace + w.bytes, st);
+  if (p->objective && p->last_only) {
+    set_error("objective with last_only needs a tensor-core precision and B %% 4 == 0 (the FFMA path reads the iterates back)");
+    return DLADMM_ERR_INVALID;
+  }
   if ((rc = prepare_weights(p, w, false, st))) return rc;
   switch (p->family) {
-    case DLADMM_FAMILY_A: return forward_simt<DLADMM_FAMILY_A>(p, w, st);
-    case DLADMM_FAMILY_B: return forward_simt<DLADMM_FAMILY_B>(p, w, st);
-    default: return forward_simt<DLADMM_FAMILY_C>(p, w, st);
+    case DLADMM_FAMILY_A: rc = forward_simt<DLADMM_FAMILY_A>(p, w, st); break;
+    case DLADMM_FAMILY_B: rc = forward_simt<DLADMM_FAMILY_B>(p, w, st); break;
+    default: rc = forward_simt<DLADMM_FAMILY_C>(p, w, st); break;
   }
+  if (rc == DLADMM_OK && p->objective) rc = run_objective(p, p->objective_alpha, p->objective, st);   // Vsave is unused on this path
+  return rc;
 }
 
 int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* stream) {
@@ -524,7 +535,12 @@ int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* str
   DL_REQUIRE(p->Z && p->E && p->T && p->K > 0, "Z, E, T must be non-NULL");
   int rc;
   if ((rc = check_device())) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+  return run_objective(p, alpha, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+static int run_objective(const dladmm_problem* p, float alpha, float* out, cudaStream_t st) {
   DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * p->K, st));
   if (p->B == 0) return DLADMM_OK;
   i64 zs = (i64)p->d * p->B, ms = (i64)p->m * p->B;
@@ -533,5 +549,3 @@ int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* str
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }
-
-}  // extern "C"

@@ -80,14 +80,19 @@ template <bool PSCALAR>
 struct UEpiZ {
   static constexpr int CHUNK = 16;
   static constexpr int NIN = 1;                    // Z_{k-1}
-  struct State { PV<PSCALAR> th1; float s1; };
+  struct State { PV<PSCALAR> th1; float s1; float obj; };
   typedef NoPre Pre;
   const float* __restrict__ Zp; float* __restrict__ Zk; uint8_t* __restrict__ maskZ;
   BP th1; BP ss1; i64 B; uint32_t in_mask;
+  float* obj_part;                                 // optional: per-warp partial sums of ||Z_k||_1 (fused objective)
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; }
   const uint8_t* host_mask() const { return nullptr; }
-  __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; }
-  __device__ __forceinline__ void end(State&, int, int) const {}
+  __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; st.obj = 0.f; }
+  __device__ __forceinline__ void end(State& st, int entry, int lane) const {
+    if (!obj_part) return;
+    const float s = warp_sum(st.obj);
+    if (lane == 0) obj_part[entry] = s;
+  }
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
   template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
@@ -103,6 +108,7 @@ struct UEpiZ {
       const float z = soft_act(fsub(slot[i * TILE_B + col], wv), st.th1.at(row, b), bits);
       Zk[off] = z;
       if (maskZ) maskZ[off] = (uint8_t)bits;
+      if (obj_part) st.obj += fabsf(z);
     }
   }
 };
@@ -112,8 +118,9 @@ template <int FAM, bool PSCALAR>
 struct UEpiELT {
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 3;                    // X, L_{k-1}, E_{k-1} (family B only)
-  struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; };
+  struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; float obj; };
   typedef NoPre Pre;
+  float* obj_part;                                 // optional: per-warp partial sums of ||E_k - T_{k+1}||_1 = ||X - A Z_k||_1
   const float* __restrict__ X; const float* __restrict__ Ep; const float* __restrict__ Lp;
   float* __restrict__ Ek; float* __restrict__ Lk; float* __restrict__ Tn; uint8_t* __restrict__ maskE;
   BP b2, ss2, ss2_2, th2, bL;
@@ -123,8 +130,13 @@ struct UEpiELT {
   const uint8_t* host_mask() const { return nullptr; }
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
+    st.obj = 0.f;
   }
-  __device__ __forceinline__ void end(State&, int, int) const {}
+  __device__ __forceinline__ void end(State& st, int entry, int lane) const {
+    if (!obj_part) return;
+    const float s = warp_sum(st.obj);
+    if (lane == 0) obj_part[entry] = s;
+  }
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
   template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
@@ -154,6 +166,7 @@ struct UEpiELT {
       const float t = fsub(fadd(acc, e), x);
       const float l = fadd(lp, fmul(st.bL.at(row, b), t));
       Ek[off] = e; Tn[off] = t; Lk[off] = l;
+      if (obj_part) st.obj += fabsf(fsub(e, t));
       if (FAM != DLADMM_FAMILY_C && maskE) maskE[off] = (uint8_t)bits;
       if (has_next) V[off] = fadd(l, fmul(st.b1n.at(row, b), t));
     }

@@ -16,9 +16,11 @@ struct UWorkspace {
   float *Ab, *As;      // A  (m256 x dp) zero padded, tf32 big/small: features of the A Z product on the N side, K = d
   float *Wb, *Ws;      // nW x (d256 x mp): features of the W V product on the N side, K = m
   float *V;            // (m x B) operand V_k = L_{k-1} + beta1_k T_k of the next W V product
+  float *objp;         // fused objective: [K][2][OBJ_ENTRIES] per-warp partial sums (Z part, E - T part)
   size_t bytes;
   int m256, d256, mp, dp, nW;
 };
+constexpr int OBJ_ENTRIES = 256 * umma::EPI_WARPS;   // upper bound of (grid x epilogue warps)
 
 static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   UWorkspace w;
@@ -39,6 +41,7 @@ static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   w.Wb = take((size_t)w.nW * w.d256 * w.mp);
   w.Ws = take((size_t)w.nW * w.d256 * w.mp);
   w.V = take((size_t)p->m * p->B);
+  w.objp = take(p->objective ? (size_t)p->K * 2 * OBJ_ENTRIES : 0);
   w.bytes = off;
   return w;
 }
@@ -187,6 +190,25 @@ static __global__ void __launch_bounds__(256) make_v_kernel(const float* __restr
   store4(V, off, v, nv, vec);
 }
 
+// out[k] = alpha * sum(partZ[k][0..nz)) + sum(partE[k][0..ne)) : second stage of the fused objective, one block per layer
+static __global__ void __launch_bounds__(256) objective_reduce_kernel(const float* __restrict__ part, int nz, int ne, float alpha,
+                                                                      float* __restrict__ out) {
+  const float* pz = part + (size_t)blockIdx.x * 2 * OBJ_ENTRIES;
+  const float* pe = pz + OBJ_ENTRIES;
+  float sz = 0.f, se = 0.f;
+  for (int i = threadIdx.x; i < nz; i += 256) sz += pz[i];
+  for (int i = threadIdx.x; i < ne; i += 256) se += pe[i];
+  float s = warp_sum(alpha * sz + se);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += sm[i];
+    out[blockIdx.x] = v;
+  }
+}
+
 static int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -264,15 +286,20 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   const i64 B = p->B;
   int rc;
   if ((rc = uprepare_weights<NPASS>(p, w, st))) return rc;
+  // V_k: one reused scratch slab, or every layer's kept for the backward (dladmm_problem.Vsave)
+  auto Vslab = [&](int k) { return p->Vsave ? p->Vsave + s.ms * k : w.V; };
+  const i64 nbt = (B + umma::TILE_B - 1) / umma::TILE_B;
+  const int grid_z = (int)std::min<i64>(nbt * ((d + umma::TILE_N - 1) / umma::TILE_N), device_sm_count());
+  const int grid_e = (int)std::min<i64>(nbt * ((m + umma::TILE_N - 1) / umma::TILE_N), device_sm_count());
   // T_0 = A Z0 + E0 - X (+ V_0), or T_0 given by the caller
   if (p->T_init) {
     DL_CUDA(cudaMemcpyAsync(s.Tslab(0), p->T_init, sizeof(float) * (size_t)m * B, cudaMemcpyDeviceToDevice, st));
     const i64 quads = (B + 3) / 4;
     { LaunchScope ls(DLADMM_KIND_PREP, st);
-      make_v_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(p->L0, p->T_init, make_bp(p->layers[0].beta1), m, B, w.V); }
+      make_v_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(p->L0, p->T_init, make_bp(p->layers[0].beta1), m, B, Vslab(0)); }
     DL_CUDA(cudaGetLastError());
   } else {
-    umma::UEpiT0<PS> epi{p->E0, p->X, p->L0, s.Tslab(0), make_bp(p->layers[0].beta1), w.V, B};
+    umma::UEpiT0<PS> epi{p->E0, p->X, p->L0, s.Tslab(0), make_bp(p->layers[0].beta1), Vslab(0), B};
     if ((rc = launch_umma<umma::UEpiT0<PS>, NPASS>(DLADMM_KIND_GEMM_T0, p->Z0, d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st))) return rc;
   }
   for (int k = 0; k < p->K; ++k) {
@@ -280,7 +307,8 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
     const size_t wi = (size_t)weight_index(p, k);
     {
       umma::UEpiZ<PS> epi{s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
-      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, w.V, m, w.Wb + wi * w.d256 * w.mp, w.Ws + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st)))
+      epi.obj_part = p->objective ? w.objp + (size_t)k * 2 * OBJ_ENTRIES : nullptr;
+      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, Vslab(k), m, w.Wb + wi * w.d256 * w.mp, w.Ws + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st)))
         return rc;
     }
     {
@@ -291,10 +319,17 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
       epi.bL = make_bp(betaL(p, l));
       epi.has_next = k + 1 < p->K;
       epi.b1n = make_bp(p->layers[k + 1 < p->K ? k + 1 : k].beta1);
-      epi.V = w.V; epi.B = B;
+      epi.V = Vslab(k + 1 < p->K ? k + 1 : k); epi.B = B;
+      epi.obj_part = p->objective ? w.objp + ((size_t)k * 2 + 1) * OBJ_ENTRIES : nullptr;
       if ((rc = launch_umma<umma::UEpiELT<FAM, PS>, NPASS>(DLADMM_KIND_GEMM_ELT, s.Zout(k), d, w.Ab, w.As, w.m256, w.dp, m, B, epi, st)))
         return rc;
     }
+  }
+  if (p->objective) {
+    { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+      objective_reduce_kernel<<<p->K, 256, 0, st>>>(w.objp, grid_z * umma::EPI_WARPS, grid_e * umma::EPI_WARPS, p->objective_alpha,
+                                                   p->objective); }
+    DL_CUDA(cudaGetLastError());
   }
   return DLADMM_OK;
 }
@@ -388,11 +423,14 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
         return rc;
     }
     if (l.gW) {
-      const i64 quads = (B + 3) / 4;
-      { LaunchScope ls(DLADMM_KIND_PREP, st);
-        make_v_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(s.Lin(k), s.Tslab(k), make_bp(l.beta1), m, B, w.V); }
-      DL_CUDA(cudaGetLastError());
-      if ((rc = launch_nt<NPASS>(sw.cZ, d, w.V, m, B, l.ss1.ptr, l.gW, m, st))) return rc;
+      const float* Vk = p->Vsave ? p->Vsave + s.ms * k : w.V;    // kept by the forward, or recomputed here
+      if (!p->Vsave) {
+        const i64 quads = (B + 3) / 4;
+        { LaunchScope ls(DLADMM_KIND_PREP, st);
+          make_v_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(s.Lin(k), s.Tslab(k), make_bp(l.beta1), m, B, w.V); }
+        DL_CUDA(cudaGetLastError());
+      }
+      if ((rc = launch_nt<NPASS>(sw.cZ, d, Vk, m, B, l.ss1.ptr, l.gW, m, st))) return rc;
     }
     {
       umma::UEpiBG2<FAM, PS> epi;

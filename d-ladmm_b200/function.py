@@ -69,7 +69,8 @@ def _build_layers(spec, params, grads):
     return arr
 
 
-def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, for_backward, T_init=None):
+def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, for_backward, T_init=None, Vsave=None,
+             objective=None, objective_alpha=0.0):
     lib = _lib.load()
     p = _lib.Problem()
     p.abi_version = _lib.ABI_VERSION
@@ -84,6 +85,9 @@ def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only
     p.maskZ = maskZ.data_ptr() if maskZ is not None else None
     p.maskE = maskE.data_ptr() if maskE is not None else None
     p.T_init = T_init.data_ptr() if T_init is not None else None
+    p.Vsave = Vsave.data_ptr() if Vsave is not None else None
+    p.objective = objective.data_ptr() if objective is not None else None
+    p.objective_alpha = float(objective_alpha)
     nbytes = lib.dladmm_workspace_bytes(C.byref(p), 1 if for_backward else 0)
     ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=X.device)
     p.workspace = ws.data_ptr()
@@ -107,9 +111,11 @@ def _check_inputs(spec, A, X, Z0, E0, L0, params):
                            (B, tuple(Z0.shape), tuple(E0.shape), tuple(L0.shape)))
 
 
-def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_init=None):
+def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_init=None, objective_alpha=None, extras=None):
     """Launch the K-layer forward.  Returns stacked (Z, E, L, T, maskZ, maskE).  `T_init` (m,B): T_0 supplied by the
-    caller instead of A Z0 + E0 - X (single-layer steps from an arbitrary state)."""
+    caller instead of A Z0 + E0 - X (single-layer steps from an arbitrary state).  `objective_alpha`: also compute the
+    per-layer L1-L1 objective inside the product epilogues; `extras` (a dict) receives "objective" (K floats) and, in
+    training mode (`want_masks`), "Vsave" (the kept W V operands the backward reuses)."""
     lib = _lib.load()
     _check_inputs(spec, A, X, Z0, E0, L0, params)
     X = X.contiguous()
@@ -132,11 +138,18 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
         T_init = T_init.contiguous()
         if tuple(T_init.shape) != (m, B):
             raise RuntimeError("T_init must be (m, B)")
+    # the tensor-core path keeps every layer's W V operand for the backward (the FFMA path recomputes it in its loader)
+    keep_v = want_masks and extras is not None and spec.precision != _lib.PRECISIONS["fp32"] and B % 4 == 0
+    Vsave = torch.empty((K, m, B), dtype=torch.float32, device=dev) if keep_v else None
+    obj = torch.empty(K, dtype=torch.float32, device=dev) if objective_alpha is not None else None
     layers = _build_layers(spec, params, None)
     with torch.cuda.device(dev):
-        p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, False, T_init)
+        p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, False, T_init, Vsave, obj,
+                         objective_alpha or 0.0)
         _lib.check(lib.dladmm_forward(C.byref(p), torch.cuda.current_stream(dev).cuda_stream))
         ws.record_stream(torch.cuda.current_stream(dev))
+    if extras is not None:
+        extras["Vsave"], extras["objective"] = Vsave, obj
     return Z, E, L, T, maskZ, maskE
 
 
@@ -146,11 +159,12 @@ class UnrolledLADMM(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, A, X, Z0, E0, L0, *params):
-        Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True)
+        extras = {}
+        Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True, extras=extras)
         ctx.spec = spec
         ctx.nparams = len(params)
         ctx.has_maskE = maskE is not None
-        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ] + ([maskE] if maskE is not None else []) + list(params)
+        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ, extras["Vsave"]] + ([maskE] if maskE is not None else []) + list(params)
         ctx.save_for_backward(*saved)
         ctx.set_materialize_grads(False)
         return Z, E, L, T
@@ -160,12 +174,12 @@ class UnrolledLADMM(torch.autograd.Function):
         lib = _lib.load()
         spec = ctx.spec
         saved = ctx.saved_tensors
-        A, X, Z0, E0, L0, Z, E, L, T, maskZ = saved[:10]
-        off = 10
+        A, X, Z0, E0, L0, Z, E, L, T, maskZ, Vsave = saved[:11]
+        off = 11
         maskE = None
         if ctx.has_maskE:
-            maskE = saved[10]
-            off = 11
+            maskE = saved[11]
+            off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[6:]
         grads = [torch.zeros_like(t) if needs[i] else None for i, t in enumerate(params)]
@@ -180,7 +194,7 @@ class UnrolledLADMM(torch.autograd.Function):
         layers = _build_layers(spec, params, grads)
         dev = X.device
         with torch.cuda.device(dev):
-            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True)
+            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True, Vsave=Vsave)
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
         return (None, None, None, None, None, None) + tuple(grads)
@@ -197,15 +211,16 @@ class UnrolledLADMML1L1(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, alpha, weights, A, X, Z0, E0, L0, *params):
-        from .objective import l1l1_objective
-        Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True)
+        extras = {}
+        Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True,
+                                               objective_alpha=float(alpha), extras=extras)
         B = X.shape[1]
-        obj = l1l1_objective(Z, E, T, alpha)
+        obj = extras["objective"]
         w = torch.tensor([float(v) for v in weights], dtype=torch.float32, device=X.device)
         loss = (obj * w).sum() / float(max(B, 1))
         ctx.spec, ctx.alpha, ctx.weights, ctx.B = spec, float(alpha), [float(v) for v in weights], B
         ctx.has_maskE = maskE is not None
-        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ] + ([maskE] if maskE is not None else []) + list(params)
+        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ, extras["Vsave"]] + ([maskE] if maskE is not None else []) + list(params)
         ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(Z, E, L, T)
         return loss, Z, E, L, T
@@ -215,12 +230,12 @@ class UnrolledLADMML1L1(torch.autograd.Function):
         lib = _lib.load()
         spec = ctx.spec
         saved = ctx.saved_tensors
-        A, X, Z0, E0, L0, Z, E, L, T, maskZ = saved[:10]
-        off = 10
+        A, X, Z0, E0, L0, Z, E, L, T, maskZ, Vsave = saved[:11]
+        off = 11
         maskE = None
         if ctx.has_maskE:
-            maskE = saved[10]
-            off = 11
+            maskE = saved[11]
+            off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[8:]
         grads = [torch.zeros_like(t) if needs[i] else None for i, t in enumerate(params)]
@@ -234,7 +249,7 @@ class UnrolledLADMML1L1(torch.autograd.Function):
         layers = _build_layers(spec, params, grads)
         dev = X.device
         with torch.cuda.device(dev):
-            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True)
+            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True, Vsave=Vsave)
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
             scale.record_stream(torch.cuda.current_stream(dev))

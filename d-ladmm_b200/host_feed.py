@@ -1,0 +1,75 @@
+"""Host -> device feed of observation batches for inference over data that lives in host memory.
+
+The reference's drivers slice a host-side numpy array per mini-batch and upload it synchronously before each
+forward (`torch.from_numpy(...).cuda()`, main_syn_l1l1_scalar.py:264-268, 319-323).  Batches of problem instances are
+independent, so the upload of batch i+1 can run on a copy stream while the K-layer forward of batch i computes:
+`HostFeed` is that double buffer.  Every batch is still copied host -> device once, from pinned memory; only the
+waiting is hidden.
+"""
+import torch
+
+
+class HostFeed(object):
+    """Iterate over `batches` (an iterable of (m, B) float32 host tensors, pinned for asynchronous copies) and yield
+    each one as a device tensor.  The copy of the next batch is enqueued on a side stream before the current one is
+    handed out.  A yielded tensor is valid until the next `next()` call on the feed (its buffer is then recycled)."""
+
+    def __init__(self, batches, device, depth=2):
+        if depth < 2:
+            raise ValueError("depth must be >= 2 (one buffer in use, one in flight)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HostFeed needs a CUDA device: d-ladmm_b200 has no CPU path")
+        self._it = iter(batches)
+        self._depth = depth
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._bufs = [None] * depth
+        self._ready = [None] * depth          # event: copy into buffer j finished
+        self._released = [None] * depth       # event: consumer's work on buffer j was enqueued before this point
+        self._queue = []                      # buffer indices holding uploaded batches, oldest first
+        self._next_buf = 0
+        self._current = None
+        self.bytes_copied = 0
+
+    def _enqueue_one(self):
+        try:
+            host = next(self._it)
+        except StopIteration:
+            return False
+        if host.dtype != torch.float32 or host.dim() != 2:
+            raise RuntimeError("HostFeed batches must be (m, B) float32 tensors")
+        j = self._next_buf
+        self._next_buf = (j + 1) % self._depth
+        buf = self._bufs[j]
+        if buf is None or buf.shape != host.shape:
+            buf = self._bufs[j] = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            if self._released[j] is not None:
+                self._copy_stream.wait_event(self._released[j])     # do not overwrite a buffer a forward still reads
+            buf.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._ready[j] = ev
+        self._queue.append(j)
+        self.bytes_copied += host.numel() * 4
+        return True
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self._current is not None:         # everything the consumer enqueued on the last batch precedes this event
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._released[self._current] = ev
+            self._current = None
+        while len(self._queue) < self._depth - 1 and self._enqueue_one():
+            pass
+        if not self._queue:
+            raise StopIteration
+        j = self._queue.pop(0)
+        self._enqueue_one()                   # start the next upload before handing this batch out
+        cur.wait_event(self._ready[j])
+        self._current = j
+        return self._bufs[j]

@@ -206,6 +206,26 @@ class DLADMMNet(nn.Module):
         return Zl, El, Ll
 
 
+    def forward_objective(self, x, alpha, last_only=False):
+        """Inference: forward(x) and the per-layer L1-L1 objective of the reference's evaluation loop
+        (main_syn_l1l1_scalar.py:333-334), obj[k] = sum_b ( alpha*||Z_k[:,b]||_1 + ||x[:,b] - A Z_k[:,b]||_1 ), accumulated
+        inside the product epilogues (no second pass over the iterates, no A@Z_k products).  Returns (obj (K,), outputs)
+        with `outputs` what forward(x, last_only) returns."""
+        if not x.is_cuda:
+            raise RuntimeError("DLADMMNet.forward_objective needs a CUDA tensor: d-ladmm_b200 has no CPU path")
+        spec, params = self._spec_and_params()
+        K = self.layers
+        extras = {}
+        with torch.no_grad():
+            Z, E, L, T, _, _ = run_forward(spec, self.A, x, self.Z0, self.E0, self.L0, [p.detach() for p in params],
+                                           want_masks=False, last_only=last_only, objective_alpha=float(alpha), extras=extras)
+        if last_only:
+            Zl, El, Ll, Tl = [Z[(K - 1) % 2]], [E[(K - 1) % 2]], [L[(K - 1) % 2]], [T[K % 2]]
+            outs = (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)
+        else:
+            outs = self._as_lists(Z, E, L, T)
+        return extras["objective"], outs
+
     def _as_lists(self, Z, E, L, T):
         Zl, El, Ll, Tl = list(Z.unbind(0)), list(E.unbind(0)), list(L.unbind(0)), list(T.unbind(0))
         return (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLADMM_ABI_VERSION 3
+#define DLADMM_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define DLADMM_API __attribute__((visibility("default")))
@@ -114,6 +114,18 @@ typedef struct dladmm_problem {
   const float* T_init;    /* optional (m,B): T_0 supplied by the caller instead of A Z0 + E0 - X (it is copied to T[0]).
                              Used to advance ONE layer from an arbitrary state (Z0,E0,L0,T_init), e.g. the classical KM
                              step and the safeguard operator of test_syn_l1l1_scalar.py:131-176 */
+  /* ABI v4 */
+  float* Vsave;           /* optional (K,m,B), training: the forward keeps every V_k = L_{k-1} + beta1_k T_k (the operand of
+                             the W V product, main_syn_l1l1_scalar.py:93,111) here instead of one reused scratch slab, and a
+                             backward given the same buffer reads it instead of recomputing V_k for the dW product.
+                             Contents are defined only between a forward and the backward of the same problem. */
+  float* objective;       /* optional out, K floats on the device, overwritten by the forward:
+                             objective[k] = sum_b ( objective_alpha*||Z_k[:,b]||_1 + ||X[:,b] - A Z_k[:,b]||_1 )
+                             (main_syn_l1l1_scalar.py:289-299, 333-334), accumulated inside the product epilogues from
+                             Z_k and E_k - T_{k+1} -- the iterates are not read again.  Works with last_only = 1 too
+                             (tensor-core precisions). */
+  float objective_alpha;
+  int32_t reserved2;
 } dladmm_problem;
 
 /* Upstream cotangents for backward; each may be NULL (= zero).  Shapes as the forward outputs. */

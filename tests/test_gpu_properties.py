@@ -151,6 +151,27 @@ def test_fused_objective_matches_script_side_loop():
     assert rel_l2(got, exp) < 1e-4
 
 
+@pytest.mark.parametrize("variant,B,precision", [("scalar", 4096, "tf32x3"), ("full", 1000, "tf32x3"), ("lasso", 516, "tf32"),
+                                               ("ltheta", 2048, "tf32x3"), ("tied", 1001, "tf32x3"), ("scalar", 300, "fp32")])
+def test_epilogue_fused_objective_matches_script_side_loop(variant, B, precision):
+    """forward_objective (dladmm_problem.objective: accumulated inside the product epilogues) against the script-side
+    loop of main_syn_l1l1_scalar.py:333-334, at tile-multiple and ragged batch sizes (B % 4 != 0 runs the FFMA kernels
+    followed by the reduction pass), and the same numbers with last_only=True where no iterate is kept."""
+    K, alpha = 6, 0.01
+    model, data = _model(variant, 250, 500, B, K, precision=precision)
+    obj, outs = model.forward_objective(data.X, alpha)
+    Z = outs[0]
+    exp = torch.stack([alpha * Z[k].abs().sum() + (data.X - data.A @ Z[k]).abs().sum() for k in range(K)])
+    # single-pass tf32 carries the product's 2^-11 operand rounding into E_k - T_{k+1}; the other precisions are fp32-level
+    assert rel_l2(obj, exp) < (2e-3 if precision == "tf32" else 1e-4)
+    plain = model(data.X)
+    assert torch.equal(plain[0][K - 1], Z[K - 1])                 # same iterates as the plain forward
+    if precision != "fp32" and B % 4 == 0:
+        obj2, last = model.forward_objective(data.X, alpha, last_only=True)
+        assert rel_l2(obj2, obj) < 1e-6
+        assert torch.equal(last[0][0], Z[K - 1])
+
+
 def test_objective_improves_with_depth_under_km_parameters():
     m, d, B, K, alpha = 250, 500, 2048, 40, 0.01
     data = dl.gen_syn_data(B, m=m, d=d, seed=3)
