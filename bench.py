@@ -294,11 +294,43 @@ def run_ours(args):
         train = {"columns_per_gpu": Bt, "ms_per_step": ms_train / nst,
                  "kernel_ms_per_step": {k: v[0] for k, v in tprof.items() if v[1] > 0}}
 
+    # ---- optional: the large-scale shape (BASELINE configs[4] "C5": A 1000x2000, K=40), tensor-bound regime ---------
+    c5 = None
+    if args.c5_columns > 0:
+        if args.train_columns > 0:
+            del tm, Xt
+        torch.cuda.empty_cache()
+        m5, d5, K5, B5 = 1000, 2000, 40, args.c5_columns
+        data5 = dl.gen_syn_data(B5, m=m5, d=d5, p=0.1, sigma=1.0, seed=1126, device=dev, col_offset=rank * B5)
+        z5 = lambda r: torch.zeros(r, B5, device=dev)
+        torch.manual_seed(1126)
+        model5 = dl.VARIANT_CLASSES[VARIANT](m5, 10000, d5, B5, data5.A, torch.rand(d5, B5, device=dev) / d5, z5(m5), z5(m5), K5,
+                                             precision=precision, device=dev)
+        c5 = {"columns_per_gpu": B5}
+        for label, last_only in (("all_iterates", False), ("last_only", True)):
+            def step5():
+                with torch.no_grad():
+                    return model5(data5.X, last_only=last_only)
+            for _ in range(2):
+                step5()
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n5 = 3
+            t0.record()
+            for _ in range(n5):
+                step5()
+            t1.record()
+            barrier()
+            c5[label] = t0.elapsed_time(t1) / n5
+        del model5, data5
+        torch.cuda.empty_cache()
+
     # ---- max over ranks -------------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, ms_e2e, train["ms_per_step"] if train else 0.0], device=dev, dtype=torch.float64)
+    stats = torch.tensor([ms_total, ms_e2e, train["ms_per_step"] if train else 0.0,
+                          c5["all_iterates"] if c5 else 0.0, c5["last_only"] if c5 else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_train_step = [float(v) for v in stats.tolist()]
+    ms_total, ms_e2e, ms_train_step, ms_c5_all, ms_c5_last = [float(v) for v in stats.tolist()]
 
     if rank == 0:
         peaks = _peaks()
@@ -371,6 +403,20 @@ def run_ours(args):
                              "unit": "samples/s", "columns_per_gpu": train["columns_per_gpu"], "ms_per_step": ms_train_step,
                              "library_kernel_ms_per_step": train["kernel_ms_per_step"],
                              "what": "DLADMMNet.l1l1_loss(x).backward(): forward + fused L1-L1 objective + backward + parameter gradients%s, scalar K=15" % (" + NCCL allreduce" if world > 1 else "")}
+        if c5:
+            f5 = 2.0 * 1000 * 2000 * (2 * 40 + 1)                  # algorithmic flops per instance (324 MFLOP)
+            B5 = c5["columns_per_gpu"]
+            tp = peaks["tf32_tflops"] / mma_passes
+            line["c5"] = {
+                "workload": "large-scale shape of BASELINE configs[4]: scalar D-LADMM forward, m=1000 d=2000 K=40, %d instances per GPU" % B5,
+                "unit": UNIT, "tensor_peak_tflops": tp,
+                "all_iterates": {"ms_per_step": ms_c5_all, "value": world * B5 / (ms_c5_all * 1e-3),
+                                 "algorithmic_tflops_per_gpu": B5 * f5 / (ms_c5_all * 1e-3) / 1e12,
+                                 "frac_of_tensor_peak": B5 * f5 / (ms_c5_all * 1e-3) / 1e12 / tp},
+                "last_only": {"ms_per_step": ms_c5_last, "value": world * B5 / (ms_c5_last * 1e-3),
+                              "algorithmic_tflops_per_gpu": B5 * f5 / (ms_c5_last * 1e-3) / 1e12,
+                              "frac_of_tensor_peak": B5 * f5 / (ms_c5_last * 1e-3) / 1e12 / tp},
+            }
         if world == 1 and not args.no_cpu_baseline:
             times, threads = cpu_forward_rate(8192, 3)
             cpu_val = 8192 * 2 / sum(times[1:])
@@ -391,6 +437,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32x3", "tf32"])
     ap.add_argument("--columns", type=int, default=B_PER_GPU, help="problem instances per GPU")
     ap.add_argument("--train-columns", type=int, default=65536, help="columns per GPU for the training leg (0 = skip)")
+    ap.add_argument("--c5-columns", type=int, default=32768,
+                    help="columns per GPU for the m=1000 d=2000 K=40 leg (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

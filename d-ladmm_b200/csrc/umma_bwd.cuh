@@ -117,7 +117,8 @@ struct UEpiBG2 {
   float lw; const float* __restrict__ lscale;       // fused L1-L1 loss cotangents on E_{k-1} / T_k
   uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const {
-    p[0] = Lp; p[1] = Tk; p[2] = cLin;
+    p[0] = ss1.p ? Lp : nullptr;                     // L_{k-1} only feeds V_k for d(ss1) (tied variant)
+    p[1] = Tk; p[2] = cLin;
     p[3] = has_prev ? cEin : nullptr; p[4] = has_prev ? Ek : nullptr; p[5] = has_prev ? Lpp : nullptr;
     p[6] = (has_prev && FAM == DLADMM_FAMILY_B) ? Ep : nullptr;
     p[7] = has_prev ? gL : nullptr; p[8] = has_prev ? gE : nullptr; p[9] = has_prev ? gT : nullptr;

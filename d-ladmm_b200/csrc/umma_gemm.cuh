@@ -24,6 +24,7 @@
 // two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace dladmm {
@@ -233,7 +234,24 @@ struct GemmShape {
   int k_chunks;      // ceil(Kdim / KC)
   i64 B;             // batch columns
   i64 n_btiles;      // ceil(B / TILE_B)
+  // Tile list: tiles [0, n_full) are (128 columns x 256 rows), numbered batch-tile major; tiles [n_full, n_tiles) are the
+  // remaining batch tiles cut into (128 x 128) halves.  The host cuts the last, partly filled round of the persistent
+  // grid this way when that shortens the longest CTA (512 tiles on 148 SMs: 4 rounds -> 3 rounds + a round of halves).
+  i64 n_full, n_tiles;
 };
+
+struct TileInfo { i64 bt; int j0; int nrows; };
+__device__ __forceinline__ TileInfo decode_tile(const GemmShape& gs, i64 tile) {
+  TileInfo t;
+  if (tile < gs.n_full) {
+    t.bt = tile / gs.n_ntiles; t.j0 = (int)(tile % gs.n_ntiles) * TILE_N; t.nrows = TILE_N;
+  } else {
+    const i64 h = tile - gs.n_full;
+    const int per = 2 * gs.n_ntiles;
+    t.bt = gs.n_full / gs.n_ntiles + h / per; t.j0 = (int)(h % per) * (TILE_N / 2); t.nrows = TILE_N / 2;
+  }
+  return t;
+}
 
 // Epilogue inputs (the (rows x B) arrays the fused epilogue reads elementwise) are staged through a shared-memory
 // ring by TMA: a dedicated producer thread streams (CHUNK rows x 128 columns) boxes of every input array, several
@@ -282,8 +300,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
   constexpr uint32_t B_SBO = 8 * KC * 4;            // 8 rows of KC floats
   constexpr int CHK = Epi::CHUNK;
-  constexpr int ROWS_PER_WARP = TILE_N / (EPI_WARPS / 4);
-  constexpr int NCH = ROWS_PER_WARP / CHK;          // chunks per (tile, half)
   constexpr int SUB_BYTES = CHK * TILE_B * 4;       // one staged array of one chunk
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment as an offset from the __shared__ symbol: keeps the address space visible to the compiler (LDS/STS, not generic)
@@ -300,7 +316,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4 + 2 * MAX_RING_DEPTH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const i64 ntiles = gs.n_btiles * gs.n_ntiles;
+  const i64 ntiles = gs.n_tiles;
   // staging ring geometry (uniform over the CTA)
   const int nin = __popc(epi.in_mask & ~EIN_MASK_BIT);
   const bool mk_staged = (epi.in_mask & EIN_MASK_BIT) != 0;
@@ -329,10 +345,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== TMA producer (MMA operands): the whole warp walks the schedule, one elected lane issues =====
     int s = 0; uint32_t ph = 0; int trp = 0; (void)trp;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int nt = (int)(tile % gs.n_ntiles);
-      const i64 bt = tile / gs.n_ntiles;
-      const int b0 = (int)(bt * TILE_B);             // batch column (TMA coordinates are 32-bit)
-      const int j0 = nt * TILE_N;
+      const TileInfo ti = decode_tile(gs, tile);
+      const int b0 = (int)(ti.bt * TILE_B);          // batch column (TMA coordinates are 32-bit)
+      const int j0 = ti.j0;                          // (a half tile still loads the 256-row weight box; its MMAs read 128 rows)
       for (int kc = 0; kc < gs.k_chunks; ++kc) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
@@ -355,7 +370,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, one elected lane issues; descriptors are precomputed, only `lo` moves =====
-    constexpr uint32_t idesc = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0);
+    constexpr uint32_t idesc_full = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0);
+    constexpr uint32_t idesc_half = make_idesc(TILE_B, TILE_N / 2, 1, 0);
     // A (MN-major, 128B swizzle / 32B atoms): rows of 32 batch columns (128 B); one k-step = 8 rows = 2 atoms (SBO = 512 B
     // apart); batch groups of 32 are KC*128 B apart (LBO).  B (K-major): rows of KC floats; 8-row groups B_SBO apart;
     // a k-step advances 32 B inside the swizzled row.
@@ -367,6 +383,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int s = 0; uint32_t ph = 0; int trm = 0; (void)trm;
     int acc = 0; uint32_t aph = 0;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t idesc = decode_tile(gs, tile).nrows == TILE_N ? idesc_full : idesc_half;
       mbar_wait(&tempty[acc], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * TILE_N;
@@ -421,15 +438,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (nin > 0) {
       RingPos rp; rp.init(0, depth);
       for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nt = (int)(tile % gs.n_ntiles);
-        const i64 bt = tile / gs.n_ntiles;
-        const int b0 = (int)(bt * TILE_B);
-        const int j0 = nt * TILE_N;
-        for (int c = 0; c < NCH; ++c) {
+        const TileInfo ti = decode_tile(gs, tile);
+        const int b0 = (int)(ti.bt * TILE_B);
+        const int j0 = ti.j0;
+        const int rpw = ti.nrows / (EPI_WARPS / 4);   // feature rows per (tile, half)
+        const int nch = rpw / CHK;
+        for (int c = 0; c < nch; ++c) {
           for (int h = 0; h < 2; ++h, rp.advance(1, depth)) {
             const int s = rp.s;
             mbar_wait(&eempty[s], rp.ph ^ 1);
-            const int row0 = j0 + h * ROWS_PER_WARP + c * CHK;
+            const int row0 = j0 + h * rpw + c * CHK;
             if (elect_one()) {
               if (row0 >= gs.n_feat) {
                 mbar_arrive(&efull[s]);                  // nothing to stage, keep the phases in step
@@ -480,22 +498,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     epi.begin(state);
     RingPos rp; rp.init(half, depth);                  // this half's chunks are every other slot of the staging ring
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int nt = (int)(tile % gs.n_ntiles);
-      const i64 bt = tile / gs.n_ntiles;
+      const TileInfo ti = decode_tile(gs, tile);
+      const i64 bt = ti.bt;
       const i64 b = bt * TILE_B + col;
-      const int j0 = nt * TILE_N;
       const bool valid = b < gs.B;
-      const int jw = j0 + half * ROWS_PER_WARP;        // first feature row of this warp
+      const int rpw = ti.nrows / (EPI_WARPS / 4);      // feature rows per (tile, half): 128, or 64 in a half tile
+      const int nch = rpw / CHK;
+      const int jw = ti.j0 + half * rpw;               // first feature row of this warp
       typename Epi::Pre pre;
       epi.prefetch(pre, jw, b, valid, gs.n_feat);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + acc * TILE_N + half * ROWS_PER_WARP + ((uint32_t)(q * 32) << 16);
+      const uint32_t t0 = tmem_base + acc * TILE_N + half * rpw + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c, rp.advance(2, depth)) {
+      for (int c = 0; c < nch; ++c, rp.advance(2, depth)) {
         const int row0 = jw + c * CHK;
         typename Epi::Pre pre_next;
-        epi.prefetch(pre_next, row0 + CHK, b, valid && c + 1 < NCH, gs.n_feat);
+        epi.prefetch(pre_next, row0 + CHK, b, valid && c + 1 < nch, gs.n_feat);
         const int s = rp.s;
         if (nin > 0) mbar_wait(&efull[s], rp.ph);
         if (row0 < gs.n_feat) {                          // warp-uniform
@@ -528,6 +547,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ---- host side: tile list ---------------------------------------------------------------------------------------
+// Persistent CTAs take tiles round-robin, so the kernel lasts as long as its busiest CTA: ceil(tiles / grid) tile times.
+// When the last round is at most half full, its batch tiles are cut into 128-row halves (a half costs ~0.55 of a tile:
+// half the MMAs, the same operand loads) so that twice as many CTAs share it.
+inline void plan_tiles(GemmShape& gs, int grid) {
+  const i64 ntiles = gs.n_btiles * gs.n_ntiles;
+  gs.n_full = ntiles; gs.n_tiles = ntiles;
+  if (grid <= 0 || ntiles <= grid) return;
+  const i64 rounds = ntiles / grid;
+  i64 n_full = rounds * grid;
+  n_full -= n_full % gs.n_ntiles;                 // whole batch tiles only
+  const i64 rest = ntiles - n_full;               // tiles that would form the last round
+  if (rest == 0) return;
+  auto cost = [&](i64 nf, i64 nh) {               // longest CTA, in tile times
+    double worst = 0;
+    for (int c = 0; c < grid; ++c) {
+      const i64 f = nf > c ? (nf - c + grid - 1) / grid : 0;
+      const i64 t = nf + nh > c ? (nf + nh - c + grid - 1) / grid : 0;
+      worst = std::max(worst, (double)f + 0.55 * (double)(t - f));
+    }
+    return worst;
+  };
+  if (cost(n_full, 2 * rest) + 0.1 < cost(ntiles, 0)) { gs.n_full = n_full; gs.n_tiles = n_full + 2 * rest; }
+}
 
 // ---- host side: tensor maps ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

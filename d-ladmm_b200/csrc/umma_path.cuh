@@ -271,6 +271,7 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
   }
   const i64 ntiles = gs.n_btiles * gs.n_ntiles;
   const int grid = grid_override > 0 ? grid_override : (int)std::min<i64>(ntiles, device_sm_count());
+  umma::plan_tiles(gs, grid);
   {
     LaunchScope ls(kind, st);
     kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tA, tBb, tBs, em, gs, epi);

@@ -200,6 +200,21 @@ class UnrolledLADMM(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(grads)
 
 
+_WEIGHT_CACHE = {}
+
+
+def _layer_weight_tensor(weights, device):
+    """Per-layer loss weights on the device, cached: building them per step would be a synchronous pageable H2D copy
+    that makes the host wait for the whole forward before it can enqueue the backward."""
+    key = (tuple(float(v) for v in weights), str(device))
+    t = _WEIGHT_CACHE.get(key)
+    if t is None:
+        if len(_WEIGHT_CACHE) > 64:
+            _WEIGHT_CACHE.clear()
+        t = _WEIGHT_CACHE[key] = torch.tensor(key[0], dtype=torch.float32, device=device)
+    return t
+
+
 class UnrolledLADMML1L1(torch.autograd.Function):
     """forward(spec, alpha, weights, A, X, Z0, E0, L0, *params) -> (loss, Z, E, L, T) with
 
@@ -216,7 +231,7 @@ class UnrolledLADMML1L1(torch.autograd.Function):
                                                objective_alpha=float(alpha), extras=extras)
         B = X.shape[1]
         obj = extras["objective"]
-        w = torch.tensor([float(v) for v in weights], dtype=torch.float32, device=X.device)
+        w = _layer_weight_tensor(weights, X.device)
         loss = (obj * w).sum() / float(max(B, 1))
         ctx.spec, ctx.alpha, ctx.weights, ctx.B = spec, float(alpha), [float(v) for v in weights], B
         ctx.has_maskE = maskE is not None

@@ -232,3 +232,28 @@ def test_config5_shape_multiple_feature_tiles(precision):
         # the L1 objective is non-smooth: sign(E_k - T_{k+1}) and the prox masks flip for entries within rounding of
         # zero, and with only 256 columns a handful of flips moves dW by ~0.5 % in 3xTF32
         assert rel_l2(p.grad.cpu(), gref[n], floor=floor) < (2e-2 if precision == "tf32x3" else 2e-3), n
+
+
+@pytest.mark.parametrize("variant,B", [("scalar", 21504), ("full", 21444), ("lasso", 21504)])
+def test_half_tile_tail_round_matches_ffma_path(variant, B):
+    """168 batch tiles on 148 SMs: the last round of the persistent tcgen05 kernels is cut into 128-row half tiles
+    (umma::plan_tiles).  Forward iterates, loss and every parameter gradient against the FFMA (fp32) kernels, which the
+    parity tests pin to the oracle; `full` exercises the per-row parameter-gradient reductions, 21444 a ragged last tile."""
+    m, d, K = 250, 500, 3
+    w = [0.5, 0.5, 1.0]
+    res = {}
+    for precision in ("fp32", "tf32x3"):
+        model, data = _model(variant, m, d, B, K, seed=5, precision=precision)
+        loss, outs = model.l1l1_loss(data.X, 0.01, w)
+        loss.backward()
+        res[precision] = (loss.item(), [t.clone() for t in outs[0]], [t.clone() for t in outs[1]],
+                          {n: p.grad.clone() for n, p in model.named_parameters()})
+    l0, Z0_, E0_, g0 = res["fp32"]
+    l1, Z1_, E1_, g1 = res["tf32x3"]
+    assert abs(l0 - l1) < 1e-5 * abs(l0)
+    for k in range(K):
+        assert rel_l2(Z1_[k], Z0_[k]) < 2e-5 and rel_l2(E1_[k], E0_[k]) < 2e-5
+    # over 21 K columns a handful of prox masks sit within rounding of their threshold and differ between the two
+    # arithmetics; that moves a gradient by ~1e-3 relative (a half-tile bug would be O(1))
+    for n in g0:
+        assert rel_l2(g1[n], g0[n], floor=1e-5) < 5e-3, n

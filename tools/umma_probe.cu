@@ -83,6 +83,8 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
   i64 ntiles = gs.n_btiles * gs.n_ntiles;
   int grid = (int)(ntiles < nsm ? ntiles : nsm);
+  plan_tiles(gs, grid);
+  printf("tiles: %lld full + %lld halves on %d CTAs\n", (long long)gs.n_full, (long long)(gs.n_tiles - gs.n_full), grid);
   kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, em, gs, epi);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -128,7 +130,7 @@ int main(int argc, char** argv) {
   for (auto& x : W) x = (float)rand() / RAND_MAX - 0.5f;
   for (auto& x : Act) x = (float)rand() / RAND_MAX - 0.5f;
   std::vector<double> ref((size_t)n_feat * B, 0.0);
-  if (B * n_feat <= 4000000) {
+  if (B * n_feat <= 8000000) {
     for (int j = 0; j < n_feat; ++j)
       for (int k = 0; k < Kdim; ++k) {
         double w = W[(size_t)j * Kdim + k];
