@@ -52,7 +52,7 @@ class GenDesc(C.Structure):
                 ("seed", C.c_uint64), ("p", C.c_float), ("mu", C.c_float), ("sigma", C.c_float),
                 ("dense_noise", C.c_int32), ("sigma_e", C.c_float), ("generate_A", C.c_int32),
                 ("A", C.c_void_p), ("Zs", C.c_void_p), ("Es", C.c_void_p), ("X", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("amplitude", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SgPair(C.Structure):

@@ -3,6 +3,8 @@
 //   Z = Bernoulli(p) * N(mu, sigma)   (d x B)                         (:26-33)
 //   E = Bernoulli(p) * N(mu, sigma)   (m x B)   [or dense N(0, sigma_e), gen_syn_unseen_data_lasso.py:41-42]
 //   X = A Z + E                                                       (:46-47)
+// and its out-of-distribution variants: amplitudes cos(g) / 1/(1+exp(g)) (gen_syn_unseen_data_cosine.py,
+// gen_syn_unseen_data_logistic.py); replaced columns of A are a host-side edit of A (gen_syn.py::replace_A_columns).
 // Random numbers come from Philox4x32-10 keyed by (seed) and countered by (stream, row, global column pair),
 // so the data does not depend on how columns are sharded over GPUs.
 #include "common.cuh"
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) normalize_cols_kernel(float* __restrict__
 // rows x B sparse (or dense) Gaussian field; each thread writes 4 consecutive columns of one row
 __global__ void __launch_bounds__(256) gen_field_kernel(float* __restrict__ out, int rows, i64 B, i64 col_offset,
                                                         uint64_t seed, int stream, float p, float mu, float sigma,
-                                                        int dense) {
+                                                        int dense, int amplitude) {
   const i64 quads = (B + 3) / 4;
   i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
   if (idx >= quads * rows) return;
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(256) gen_field_kernel(float* __restrict__ out,
       float nrm = (gc & 1) ? n1 : n0;
       float u = u01((gc & 1) ? c[3] : c[2]);
       float val = mu + sigma * nrm;
+      if (amplitude == 1) val = cosf(val);                       // gen_syn_unseen_data_cosine.py:33-34
+      else if (amplitude == 2) val = 1.0f / (1.0f + expf(val));   // gen_syn_unseen_data_logistic.py:33-34
       v[2 * h + e] = dense ? val : (u <= p ? val : 0.f);
     }
   }
@@ -125,6 +129,7 @@ int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream) {
   DL_REQUIRE(g->m > 0 && g->d > 0 && g->B >= 0, "bad sizes m=%d d=%d", g->m, g->d);
   DL_REQUIRE(g->A && (g->B == 0 || (g->Zs && g->Es && g->X)), "A, Zs, Es, X must be non-NULL");
   DL_REQUIRE(g->p >= 0.f && g->p <= 1.f, "p must be in [0,1]");
+  DL_REQUIRE(g->amplitude >= 0 && g->amplitude <= 2, "unknown amplitude %d", g->amplitude);
   cudaStream_t st = (cudaStream_t)stream;
   const int m = g->m, d = g->d;
   if (g->generate_A) {
@@ -143,15 +148,15 @@ int dladmm_gen_syn(const dladmm_gen_desc* g, void* stream) {
   const i64 quads = (g->B + 3) / 4;
   { LaunchScope ls(DLADMM_KIND_GEN, st);
     gen_field_kernel<<<(unsigned)((quads * d + 255) / 256), 256, 0, st>>>(g->Zs, d, g->B, g->col_offset, g->seed, STREAM_Z,
-                                                                          g->p, g->mu, g->sigma, 0); }
+                                                                          g->p, g->mu, g->sigma, 0, g->amplitude); }
   DL_CUDA(cudaGetLastError());
   LaunchScope lsE(DLADMM_KIND_GEN, st);
   if (g->dense_noise)
     gen_field_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(g->Es, m, g->B, g->col_offset, g->seed, STREAM_E,
-                                                                          1.f, 0.f, g->sigma_e, 1);
+                                                                          1.f, 0.f, g->sigma_e, 1, 0);
   else
     gen_field_kernel<<<(unsigned)((quads * m + 255) / 256), 256, 0, st>>>(g->Es, m, g->B, g->col_offset, g->seed, STREAM_E,
-                                                                          g->p, g->mu, g->sigma, 0);
+                                                                          g->p, g->mu, g->sigma, 0, g->amplitude);
   DL_CUDA(cudaGetLastError());
   // X = A Zs + Es through the same fused product kernel
   float* Ap = (float*)g->workspace;

@@ -169,6 +169,10 @@ typedef struct dladmm_gen_desc {
   float* X;               /* out (m,B) = A Zs + Es */
   void* workspace;        /* scratch, dladmm_gen_workspace_bytes(m, d) bytes */
   size_t workspace_bytes;
+  int32_t amplitude;      /* ABI v4: non-zero amplitudes of Zs and of a sparse Es, g ~ N(mu, sigma):
+                             0: g (gen_syn_data.py:30-33); 1: cos(g) (gen_syn_unseen_data_cosine.py:33-38);
+                             2: 1/(1+exp(g)) (gen_syn_unseen_data_logistic.py:33-38) */
+  int32_t reserved;
 } dladmm_gen_desc;
 
 /* Bytes of scratch the caller must provide in problem->workspace. */

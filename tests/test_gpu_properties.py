@@ -257,3 +257,24 @@ def test_half_tile_tail_round_matches_ffma_path(variant, B):
     # arithmetics; that moves a gradient by ~1e-3 relative (a half-tile bug would be O(1))
     for n in g0:
         assert rel_l2(g1[n], g0[n], floor=1e-5) < 5e-3, n
+
+
+def test_unseen_distribution_generators():
+    """gen_syn_unseen_data_cosine.py / _logistic.py: the non-zero amplitudes are cos(g) / 1/(1+exp(g)) of the SAME
+    Gaussian draws and Bernoulli supports as the plain generator with that seed; _Acols.py: c columns of A replaced."""
+    m, d, B, p, sigma = 250, 500, 4096, 0.1, 1.5
+    base = dl.gen_syn_data(B, m=m, d=d, p=p, sigma=sigma, mu=0.3, seed=11)
+    for name, fn in (("cosine", torch.cos), ("logistic", lambda g: 1.0 / (1.0 + torch.exp(g)))):
+        data = dl.gen_syn_data(B, m=m, d=d, p=p, sigma=sigma, mu=0.3, seed=11, A=base.A, amplitude=name)
+        for F, G in ((data.Z, base.Z), (data.E, base.E)):
+            nz = G != 0
+            assert torch.equal(F != 0, nz) or ((F != 0) ^ nz).float().mean().item() < 1e-5   # cos(g) == 0 has measure zero
+            assert (F[nz] - fn(G[nz])).abs().max().item() < 2e-6
+        assert rel_l2(data.X, data.A @ data.Z + data.E) < 1e-5
+    A2, cols = dl.replace_A_columns(base.A, 37, seed=5)
+    assert len(set(cols.tolist())) == 37
+    same = torch.ones(d, dtype=torch.bool); same[cols] = False
+    assert torch.equal(A2[:, same], base.A[:, same]) and not torch.equal(A2[:, cols], base.A[:, cols])
+    assert (A2.pow(2).sum(dim=0).sqrt() - 1).abs().max().item() < 1e-5
+    with pytest.raises(ValueError):
+        dl.gen_syn_data(8, amplitude="sine")

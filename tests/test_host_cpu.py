@@ -114,3 +114,26 @@ def test_gradient_allreduce_gloo_world_size_2():
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r][0] for r in range(world))
     assert ret[0][1] == 0 and ret[0][2] == ret[1][1]
+
+
+def test_mat_file_round_trip_in_reference_layout(tmp_path):
+    """save_mat writes gen_syn_data.py:49-53's layout (sample-major, keys A/train_*/test_*); load_mat reads it back into
+    the model's (features x B) layout; replace_A_columns follows gen_syn_unseen_data_Acols.py:14-26."""
+    import scipy.io as sio
+    import dladmm_b200 as dl
+    g = torch.Generator().manual_seed(3)
+    m, d = 12, 20
+    A = torch.randn(m, d, generator=g); A = A / A.pow(2).sum(0, keepdim=True).sqrt()
+    mk = lambda B: dl.SynData(A, torch.randn(m, B, generator=g), torch.randn(d, B, generator=g), torch.randn(m, B, generator=g))
+    train, test = mk(30), mk(7)
+    path = str(tmp_path / "syn_data.mat")
+    dl.save_mat(path, train, test)
+    raw = sio.loadmat(path)
+    assert raw["train_x"].shape == (30, m) and raw["test_z"].shape == (7, d) and raw["A"].shape == (m, d)   # sample-major
+    tr2, te2 = dl.load_mat(path)
+    for a, b in ((tr2.X, train.X), (tr2.Z, train.Z), (tr2.E, train.E), (te2.X, test.X), (te2.Z, test.Z), (te2.E, test.E)):
+        assert torch.equal(a, b)
+    A2, cols = dl.replace_A_columns(A, 5, seed=1)
+    keep = torch.ones(d, dtype=torch.bool); keep[cols] = False
+    assert torch.equal(A2[:, keep], A[:, keep]) and cols.numel() == 5
+    assert (A2.pow(2).sum(0).sqrt() - 1).abs().max() < 1e-6
