@@ -12,6 +12,9 @@ PyTorch-eager fallback -- calling ``forward`` without the library or without a C
     lasso     main_syn_lasso_scalar.py:17-118                   Z, E, L, T
     lena      main_lena.py:16-102                               Z, E, L
     ltheta    main_syn_l1l1_ltheta.py:16-108                    Z, E, L
+    newS        main_syn_scalar_newS_layerwise.py:34-116        forward(x, K) -> Z, E, L   (E -> L -> Z ordering)
+    tied_newS   main_syn_scalar_tied_newS_layerwise.py:35-117   forward(x, K) -> Z, E, L   (one fc, ss1 per layer)
+    ptied_newS  main_syn_scalar_ptied_newS_layerwise.py:37-124  forward(x, K) -> Z, E, L   (fc[k // interval])
 """
 import ctypes as C
 import os
@@ -25,9 +28,15 @@ from .function import LayerSpec, UnrolledLADMM, UnrolledLADMML1L1, run_forward
 from .mu_updater import mu_updater_dict
 
 _FAMILY = {"lena": _lib.FAMILY_A, "ltheta": _lib.FAMILY_A, "scalar": _lib.FAMILY_B, "full": _lib.FAMILY_B,
-           "tied": _lib.FAMILY_B, "lasso": _lib.FAMILY_C}
-_RETURNS_T = {"lena": False, "ltheta": False, "scalar": True, "full": False, "tied": True, "lasso": True}
-_NAME = {"scalar": "DLADMMNet_scalar", "tied": "DLADMMNet_scalar_tied"}
+           "tied": _lib.FAMILY_B, "lasso": _lib.FAMILY_C, "newS": _lib.FAMILY_B, "tied_newS": _lib.FAMILY_B,
+           "ptied_newS": _lib.FAMILY_B}
+_RETURNS_T = {"lena": False, "ltheta": False, "scalar": True, "full": False, "tied": True, "lasso": True,
+              "newS": False, "tied_newS": False, "ptied_newS": False}
+_NAME = {"scalar": "DLADMMNet_scalar", "tied": "DLADMMNet_scalar_tied", "newS": "DLADMMNet_scalar_newS_layerwise",
+         "tied_newS": "DLADMMNet_scalar_tied_newS_layerwise"}
+# which fc a layer uses: one per layer, one for all layers, or one per `interval` consecutive layers
+_TIE = {"tied": "all", "tied_newS": "all", "ptied_newS": "interval"}
+_NEWS = ("newS", "tied_newS", "ptied_newS")
 
 # reference parameter name -> slot of dladmm_layer
 _SLOT_OF = {
@@ -63,6 +72,12 @@ def _param_table(variant, m, d, bs):
     if variant == "lasso":       # main_syn_lasso_scalar.py:33-50
         return [("beta1", one(), 1.0), ("beta3", one(), 1.0), ("ss2_1", one(), 0.5), ("ss2_2", one(), 0.5),
                 ("active_para", one(), 0.2)]
+    if variant == "newS":        # main_syn_scalar_newS_layerwise.py:50-68
+        return [("beta1", one(), 1.0), ("beta2", one(), 1.0), ("beta3", one(), 1.0), ("ss2", one(), 1.0),
+                ("active_para", one(), 0.1), ("active_para1", one(), 0.1)]
+    if variant in ("tied_newS", "ptied_newS"):   # main_syn_scalar_tied_newS_layerwise.py:51-68, ptied: :53-74
+        return [("beta1", one(), 1.0), ("beta2", one(), 1.0), ("beta3", one(), 1.0), ("ss1", one(), 1.0),
+                ("ss2", one(), 1.0), ("active_para", one(), 0.01), ("active_para1", one(), 0.01)]
     raise ValueError("unknown variant %r" % (variant,))
 
 
@@ -75,12 +90,21 @@ class DLADMMNet(nn.Module):
     """
     variant = "scalar"
 
-    def __init__(self, m, n, d, batch_size, A, Z0, E0, L0, layers, variant=None, precision=None, device=None):
+    def __init__(self, m, n, d, batch_size, A, Z0, E0, L0, layers, interval=None, variant=None, precision=None, device=None):
         super(DLADMMNet, self).__init__()
         if variant is not None:
             self.variant = variant
         if self.variant not in _FAMILY:
             raise ValueError("unknown variant %r" % (self.variant,))
+        self._tie = _TIE.get(self.variant)
+        if self._tie == "interval":      # main_syn_scalar_ptied_newS_layerwise.py:38,49,63-64
+            if interval is None or int(interval) <= 0:
+                raise ValueError("the ptied variant needs a positive `interval`")
+            self.interval = int(interval)
+            if layers // self.interval * self.interval < layers:
+                raise ValueError("layers (%d) must be covered by layers // interval (%d) weights" % (layers, layers // self.interval))
+        elif interval is not None:
+            raise ValueError("`interval` is only meaningful for the ptied variant")
         self.m, self.n, self.d = m, n, d
         self.batch_size = batch_size
         self.layers = layers
@@ -103,12 +127,14 @@ class DLADMMNet(nn.Module):
         table = _param_table(self.variant, m, d, batch_size)
         for name, _, _ in table:
             setattr(self, name, nn.ParameterList())
-        tied = self.variant == "tied"
-        self.fc = nn.Linear(m, d, bias=False) if tied else nn.ModuleList()
+        self.fc = nn.Linear(m, d, bias=False) if self._tie == "all" else nn.ModuleList()
+        if self._tie == "interval":
+            for _ in range(layers // self.interval):
+                self.fc.append(nn.Linear(m, d, bias=False))
         for k in range(layers):
             for name, shape, val in table:
                 getattr(self, name).append(nn.Parameter(val * torch.ones(shape, dtype=torch.float32)))
-            if not tied:
+            if self._tie is None:
                 self.fc.append(nn.Linear(m, d, bias=False))
         if self.variant == "lena":   # fixed, non-learnable thresholds (main_lena.py:40-41)
             self.active_para = torch.tensor(0.025, dtype=torch.float32, device=self._device)
@@ -123,6 +149,8 @@ class DLADMMNet(nn.Module):
 
     # ---- reference surface ---------------------------------------------------------------------
     def name(self):
+        if self.variant == "ptied_newS":     # main_syn_scalar_ptied_newS_layerwise.py:123
+            return "DLADMMNet_scalar_ptied{}_newS_layerwise".format(self.interval)
         return _NAME.get(self.variant, "DLADMMNet")
 
     def self_active(self, x, thershold):
@@ -154,37 +182,71 @@ class DLADMMNet(nn.Module):
         return out
 
     # ---- call description for the library ---------------------------------------------------------
-    def _spec_and_params(self):
+    def _weight_module(self, k):
+        if self._tie == "all":
+            return self.fc
+        if self._tie == "interval":
+            return self.fc[k // self.interval]
+        return self.fc[k]
+
+    def _spec_and_params(self, nlayers=None, drop_last_estep=False):
+        """Flat parameter list + per-layer slot map for the first `nlayers` layers.  Layers that share an fc (tied / ptied)
+        point at the same list entry, so the library sees one weight pointer and accumulates one gradient.
+        `drop_last_estep`: the E/L-step parameters of the last layer do not reach any output (newS ordering); they are
+        passed detached so that, as in the reference, they get no gradient."""
         fam = _FAMILY[self.variant]
         names = _SLOT_OF[_FAMILY_KEY[fam]]
-        params, slots, weights = [], [], []
+        params, slots, weights, windex = [], [], [], {}
         table = _param_table(self.variant, self.m, self.d, self.batch_size)
-        tied = self.variant == "tied"
-        if tied:
-            params.append(self.fc.weight)
-        for k in range(self.layers):
+        K = self.layers if nlayers is None else int(nlayers)
+        for k in range(K):
             s = {}
             for name, _, _ in table:
+                p = getattr(self, name)[k]
+                if drop_last_estep and k == K - 1 and name in ("beta2", "beta3", "ss2", "active_para1"):
+                    p = p.detach()
                 s[names[name]] = len(params)
-                params.append(getattr(self, name)[k])
+                params.append(p)
             slots.append(s)
-            if tied:
-                weights.append(0)
-            else:
-                weights.append(len(params))
-                params.append(self.fc[k].weight)
+            wm = self._weight_module(k)
+            if id(wm) not in windex:
+                windex[id(wm)] = len(params)
+                params.append(wm.weight)
+            weights.append(windex[id(wm)])
         fixed = {}
         if self.variant == "lena":
             fixed = {"theta1": self.active_para, "theta2": self.active_para1}
-        spec = LayerSpec(fam, self.m, self.d, self.layers, _lib.PRECISIONS[self.precision], slots, weights, fixed)
+        spec = LayerSpec(fam, self.m, self.d, K, _lib.PRECISIONS[self.precision], slots, weights, fixed)
         return spec, params
 
-    def forward(self, x, last_only=False):
+    def _forward_newS(self, x, K):
+        """forward(x, K) of the E -> L -> Z ordering (main_syn_scalar_newS_layerwise.py:82-112): the first min(K, layers)
+        layers of the family-B recursion, returned as Z[k] = Z_{k+1}, E = [E0, E_1, ..], L = [L0, L_1, ..] -- i.e. the
+        E/L lists shifted by one and the last layer's E/L-step not part of the result."""
+        Kp = min(self.layers if K is None else int(K), self.layers)
+        if Kp <= 0:
+            return [], [], []
+        spec, params = self._spec_and_params(Kp, drop_last_estep=True)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            Z, E, L, _ = UnrolledLADMM.apply(spec, self.A, x, self.Z0, self.E0, self.L0, *params)
+        else:
+            Z, E, L, _, _, _ = run_forward(spec, self.A, x, self.Z0, self.E0, self.L0, [p.detach() for p in params],
+                                           want_masks=False)
+        return list(Z.unbind(0)), [self.E0] + list(E.unbind(0))[:Kp - 1], [self.L0] + list(L.unbind(0))[:Kp - 1]
+
+    def forward(self, x, K=None, last_only=False):
         """x: (m, B) float32 CUDA, B equal to the batch of Z0/E0/L0.  Returns lists (Z, E, L[, T]) of the
         per-layer iterates like the reference (a10).  ``last_only=True`` (inference, opt-in) keeps only
-        the final iterate in each list and never materialises the other K-1."""
+        the final iterate in each list and never materialises the other K-1.  ``K`` (newS variants only, as in
+        their reference signature forward(x, K)): run the first min(K, layers) layers."""
         if not x.is_cuda:
             raise RuntimeError("DLADMMNet.forward needs a CUDA tensor: d-ladmm_b200 has no CPU path")
+        if self.variant in _NEWS:
+            if last_only:
+                raise RuntimeError("last_only is not offered for the newS variants")
+            return self._forward_newS(x, K)
+        if K is not None:
+            raise TypeError("forward(x, K) exists only in the newS variants")
         spec, params = self._spec_and_params()
         K = self.layers
         train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
@@ -381,5 +443,18 @@ class DLADMMNetLtheta(DLADMMNet):
     variant = "ltheta"
 
 
+class DLADMMNetNewS(DLADMMNet):
+    variant = "newS"
+
+
+class DLADMMNetTiedNewS(DLADMMNet):
+    variant = "tied_newS"
+
+
+class DLADMMNetPtiedNewS(DLADMMNet):
+    variant = "ptied_newS"
+
+
 VARIANT_CLASSES = {"scalar": DLADMMNetScalar, "full": DLADMMNetFull, "tied": DLADMMNetTied,
-                   "lasso": DLADMMNetLasso, "lena": DLADMMNetLena, "ltheta": DLADMMNetLtheta}
+                   "lasso": DLADMMNetLasso, "lena": DLADMMNetLena, "ltheta": DLADMMNetLtheta,
+                   "newS": DLADMMNetNewS, "tied_newS": DLADMMNetTiedNewS, "ptied_newS": DLADMMNetPtiedNewS}

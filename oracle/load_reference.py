@@ -30,6 +30,10 @@ VARIANT_FILES = {
     "full": "main_syn_l1l1_full.py",              # family B, per-row params
     "tied": "main_syn_l1l1_scalar_tied.py",       # family B, one shared fc + ss1
     "lasso": "main_syn_lasso_scalar.py",          # family C, linear E-step
+    # E -> L -> Z ordering with prefix execution forward(x, K)
+    "newS": "main_syn_scalar_newS_layerwise.py",
+    "tied_newS": "main_syn_scalar_tied_newS_layerwise.py",
+    "ptied_newS": "main_syn_scalar_ptied_newS_layerwise.py",      # constructor takes `interval`
 }
 
 
@@ -64,11 +68,11 @@ def load_class(variant, alpha=0.001, script=None):
     return ns["DLADMMNet"]
 
 
-def build(variant, m, n, d, batch_size, A, Z0, E0, L0, layers, alpha=0.001):
-    """Instantiate the reference model on CPU with its own default initialisation."""
+def build(variant, m, n, d, batch_size, A, Z0, E0, L0, layers, alpha=0.001, **extra):
+    """Instantiate the reference model on CPU with its own default initialisation (`extra`: e.g. interval=...)."""
     cls = load_class(variant, alpha=alpha)
     with cuda_is_identity():
-        model = cls(m=m, n=n, d=d, batch_size=batch_size, A=A, Z0=Z0, E0=E0, L0=L0, layers=layers)
+        model = cls(m=m, n=n, d=d, batch_size=batch_size, A=A, Z0=Z0, E0=E0, L0=L0, layers=layers, **extra)
     return model
 
 

@@ -7,7 +7,8 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _ALL_NPZ = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-GOLDEN_NAMES = [n for n in _ALL_NPZ if not n.startswith("sg_") and n != "lena_psnr"]   # lena_psnr: tests/test_lena_psnr.py
+NEWS_GOLDEN_NAMES = [n for n in _ALL_NPZ if "newS" in n]             # E -> L -> Z ordering fixtures (tests/test_newS.py)
+GOLDEN_NAMES = [n for n in _ALL_NPZ if not n.startswith("sg_") and n != "lena_psnr" and "newS" not in n]   # lena_psnr: tests/test_lena_psnr.py
 SG_GOLDEN_NAMES = [n for n in _ALL_NPZ if n.startswith("sg_")]      # safeguarded evaluation fixtures
 SMALL_GOLDEN = [n for n in GOLDEN_NAMES if "shape" not in n]
 
@@ -53,6 +54,35 @@ def syn(m, d, B, seed, p=0.1, sigma=1.0):
     Z = (torch.rand(d, B, generator=gen) < p).float() * torch.randn(d, B, generator=gen) * sigma
     E = (torch.rand(m, B, generator=gen) < p).float() * torch.randn(m, B, generator=gen) * sigma
     return A, A.mm(Z) + E
+
+
+class NewSGolden(object):
+    """A fixture written by oracle/make_golden_newS.py (reference newS / tied_newS / ptied_newS outputs)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.variant, self.ref_name = str(z["variant"]), str(z["name"])
+        self.layers, self.K_run, self.bs, self.interval = int(z["layers"]), int(z["K_run"]), int(z["bs"]), int(z["interval"])
+        t = lambda k: torch.from_numpy(z[k].copy())
+        self.A, self.X, self.Z0, self.E0, self.L0 = t("A"), t("X"), t("Z0"), t("E0"), t("L0")
+        self.Z, self.E, self.L = t("Z"), t("E"), t("L")
+        self.cz, self.ce, self.cl = t("cz"), t("ce"), t("cl")
+        self.loss = float(z["loss"])
+        self.keys = [str(k) for k in z["keys"]]
+        self.sd = {k: t("sd/" + k) for k in self.keys}
+        self.grads = {k: t("grad/" + k) for k in self.keys}
+        self.nograd = [str(k) for k in z["nograd"] if str(k)]
+        self.m, self.d = self.A.shape
+
+    def build(self, device, precision=None):
+        import dladmm_b200 as dl
+        extra = {"interval": self.interval} if self.interval else {}
+        model = dl.VARIANT_CLASSES[self.variant](m=self.m, n=10000, d=self.d, batch_size=self.bs, A=self.A, Z0=self.Z0,
+                                                 E0=self.E0, L0=self.L0, layers=self.layers, precision=precision,
+                                                 device=device, **extra)
+        model.load_state_dict(self.sd)
+        return model
 
 
 class SgGolden(object):
