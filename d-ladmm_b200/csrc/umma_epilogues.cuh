@@ -47,6 +47,7 @@ struct NoPre {};
 // T_0 = A Z0 + E0 - X, and V_0 = L0 + beta1_0 * T_0 for the first Z-step
 template <bool PSCALAR>
 struct UEpiT0 {
+  static constexpr int WARPS = 8;
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 3;                    // E0, X, L0
   struct State { PV<PSCALAR> b1; };
@@ -78,6 +79,7 @@ struct UEpiT0 {
 // Z_k = act(Z_{k-1} - [ss1*] acc, theta1)
 template <bool PSCALAR>
 struct UEpiZ {
+  static constexpr int WARPS = 8;
   static constexpr int CHUNK = 16;
   static constexpr int NIN = 1;                    // Z_{k-1}
   struct State { PV<PSCALAR> th1; float s1; float obj; };
@@ -116,6 +118,7 @@ struct UEpiZ {
 // E_k, T_{k+1}, L_k from acc = A Z_k; then V_{k+1} = L_k + beta1_{k+1} * T_{k+1} unless this is the last layer
 template <int FAM, bool PSCALAR>
 struct UEpiELT {
+  static constexpr int WARPS = 8;
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 3;                    // X, L_{k-1}, E_{k-1} (family B only)
   struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; float obj; };

@@ -33,12 +33,13 @@ namespace umma {
 constexpr int TILE_B = 128;      // batch columns per tile (UMMA M)
 constexpr int TILE_N = 256;      // feature rows per tile (UMMA N)
 constexpr int UMMA_K = 8;        // tf32
-constexpr int EPI_WARPS = 8;          // two per TMEM lane quadrant, each owning half of the tile's feature rows
+// Epilogue warps: `parts` per TMEM lane quadrant, each owning 1/parts of the tile's feature rows.  Each epilogue functor
+// picks its own count (Epi::WARPS = 8 or 16: the heavier elementwise chains want more warps to hide LDS/LDTM latency, the
+// ones with many staged inputs want fewer parts so that each part keeps several ring slots in flight).
+constexpr int MAX_EPI_WARPS = 16;
+constexpr int roles_threads(int epi_warps) { return 64 + 32 * epi_warps + 32 * 4 + 32; }
 constexpr int SPLIT_WARPS = 4;        // shared-memory tf32 splitters (3-pass mode)
-constexpr int SPLIT_WARP0 = 2 + EPI_WARPS;
-constexpr int EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS;   // producer of the epilogue-input staging ring
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * SPLIT_WARPS + 32;
-constexpr int EPI_WARP0 = 2;
+constexpr int EPI_WARP0 = 2;             // warps [2, 2 + WARPS) = epilogue, then SPLIT_WARPS splitters, then the staging-ring producer
 constexpr int CH = 16;            // feature rows per epilogue step (one tcgen05.ld.32x32b.x16)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -292,11 +293,14 @@ struct RingPos {
 };
 
 template <class Epi, int NPASS, int KC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(roles_threads(Epi::WARPS), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_big,
                  const __grid_constant__ CUtensorMap tmB_small, const __grid_constant__ EMaps emaps, GemmShape gs, Epi epi) {
   using Plan = SmemPlan<NPASS, KC>;
   constexpr int STAGES = Plan::STAGES;
+  constexpr int EPI_WARPS = Epi::WARPS, EPI_PARTS = EPI_WARPS / 4;
+  constexpr int SPLIT_WARP0 = EPI_WARP0 + EPI_WARPS, EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS;
+  static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
   constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
   constexpr uint32_t B_SBO = 8 * KC * 4;            // 8 rows of KC floats
   constexpr int CHK = Epi::CHUNK;
@@ -321,8 +325,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nin = __popc(epi.in_mask & ~EIN_MASK_BIT);
   const bool mk_staged = (epi.in_mask & EIN_MASK_BIT) != 0;
   const int slot_bytes = nin * SUB_BYTES + (mk_staged ? CHK * TILE_B : 0);
-  int depth = nin > 0 ? RING_BYTES / slot_bytes : 1;
+  // The depth is a multiple of EPI_PARTS, so that a ring slot is always consumed by the same part: mbarrier waits only
+  // see the phase PARITY, and a part that shared a slot with another part could reach the slot's wrap w+2 while wrap w+1
+  // (the other part's) was still in flight -- its wait would pass on the stale phase.  (The host refuses depth < EPI_PARTS.)
+  int depth = nin > 0 ? RING_BYTES / slot_bytes : EPI_PARTS;
   if (depth > MAX_RING_DEPTH) depth = MAX_RING_DEPTH;
+  depth -= depth % EPI_PARTS;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB_big);
@@ -434,17 +442,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
   } else if (warp == EIN_WARP) {
-    // ===== TMA producer (epilogue inputs): chunk n = ((tile_iter * NCH + c) * 2 + half) -> ring slot n % depth =====
+    // ===== TMA producer (epilogue inputs): chunk n = ((tile_iter * NCH + c) * EPI_PARTS + part) -> ring slot n % depth =====
     if (nin > 0) {
       RingPos rp; rp.init(0, depth);
       for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileInfo ti = decode_tile(gs, tile);
         const int b0 = (int)(ti.bt * TILE_B);
         const int j0 = ti.j0;
-        const int rpw = ti.nrows / (EPI_WARPS / 4);   // feature rows per (tile, half)
+        const int rpw = ti.nrows / EPI_PARTS;         // feature rows per (tile, part)
         const int nch = rpw / CHK;
         for (int c = 0; c < nch; ++c) {
-          for (int h = 0; h < 2; ++h, rp.advance(1, depth)) {
+          for (int h = 0; h < EPI_PARTS; ++h, rp.advance(1, depth)) {
             const int s = rp.s;
             mbar_wait(&eempty[s], rp.ph ^ 1);
             const int row0 = j0 + h * rpw + c * CHK;
@@ -491,18 +499,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===== epilogue warps =====
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
-    const int half = (warp - EPI_WARP0) >> 2;          // which half of the tile's feature rows
+    const int half = (warp - EPI_WARP0) >> 2;          // which part (1/EPI_PARTS) of the tile's feature rows
     const int col = q * 32 + lane;                     // column inside the tile
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
-    RingPos rp; rp.init(half, depth);                  // this half's chunks are every other slot of the staging ring
+    RingPos rp; rp.init(half, depth);                  // this part's chunks are every EPI_PARTS-th slot of the staging ring
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(gs, tile);
       const i64 bt = ti.bt;
       const i64 b = bt * TILE_B + col;
       const bool valid = b < gs.B;
-      const int rpw = ti.nrows / (EPI_WARPS / 4);      // feature rows per (tile, half): 128, or 64 in a half tile
+      const int rpw = ti.nrows / EPI_PARTS;            // feature rows per (tile, part); half as many in a half tile
       const int nch = rpw / CHK;
       const int jw = ti.j0 + half * rpw;               // first feature row of this warp
       typename Epi::Pre pre;
@@ -511,7 +519,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t0 = tmem_base + acc * TILE_N + half * rpw + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c, rp.advance(2, depth)) {
+      for (int c = 0; c < nch; ++c, rp.advance(EPI_PARTS, depth)) {
         const int row0 = jw + c * CHK;
         typename Epi::Pre pre_next;
         epi.prefetch(pre_next, row0 + CHK, b, valid && c + 1 < nch, gs.n_feat);

@@ -20,7 +20,7 @@ struct UWorkspace {
   size_t bytes;
   int m256, d256, mp, dp, nW;
 };
-constexpr int OBJ_ENTRIES = 256 * umma::EPI_WARPS;   // upper bound of (grid x epilogue warps)
+constexpr int OBJ_ENTRIES = 256 * umma::MAX_EPI_WARPS;   // upper bound of (grid x epilogue warps)
 
 static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   UWorkspace w;
@@ -70,7 +70,7 @@ static UBwdWorkspace ucarve_bwd(const dladmm_problem* p, char* base) {
   w.nW = unique_weights(p);
   w.ngroups = (int)(((p->B + umma::TILE_B - 1) / umma::TILE_B) * (umma::TILE_B / 32));
   w.prow = round_up(std::max(p->m, p->d), 32);
-  w.nentries = 256 * umma::EPI_WARPS;      // upper bound of (grid x epilogue warps)
+  w.nentries = 256 * umma::MAX_EPI_WARPS;      // upper bound of (grid x epilogue warps)
   size_t off = 0;
   auto take = [&](size_t nfloats) {
     float* r = (float*)(base + off);
@@ -257,6 +257,16 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
       epi.in_mask |= umma::EIN_MASK_BIT;
     }
   }
+  {
+    // every epilogue part must own at least one slot of the staging ring (a consumer whose first slot is a wrapped one
+    // would see that slot's barrier as already completed)
+    const int nin = __builtin_popcount(epi.in_mask & ~umma::EIN_MASK_BIT);
+    const int slot_bytes = nin * Epi::CHUNK * umma::TILE_B * 4 + ((epi.in_mask & umma::EIN_MASK_BIT) ? Epi::CHUNK * umma::TILE_B : 0);
+    if (nin > 0 && umma::RING_BYTES / slot_bytes < Epi::WARPS / 4) {
+      set_error("epilogue staging ring too small: %d bytes per slot, %d parts", slot_bytes, Epi::WARPS / 4);
+      return DLADMM_ERR_INVALID;
+    }
+  }
   umma::GemmShape gs;
   gs.n_feat = n_feat;
   gs.n_ntiles = (n_feat + umma::TILE_N - 1) / umma::TILE_N;
@@ -274,7 +284,7 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
   umma::plan_tiles(gs, grid);
   {
     LaunchScope ls(kind, st);
-    kern<<<grid, umma::NUM_THREADS, Plan::TOTAL, st>>>(tA, tBb, tBs, em, gs, epi);
+    kern<<<grid, umma::roles_threads(Epi::WARPS), Plan::TOTAL, st>>>(tA, tBb, tBs, em, gs, epi);
   }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
@@ -328,7 +338,7 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   }
   if (p->objective) {
     { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
-      objective_reduce_kernel<<<p->K, 256, 0, st>>>(w.objp, grid_z * umma::EPI_WARPS, grid_e * umma::EPI_WARPS, p->objective_alpha,
+      objective_reduce_kernel<<<p->K, 256, 0, st>>>(w.objp, grid_z * umma::UEpiZ<PS>::WARPS, grid_e * umma::UEpiELT<FAM, PS>::WARPS, p->objective_alpha,
                                                    p->objective); }
     DL_CUDA(cudaGetLastError());
   }
@@ -358,7 +368,7 @@ static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const 
   }
   {
     LaunchScope ls(DLADMM_KIND_BWD_GEMM_DW, st);
-    kern<<<dim3(mt, split, nt), umma::NUM_THREADS, Plan::TOTAL, st>>>(tP, tQ, ns, s1ptr, -1.f, C);
+    kern<<<dim3(mt, split, nt), umma::roles_threads(umma::NT_EPI_WARPS), Plan::TOTAL, st>>>(tP, tQ, ns, s1ptr, -1.f, C);
   }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
@@ -407,7 +417,10 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
   const i64 tiles_dz = nbt * ((d + umma::TILE_N - 1) / umma::TILE_N), tiles_dv = nbt * ((m + umma::TILE_N - 1) / umma::TILE_N);
   const int grid = (int)std::min<i64>(std::max(tiles_dz, tiles_dv), std::min(device_sm_count(), 256));
   umma::RedOut ro;
-  ro.part = w.part; ro.nentries = grid * umma::EPI_WARPS; ro.ngroups = w.ngroups; ro.prow = w.prow;
+  // per-warp partial entries (all-scalar parameters): the two epilogues use different warp counts, so entries are laid
+  // out for the larger one and the buffer is cleared once -- a kernel rewrites only its own entries every layer
+  ro.part = w.part; ro.nentries = grid * umma::MAX_EPI_WARPS; ro.ngroups = w.ngroups; ro.prow = w.prow;
+  if (PS) DL_CUDA(cudaMemsetAsync(w.part, 0, sizeof(float) * (size_t)SL_COUNT * ro.nentries, st));
   for (int k = K - 1; k >= 0; --k) {
     const dladmm_layer& l = p->layers[k];
     const size_t wi = (size_t)weight_index(p, k);

@@ -20,6 +20,10 @@ using namespace dladmm;
 using namespace dladmm::umma;
 
 struct EpiStore {
+#ifndef PROBE_EPI_WARPS
+#define PROBE_EPI_WARPS 8
+#endif
+  static constexpr int WARPS = PROBE_EPI_WARPS;
   static constexpr int CHUNK = CH;
   static constexpr int NIN = 0;
   struct State {};
@@ -85,7 +89,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   int grid = (int)(ntiles < nsm ? ntiles : nsm);
   plan_tiles(gs, grid);
   printf("tiles: %lld full + %lld halves on %d CTAs\n", (long long)gs.n_full, (long long)(gs.n_tiles - gs.n_full), grid);
-  kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, em, gs, epi);
+  kern<<<grid, roles_threads(EpiStore::WARPS), smem>>>(tAb, tBb, tBs, em, gs, epi);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> C((size_t)n_feat * B);
@@ -110,7 +114,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   if (reps > 0) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) kern<<<grid, NUM_THREADS, smem>>>(tAb, tBb, tBs, em, gs, epi);
+    for (int r = 0; r < reps; ++r) kern<<<grid, roles_threads(EpiStore::WARPS), smem>>>(tAb, tBb, tBs, em, gs, epi);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
   }
