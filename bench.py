@@ -36,9 +36,10 @@ F_FWD = 2.0 * M * D * (2 * K_LAYERS + 1)          # algorithmic flops per instan
 F_GEMM_PER_COL = 2.0 * M * D                      # one (d x m)(m x 1) or (m x d)(d x 1) product
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
-# (profiles/r01_ncu_full_summary_v4.md), keyed by (precision, kernel kind)
-TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 332.102144e6 + 216.018688e6, ("tf32x3", "gemm_z"): 197.864448e6 + 92.462848e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture of the final build
+# (profiles/r01_ncu_full_summary_v6.md; a training-mode launch: it also writes the 1-byte prox masks, 16.4 MB for `gemm_elt`
+# and 32.8 MB for `gemm_z`, which the inference launch timed here does not), keyed by (precision, kernel kind)
+TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 332.134144e6 + 228.335616e6, ("tf32x3", "gemm_z"): 197.939712e6 + 121.106432e6}
 
 
 def _peaks():
