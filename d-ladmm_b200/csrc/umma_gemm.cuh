@@ -104,6 +104,10 @@ __device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* small, i
   for (int i = 0; i < N; ++i)
     dst[tid + i * NTHREADS] = make_float4(tf32_small(v[i].x), tf32_small(v[i].y), tf32_small(v[i].z), tf32_small(v[i].w));
 }
+// Programmatic dependent launch: a kernel launched with programmatic stream serialization may become resident while its
+// predecessor drains; everything that reads or writes global memory sits behind grid_dep_wait().
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -348,6 +352,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The next product kernel of the stream may start its own prologue (barriers, TMEM, tensor-map prefetch) on SMs this
+  // grid has left; this grid's global reads and writes all happen after the wait below (the MMA issuer and the splitters
+  // touch shared memory and TMEM only, downstream of the producers' loads).
+  grid_dep_launch_dependents();
+  if (warp != 1 && !(warp >= SPLIT_WARP0 && warp < EIN_WARP)) grid_dep_wait();
 
   if (warp == 0) {
     // ===== TMA producer (MMA operands): the whole warp walks the schedule, one elected lane issues =====

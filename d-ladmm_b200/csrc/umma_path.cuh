@@ -209,6 +209,13 @@ static __global__ void __launch_bounds__(256) objective_reduce_kernel(const floa
   }
 }
 
+// DLADMM_NO_PDL=1 launches the product kernels fully serialized (measurement / debugging)
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DLADMM_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 static int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -216,6 +223,8 @@ static int device_sm_count() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    const char* cap = getenv("DLADMM_GRID_CAP");     // experiments: persistent grids of at most this many CTAs
+    if (cap && atoi(cap) > 0 && atoi(cap) < n) n = atoi(cap);
   }
   return n;
 }
@@ -284,7 +293,16 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
   umma::plan_tiles(gs, grid);
   {
     LaunchScope ls(kind, st);
-    kern<<<grid, umma::roles_threads(Epi::WARPS), Plan::TOTAL, st>>>(tA, tBb, tBs, em, gs, epi);
+    // programmatic stream serialization: the kernel may be scheduled while the previous product kernel drains (it calls
+    // griddepcontrol.launch_dependents after its prologue); its own loads and stores wait for that grid to complete
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::roles_threads(Epi::WARPS)); cfg.dynamicSmemBytes = Plan::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DL_CUDA(cudaLaunchKernelEx(&cfg, kern, tA, tBb, tBs, em, gs, epi));
   }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;

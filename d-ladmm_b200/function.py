@@ -153,6 +153,24 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
     return Z, E, L, T, maskZ, maskE
 
 
+def _flat_zero_grads(params, needs):
+    """Zero-initialised gradient buffers for the parameters that need one, carved out of ONE flat allocation (one fill
+    instead of one per parameter -- 106 launches at K=15; 16-byte aligned pieces).  autograd copies them into `.grad`."""
+    sizes = [(-(-t.numel() // 4) * 4) if needs[i] else 0 for i, t in enumerate(params)]
+    total = sum(sizes)
+    if total == 0:
+        return [None] * len(params)
+    flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+    grads, off = [], 0
+    for i, t in enumerate(params):
+        if not needs[i]:
+            grads.append(None)
+            continue
+        grads.append(flat[off:off + t.numel()].view(t.shape))
+        off += sizes[i]
+    return grads
+
+
 class UnrolledLADMM(torch.autograd.Function):
     """forward(spec, A, X, Z0, E0, L0, *params) -> (Z, E, L, T) stacks; gradients flow to `params` only
     (A, Z0, E0, L0 are plain tensors in the reference, main_syn_l1l1_scalar.py:40-44)."""
@@ -182,7 +200,7 @@ class UnrolledLADMM(torch.autograd.Function):
             off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[6:]
-        grads = [torch.zeros_like(t) if needs[i] else None for i, t in enumerate(params)]
+        grads = _flat_zero_grads(params, needs)
         cot = _lib.Cotangents()
         keep = []
         for name, g in (("gZ", gZ), ("gE", gE), ("gL", gL), ("gT", gT)):
@@ -253,7 +271,7 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[8:]
-        grads = [torch.zeros_like(t) if needs[i] else None for i, t in enumerate(params)]
+        grads = _flat_zero_grads(params, needs)
         scale = (gloss.detach().to(torch.float32) / float(max(ctx.B, 1))).reshape(1).contiguous()
         cot = _lib.Cotangents()
         cot.loss_kind = 1

@@ -39,11 +39,12 @@ def allreduce_gradients(parameters, group=None, average=False, bucket_bytes=64 <
         calls += 1
         if average:
             flat.div_(world)
-        off = 0
+        views, off = [], 0
         for g in bucket:
             n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
+            views.append(flat[off:off + n].view_as(g))
             off += n
+        torch._foreach_copy_(bucket, views)           # one multi-tensor launch instead of one copy per parameter
     return calls
 
 

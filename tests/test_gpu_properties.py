@@ -278,3 +278,4 @@ def test_unseen_distribution_generators():
     assert (A2.pow(2).sum(dim=0).sqrt() - 1).abs().max().item() < 1e-5
     with pytest.raises(ValueError):
         dl.gen_syn_data(8, amplitude="sine")
+
