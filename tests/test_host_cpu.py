@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import dladmm_b200 as dl
-from _util import GOLDEN_NAMES, Golden
+from _util import GOLDEN_NAMES, Golden, build_model
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
@@ -137,3 +137,24 @@ def test_mat_file_round_trip_in_reference_layout(tmp_path):
     keep = torch.ones(d, dtype=torch.bool); keep[cols] = False
     assert torch.equal(A2[:, keep], A[:, keep]) and cols.numel() == 5
     assert (A2.pow(2).sum(0).sqrt() - 1).abs().max() < 1e-6
+
+
+def test_call_description_cache_tracks_replaced_parameters():
+    """_spec_and_params caches the static call description; replacing a Parameter object (as the constructor itself does
+    for the fc weights) or moving the module must not leave a stale entry behind."""
+    import dladmm_b200 as dl
+    g = Golden("scalar_small")
+    model = build_model(g, "cpu")
+    spec1, params1 = model._spec_and_params()
+    spec2, params2 = model._spec_and_params()
+    assert spec1 is spec2 and all(a is b for a, b in zip(params1, params2))          # cache hit
+    model.fc[1].weight = torch.nn.Parameter(torch.zeros_like(model.fc[1].weight))
+    spec3, params3 = model._spec_and_params()
+    assert any(p is model.fc[1].weight for p in params3) and spec3 is not spec1
+    model.float()                                                                    # _apply drops the cache
+    assert "_spec_cache" not in model.__dict__
+    news = dl.DLADMMNetNewS(g.m, 1, g.d, g.bs, g.A, g.Z0, g.E0, g.L0, 4, device="cpu")
+    _, pa = news._spec_and_params(3, drop_last_estep=True)
+    _, pb = news._spec_and_params(3, drop_last_estep=True)
+    nograd = [p for p in pb if not p.requires_grad]
+    assert len(nograd) == 4 and all(any(q.data_ptr() == p.data_ptr() for q in news.parameters()) for p in nograd)

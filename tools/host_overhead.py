@@ -13,6 +13,17 @@ def run(n):
     torch.cuda.synchronize()
 run(20)
 t0 = time.perf_counter(); run(200); t1 = time.perf_counter()
-print("B=%d: %.3f ms per forward call (wall, GPU mostly idle)" % (B, (t1 - t0) / 200 * 1e3))
+print("B=%d: %.3f ms per forward call (wall incl. final sync)" % (B, (t1 - t0) / 200 * 1e3))
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+with torch.no_grad():
+    for _ in range(50):
+        model(data.X)
+t1 = time.perf_counter()
+torch.cuda.synchronize(); t2 = time.perf_counter()
+print("B=%d: host enqueue %.3f ms per call; GPU drained %.3f ms after the last enqueue" % (B, (t1 - t0) / 50 * 1e3, (t2 - t1) * 1e3))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(50); e1.record(); torch.cuda.synchronize()
+print("B=%d: device time %.3f ms per call" % (B, e0.elapsed_time(e1) / 50))
 pr = cProfile.Profile(); pr.enable(); run(100); pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
