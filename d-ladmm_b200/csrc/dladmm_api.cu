@@ -3,6 +3,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -22,7 +23,7 @@ void set_error(const char* fmt, ...) {
 
 // ---- launch accounting ---------------------------------------------------------------------------
 struct ProfRec { int kind; cudaEvent_t a, b; };
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // the profiling hooks below are single-threaded measurement aids
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
@@ -419,7 +420,7 @@ extern "C" {
 
 const char* dladmm_last_error(void) { return g_err; }
 
-int64_t dladmm_launch_count(void) { return g_launches; }
+int64_t dladmm_launch_count(void) { return g_launches.load(); }
 
 int dladmm_profile_start(void) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

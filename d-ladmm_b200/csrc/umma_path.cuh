@@ -216,11 +216,20 @@ static bool use_pdl() {
   return v == 1;
 }
 
+// the only mutable state of the library besides the measurement hooks: per-device caches of "attribute already set" and
+// of the SM count (one process may drive several devices, one host thread each)
+constexpr int MAX_DEVICES = 64;
+static int current_device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+
 static int device_sm_count() {
-  static int n = 0;
+  static int cache[MAX_DEVICES] = {0};
+  const int dev = current_device_index();
+  int& n = cache[dev];
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
     const char* cap = getenv("DLADMM_GRID_CAP");     // experiments: persistent grids of at most this many CTAs
@@ -247,7 +256,7 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
     tBs = tBb;
   }
   // epilogue inputs staged by TMA: one (CHUNK rows x 128 columns) box per present array
-  static umma::EMaps em;
+  umma::EMaps em;                          // per call, on the stack: the launch copies it into the kernel parameters
   {
     const float* ptrs[umma::MAX_EIN] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     epi.host_inputs(ptrs);
@@ -283,10 +292,11 @@ static int launch_umma(int kind, const float* act, int Kdim, const float* w_big,
   gs.B = B;
   gs.n_btiles = (B + umma::TILE_B - 1) / umma::TILE_B;
   auto kern = umma::umma_gemm_kernel<Epi, NPASS, KC>;
-  static bool attr_set = false;     // per template instantiation
-  if (!attr_set) {
+  static bool attr_set[MAX_DEVICES] = {false};     // per template instantiation and per device
+  const int dev = current_device_index();
+  if (!attr_set[dev]) {
     DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const i64 ntiles = gs.n_btiles * gs.n_ntiles;
   const int grid = grid_override > 0 ? grid_override : (int)std::min<i64>(ntiles, device_sm_count());
@@ -379,10 +389,11 @@ static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const 
   umma::NtShape ns;
   ns.M = M; ns.N = N; ns.B = B; ns.chunk = chunk; ns.ldc = ldc;
   auto kern = umma::umma_nt_kernel<NPASS, KC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MAX_DEVICES] = {false};
+  const int dev = current_device_index();
+  if (!attr_set[dev]) {
     DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   {
     LaunchScope ls(DLADMM_KIND_BWD_GEMM_DW, st);
