@@ -67,3 +67,33 @@ def test_invalid_arguments_are_rejected_with_messages():
 
 def test_library_is_in_tree():
     assert os.path.dirname(dl.library_path()).endswith(os.path.join("d-ladmm_b200", "csrc"))
+
+
+def test_ctypes_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
+    """The header is plain C: compile a probe with gcc and compare sizeof / offsetof of every struct with the ctypes
+    mirrors the Python host uses (field names alone would not catch a type or padding drift)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = [("dladmm_bparam", _lib.BParam), ("dladmm_layer", _lib.Layer), ("dladmm_problem", _lib.Problem),
+               ("dladmm_cotangents", _lib.Cotangents), ("dladmm_caps", _lib.Caps), ("dladmm_gen_desc", _lib.GenDesc),
+               ("dladmm_sg_pair", _lib.SgPair)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dladmm.h"', "int main(void) {",
+             '  printf("abi %d\\n", DLADMM_ABI_VERSION);']
+    for cname, cls in structs:
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f[0], cname, f[0]))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out["abi"]) == _lib.ABI_VERSION
+    for cname, cls in structs:
+        assert int(out[cname + " size"]) == C.sizeof(cls), cname
+        for f in cls._fields_:
+            assert int(out["%s.%s" % (cname, f[0])]) == getattr(cls, f[0]).offset, (cname, f[0])
