@@ -300,3 +300,28 @@ def test_host_feed_delivers_every_batch_in_order_while_overlapping_uploads():
         dl.HostFeed(iter(host), "cpu")
     with pytest.raises(ValueError):
         dl.HostFeed(iter(host), "cuda", depth=1)
+
+
+@pytest.mark.parametrize("variant", ["lasso", "tied"])
+def test_config3_k15_forward_backward_both_arithmetics_agree(variant):
+    """BASELINE configs[2] (main_syn_lasso_scalar.py, tied/untied layers, K=15 forward + backward) at m=250, d=500: loss and
+    every parameter gradient of the tcgen05 path against the FFMA (fp32) path, which the fixtures pin to the reference; the
+    LASSO training objective of the reference driver is alpha*|Z_k|_1 + 0.5*|X - A Z_k|_2^2 per layer (squared residual)."""
+    m, d, B, K = 250, 500, 4096, 15
+    res = {}
+    for precision in ("fp32", "tf32x3"):
+        model, data = _model(variant, m, d, B, K, seed=9, precision=precision)
+        if variant == "lasso":
+            Z, E, L, T = model(data.X)
+            loss = sum((0.6 ** (K - 1 - k)) * (0.01 * Z[k].abs().sum() + 0.5 * (E[k] - T[k + 1]).pow(2).sum()) for k in range(K)) / B
+        else:
+            loss, _ = model.l1l1_loss(data.X, 0.01, [0.6 ** (K - 1 - k) for k in range(K)])
+        loss.backward()
+        res[precision] = (loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()})
+    (l0, g0), (l1, g1) = res["fp32"], res["tf32x3"]
+    assert abs(l0 - l1) < 2e-5 * abs(l0)
+    # some scalar gradients are sums that cancel to ~1e-5 of the others: errors are judged against the largest scalar gradient too
+    G = max(v.norm().item() for n, v in g0.items() if v.numel() == 1)
+    for n in g0:
+        assert torch.isfinite(g1[n]).all(), n
+        assert rel_l2(g1[n], g0[n], floor=1e-2 * G if g0[n].numel() == 1 else 1e-5) < 1e-2, n
