@@ -297,6 +297,8 @@ class DLADMMNet(nn.Module):
             Z, E, L, T, _, _ = run_forward(spec, self.A, x, self.Z0, self.E0, self.L0, [p.detach() for p in params],
                                            want_masks=False, last_only=last_only, objective_alpha=float(alpha), extras=extras)
         if last_only:
+            if self.variant in _NEWS:
+                raise RuntimeError("last_only is not offered for the newS variants")
             Zl, El, Ll, Tl = [Z[(K - 1) % 2]], [E[(K - 1) % 2]], [L[(K - 1) % 2]], [T[K % 2]]
             outs = (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)
         else:
@@ -305,6 +307,8 @@ class DLADMMNet(nn.Module):
 
     def _as_lists(self, Z, E, L, T):
         Zl, El, Ll, Tl = list(Z.unbind(0)), list(E.unbind(0)), list(L.unbind(0)), list(T.unbind(0))
+        if self.variant in _NEWS:        # the variant's own return convention: E = [E0, E_1, ..], L = [L0, L_1, ..]
+            return Zl, [self.E0] + El[:-1], [self.L0] + Ll[:-1]
         return (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)
 
     def l1l1_loss(self, x, alpha, layer_weights=None):
@@ -350,7 +354,7 @@ class DLADMMNet(nn.Module):
     def KM(self, Zk, Ek, Lk, Tk, X, **kwargs):
         """One classical LADMM iteration (test_syn_l1l1_scalar.py:131-160): the learned family-B layer with W = A^T scaled
         by ss1, all betas = beta, thresholds ss1*alpha and ss2.  Returns (Varn, Zn, En, Tn, Ln)."""
-        if _FAMILY[self.variant] != _lib.FAMILY_B:
+        if _FAMILY[self.variant] != _lib.FAMILY_B or self.variant in _NEWS:
             raise NotImplementedError("KM/S/safeguard are built for the family-B variants (scalar, full, tied)")
         beta = float(kwargs.get("beta", 1.0))
         ss1 = kwargs.get("ss1", None)
@@ -384,8 +388,9 @@ class DLADMMNet(nn.Module):
         """The evaluation forward of test_syn_l1l1_scalar.py:179-317: per layer the classical KM step, the learned step,
         the safeguard test ||S(u_L2O)|| < (1-delta)*mu_k per column, the per-column selection and the mu_k update.
         Returns (Z, E, L, T) lists, plus sg_count (columns that fell back to KM, per layer) when both flags are set."""
-        if _FAMILY[self.variant] != _lib.FAMILY_B:
-            raise NotImplementedError("forward_safeguarded is built for the family-B variants (scalar, full, tied)")
+        if _FAMILY[self.variant] != _lib.FAMILY_B or self.variant in _NEWS:
+            raise NotImplementedError("forward_safeguarded is built for the family-B variants (scalar, full, tied); the newS "
+                                      "ordering has its own safeguard (KM_ELZ / Snorm_ELZ), not built")
         layers = self.layers
         if K is None:
             K = layers if (not continued and (use_learned or use_safeguard)) else num_iter

@@ -85,3 +85,24 @@ def test_newS_forward_and_gradients_match_reference_on_gpu(name, precision):
             assert p.grad is None or p.grad.abs().max().item() == 0, nme   # the reference leaves these without a gradient
         else:
             assert rel_l2(p.grad.cpu(), g.grads[nme], floor=1e-5) < GRAD_TOL[precision], (name, nme)
+
+
+@pytest.mark.gpu
+def test_newS_objective_and_loss_follow_the_variant_conventions():
+    """forward_objective / l1l1_loss on a newS module: the objective depends on Z_k only (identical lists), the returned
+    E / L lists use the variant's own shifted convention, and the family-B safeguard entry points refuse the variant."""
+    g = NewSGolden("newS_small")
+    model = g.build("cuda")
+    x = g.X.cuda()
+    with torch.no_grad():
+        Z, E, L = model(x, g.layers)
+    obj, (Zo, Eo, Lo) = model.forward_objective(x, 0.01)
+    assert all(torch.equal(a, b) for a, b in zip(Z, Zo)) and all(torch.equal(a, b) for a, b in zip(E, Eo))
+    assert all(torch.equal(a, b) for a, b in zip(L, Lo)) and torch.equal(Eo[0], model.E0)
+    A = g.A.cuda()
+    exp = torch.stack([0.01 * Z[k].abs().sum() + (x - A @ Z[k]).abs().sum() for k in range(g.layers)])
+    assert rel_l2(obj, exp) < 1e-4
+    loss, outs = model.l1l1_loss(x, 0.01)
+    assert len(outs) == 3 and abs(loss.item() - exp.sum().item() / x.shape[1]) < 1e-4 * abs(loss.item())
+    with pytest.raises(NotImplementedError):
+        model.forward_safeguarded(x, True, True)
