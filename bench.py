@@ -283,15 +283,15 @@ def run_ours(args):
         tm = dl.VARIANT_CLASSES[VARIANT](M, 10000, D, Bt, A_host, Z0[:, :Bt].contiguous(), E0[:, :Bt].contiguous(),
                                          L0[:, :Bt].contiguous(), K_LAYERS, precision=precision, device=dev)
         Xt = X[:, :Bt].contiguous()
+        if world > 1:
+            tm.sync_gradients(True)
 
         wts = [0.6 ** 3] * (K_LAYERS - 1) + [1.0]
 
         def step_train():
             tm.zero_grad(set_to_none=True)
             loss, _ = tm.l1l1_loss(Xt, 0.001, wts)       # main_syn_l1l1_scalar.py:289-299, fused
-            loss.backward()
-            if world > 1:
-                dl.allreduce_gradients(list(tm.parameters()))
+            loss.backward()                              # world > 1: the backward allreduces the gradient buffer in place
         for _ in range(2):
             step_train()
         barrier()

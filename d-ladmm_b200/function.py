@@ -25,6 +25,7 @@ class LayerSpec(object):
         self.slots = slots          # list (K) of dict slot -> param index
         self.weights = weights      # list (K) of param index of fc weight
         self.fixed = fixed or {}    # slot -> non-learnable 0-dim tensor (lena thresholds)
+        self.grad_sync = None       # (process group or None,) : sum-allreduce the step's gradient buffer inside backward
 
 
 def _require_cuda_f32(name, t):
@@ -159,7 +160,7 @@ def _flat_zero_grads(params, needs):
     sizes = [(-(-t.numel() // 4) * 4) if needs[i] else 0 for i, t in enumerate(params)]
     total = sum(sizes)
     if total == 0:
-        return [None] * len(params)
+        return [None] * len(params), None
     flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
     grads, off = [], 0
     for i, t in enumerate(params):
@@ -168,7 +169,18 @@ def _flat_zero_grads(params, needs):
             continue
         grads.append(flat[off:off + t.numel()].view(t.shape))
         off += sizes[i]
-    return grads
+    return grads, flat
+
+
+def _sync_gradients(spec, flat):
+    """Data-parallel training over column shards: the parameter gradients of this rank's columns are one
+    contiguous buffer, sum-allreduced in place (NCCL, stream-ordered after the backward kernels) before autograd hands
+    them to `.grad` -- no staging copy, one collective per backward."""
+    if spec.grad_sync is None or flat is None:
+        return
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(spec.grad_sync[0]) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=spec.grad_sync[0])
 
 
 class UnrolledLADMM(torch.autograd.Function):
@@ -200,7 +212,7 @@ class UnrolledLADMM(torch.autograd.Function):
             off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[6:]
-        grads = _flat_zero_grads(params, needs)
+        grads, flat = _flat_zero_grads(params, needs)
         cot = _lib.Cotangents()
         keep = []
         for name, g in (("gZ", gZ), ("gE", gE), ("gL", gL), ("gT", gT)):
@@ -215,6 +227,7 @@ class UnrolledLADMM(torch.autograd.Function):
             p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True, Vsave=Vsave)
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
+            _sync_gradients(spec, flat)
         return (None, None, None, None, None, None) + tuple(grads)
 
 
@@ -271,7 +284,7 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[8:]
-        grads = _flat_zero_grads(params, needs)
+        grads, flat = _flat_zero_grads(params, needs)
         scale = (gloss.detach().to(torch.float32) / float(max(ctx.B, 1))).reshape(1).contiguous()
         cot = _lib.Cotangents()
         cot.loss_kind = 1
@@ -286,4 +299,5 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
             scale.record_stream(torch.cuda.current_stream(dev))
+            _sync_gradients(spec, flat)
         return (None,) * 8 + tuple(grads)

@@ -183,6 +183,15 @@ class DLADMMNet(nn.Module):
         return out
 
     # ---- call description for the library ---------------------------------------------------------
+    def sync_gradients(self, enable=True, group=None):
+        """Data-parallel training over column shards: with this on, every backward through the module sum-allreduces the
+        step's parameter gradients across the ranks of `group` (default: the world) in place, inside the backward, so that
+        `.grad` already holds the global sum (normalise the loss by the GLOBAL batch).  Replaces a separate
+        `allreduce_gradients(model.parameters())` call and its staging copies."""
+        self._grad_sync = (group,) if enable else None
+        self.__dict__.pop("_spec_cache", None)
+        return self
+
     def _weight_module(self, k):
         if self._tie == "all":
             return self.fc
@@ -232,6 +241,7 @@ class DLADMMNet(nn.Module):
         if self.variant == "lena":
             fixed = {"theta1": self.active_para, "theta2": self.active_para1}
         spec = LayerSpec(fam, self.m, self.d, K, _lib.PRECISIONS[self.precision], slots, weights, fixed)
+        spec.grad_sync = getattr(self, "_grad_sync", None)
         return spec, params
 
     def _forward_newS(self, x, K):

@@ -325,3 +325,17 @@ def test_config3_k15_forward_backward_both_arithmetics_agree(variant):
     for n in g0:
         assert torch.isfinite(g1[n]).all(), n
         assert rel_l2(g1[n], g0[n], floor=1e-2 * G if g0[n].numel() == 1 else 1e-5) < 1e-2, n
+
+
+def test_sync_gradients_is_inert_without_a_process_group():
+    """model.sync_gradients() allreduces inside backward only when torch.distributed is initialised with more than one
+    rank (tools/check_grad_sync.py covers world size 2 under torchrun); alone it must not change anything."""
+    model, data = _model("scalar", 60, 100, 64, 3)
+    loss, _ = model.l1l1_loss(data.X, 0.01)
+    loss.backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad(set_to_none=True)
+    model.sync_gradients(True)
+    loss, _ = model.l1l1_loss(data.X, 0.01)
+    loss.backward()
+    assert all(rel_l2(p.grad, r, floor=1e-7) < 1e-5 for p, r in zip(model.parameters(), ref))    # dW atomics: order only
