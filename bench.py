@@ -38,9 +38,9 @@ F_GEMM_PER_COL = 2.0 * M * D                      # one (d x m)(m x 1) or (m x d
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture of the final build
-# (profiles/r01_ncu_full_summary_v6.md; a training-mode launch: it also writes the 1-byte prox masks, 16.4 MB for `gemm_elt`
+# (profiles/r01_ncu_full_summary_v7.md; a training-mode launch: it also writes the 1-byte prox masks, 16.4 MB for `gemm_elt`
 # and 32.8 MB for `gemm_z`, which the inference launch timed here does not), keyed by (precision, kernel kind)
-TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 332.134144e6 + 228.335616e6, ("tf32x3", "gemm_z"): 197.939712e6 + 121.106432e6}
+TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 332.131072e6 + 228.349184e6, ("tf32x3", "gemm_z"): 197.948416e6 + 119.981056e6}
 
 
 def _peaks():
