@@ -96,13 +96,13 @@ def load_mu_updater_dict():
 
 
 def load_eval_class(layers, alpha=0.01, delta=-99.0, mu_k_method="None", mu_k_param=0.0, continued=False, num_iter=200,
-                    use_learned=True, use_safeguard=True):
+                    use_learned=True, use_safeguard=True, script="test_syn_l1l1_scalar.py"):
     """The evaluation ``DLADMMNet`` of test_syn_l1l1_scalar.py:75-317 (KM, S, safeguarded forward), unmodified.
 
     The class reads script-level globals (test_syn_l1l1_scalar.py:39-55: alpha, delta, mu_k_method, mu_k_param,
     layers, K, args.continued, mu_updater_dict); they are supplied through the exec namespace."""
     import types
-    path = os.path.join(REFERENCE_ROOT, "test_syn_l1l1_scalar.py")
+    path = os.path.join(REFERENCE_ROOT, script)       # e.g. test_syn_l1l1_newS_Acols.py: the E -> L -> Z evaluation class
     with open(path, "r") as fh:
         tree = ast.parse(fh.read(), filename=path)
     nodes = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DLADMMNet"]

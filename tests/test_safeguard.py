@@ -164,3 +164,39 @@ def test_safeguard_needs_family_b():
                             L0=torch.zeros(8, 4), layers=2, device=dev)
     with pytest.raises(NotImplementedError):
         net.forward_safeguarded(torch.zeros(8, 4, device=dev), True, True)
+
+
+@pytest.mark.skipif(not lr.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("ul,us,cont,method,param,delta", [(True, True, False, "EMA", 0.5, 0.0), (True, True, True, "GS", 0.9, 0.1),
+                                                           (True, False, False, "None", 0.0, -99.0),
+                                                           (False, False, False, "None", 0.0, -99.0)])
+def test_newS_safeguard_oracle_bit_exact_with_live_reference_class(ul, us, cont, method, param, delta):
+    """Groundwork for the SURVEY 8(f)-2 remainder (product path not built yet): the oracle's restatement of the
+    E -> L -> Z safeguarded evaluation (KM_ZEL / KM_ELZ / Snorm_ELZ, test_syn_l1l1_newS_Acols.py:136-277) against the
+    unmodified reference class, learned / classical / safeguarded / continued modes, with fallbacks actually happening."""
+    m, d, B, layers, num_iter = 24, 40, 32, 5, 12
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(m, d, generator=g); A = A / A.pow(2).sum(0, keepdim=True).sqrt()
+    Zs = (torch.rand(d, B, generator=g) < 0.1).float() * torch.randn(d, B, generator=g)
+    Es = (torch.rand(m, B, generator=g) < 0.1).float() * torch.randn(m, B, generator=g)
+    X = A.mm(Zs) + Es
+    z = lambda r: torch.zeros(r, B)
+    cls = lr.load_eval_class(layers, alpha=0.01, delta=delta, mu_k_method=method, mu_k_param=param, continued=cont,
+                             num_iter=num_iter, use_learned=ul, use_safeguard=us, script="test_syn_l1l1_newS_Acols.py")
+    torch.manual_seed(3)
+    with lr.cuda_is_identity():
+        ref = cls(m=m, n=1, d=d, batch_size=B, A=A, Z0=z(d), E0=z(m), L0=z(m), layers=layers)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    for k in sd:
+        sd[k] = sd[k] * 0.3 if k.startswith("fc") else sd[k] * (1 + 0.2 * torch.randn(sd[k].shape, generator=g))
+    ref.load_state_dict(sd)
+    K = layers if (not cont and (ul or us)) else num_iter
+    with torch.no_grad(), lr.cuda_is_identity():
+        out = ref(X, ul, us, cont, K)
+    Zo, Eo, Lo, cnt, _ = orc.safeguarded_forward_newS(sd, A, X, z(d), z(m), z(m), layers, ul, us, cont, None, num_iter, delta,
+                                                      method, param, 0.01, lip=float(ref.L))
+    assert len(out[0]) == len(Zo) == K + 1
+    for a, b in zip(list(out[0]) + list(out[1]) + list(out[2]), Zo + Eo + Lo):
+        assert torch.equal(a, b)
+    if ul and us:
+        assert [float(c) for c in out[3]] == cnt and 0 < sum(cnt) < layers * B
