@@ -8,7 +8,8 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _ALL_NPZ = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 NEWS_GOLDEN_NAMES = [n for n in _ALL_NPZ if "newS" in n]             # E -> L -> Z ordering fixtures (tests/test_newS.py)
-GOLDEN_NAMES = [n for n in _ALL_NPZ if not n.startswith("sg_") and n != "lena_psnr" and "newS" not in n]   # lena_psnr: tests/test_lena_psnr.py
+ELZ_GOLDEN_NAMES = [n for n in _ALL_NPZ if n.startswith("elz_")]     # newS-ordering safeguarded evaluation (oracle only, so far)
+GOLDEN_NAMES = [n for n in _ALL_NPZ if not n.startswith(("sg_", "elz_")) and n != "lena_psnr" and "newS" not in n]   # lena_psnr: tests/test_lena_psnr.py
 SG_GOLDEN_NAMES = [n for n in _ALL_NPZ if n.startswith("sg_")]      # safeguarded evaluation fixtures
 SMALL_GOLDEN = [n for n in GOLDEN_NAMES if "shape" not in n]
 

@@ -200,3 +200,32 @@ def test_newS_safeguard_oracle_bit_exact_with_live_reference_class(ul, us, cont,
         assert torch.equal(a, b)
     if ul and us:
         assert [float(c) for c in out[3]] == cnt and 0 < sum(cnt) < layers * B
+
+
+def test_newS_safeguard_oracle_matches_committed_reference_outputs():
+    """tests/golden/elz_*.npz (oracle/make_golden_safeguard_newS.py, unmodified test_syn_l1l1_newS_Acols.py class): the
+    oracle restatement reproduces every returned iterate and the fallback counts on any box."""
+    import os
+    from _util import ELZ_GOLDEN_NAMES, GOLDEN_DIR
+    assert len(ELZ_GOLDEN_NAMES) >= 4
+    fired = 0
+    for name in ELZ_GOLDEN_NAMES:
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        t = lambda k: torch.from_numpy(z[k].copy())
+        sd = {str(k): t("sd/" + str(k)) for k in z["keys"]}
+        A, X = t("A"), t("X")
+        m, d = A.shape
+        B = X.shape[1]
+        zz = lambda r: torch.zeros(r, B)
+        Z, E, L, cnt, _ = orc.safeguarded_forward_newS(sd, A, X, zz(d), zz(m), zz(m), int(z["layers"]), bool(z["use_learned"]),
+                                                       bool(z["use_safeguard"]), bool(z["continued"]), None, int(z["num_iter"]),
+                                                       float(z["delta"]), str(z["method"]), float(z["param"]), float(z["alpha"]),
+                                                       lip=float(z["lip"]))
+        assert len(Z) == z["Z"].shape[0]
+        for k in range(len(Z)):
+            assert rel_l2(Z[k], t("Z")[k], floor=1e-6) < 2e-6 and rel_l2(E[k], t("E")[k], floor=1e-6) < 2e-6, (name, k)
+            assert rel_l2(L[k], t("L")[k], floor=1e-6) < 2e-6, (name, k)
+        if bool(z["use_learned"]) and bool(z["use_safeguard"]):
+            assert cnt == z["sg_count"].tolist()
+            fired += int(0 < sum(cnt) < int(z["layers"]) * B)
+    assert fired >= 1
