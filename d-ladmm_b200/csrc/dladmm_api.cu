@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_gemm.cuh"
+#include "host_common.cuh"
 
 namespace dladmm {
 
@@ -47,70 +48,6 @@ LaunchScope::~LaunchScope() {
     fprintf(stderr, "[dladmm] launch kind %d -> %s\n", kind, cudaGetErrorString(e));
     fflush(stderr);
   }
-}
-
-// ---- workspace carving -------------------------------------------------------------------------
-struct Workspace {
-  // forward
-  float* Ap;    // (m x dp)      A, K-major padded
-  float* Wp;    // nW x (d x mp) W_k, K-major padded
-  // backward
-  float* Atp;   // (d x mp)      A^T
-  float* Wtp;   // nW x (m x dp) W_k^T
-  float* cZ;    // (d x B) carried dZ / dx1
-  float* cE;    // (m x B)
-  float* cL;    // (m x B)
-  float* dR;    // (m x B)
-  float* part;  // SL_COUNT x ncolTiles x prow
-  size_t bytes;
-  int mp, dp, nW, ncolTiles, prow;
-};
-
-// tied variant passes the same W pointer in every layer: map layer -> index of its unique weight
-struct WeightMap {
-  std::vector<const float*> uniq;
-  std::vector<int> idx;
-  explicit WeightMap(const dladmm_problem* p) : idx(p->K, 0) {
-    for (int k = 0; k < p->K; ++k) {
-      size_t j = 0;
-      while (j < uniq.size() && uniq[j] != p->layers[k].W) ++j;
-      if (j == uniq.size()) uniq.push_back(p->layers[k].W);
-      idx[k] = (int)j;
-    }
-  }
-};
-
-static int unique_weights(const dladmm_problem* p) { return (int)WeightMap(p).uniq.size(); }
-static int weight_index(const dladmm_problem* p, int k) { return WeightMap(p).idx[k]; }
-
-static Workspace carve(const dladmm_problem* p, int for_backward) {
-  Workspace w;
-  memset(&w, 0, sizeof(w));
-  w.mp = round_up(p->m, 32);
-  w.dp = round_up(p->d, 32);
-  w.nW = unique_weights(p);
-  w.ncolTiles = (int)((p->B + SG_BN - 1) / SG_BN);
-  w.prow = round_up(std::max(p->m, p->d), 32);
-  char* base = (char*)p->workspace;
-  size_t off = 0;
-  auto take = [&](size_t nfloats) {
-    float* r = (float*)(base + off);
-    off += round_up64((i64)nfloats * 4, 256);
-    return r;
-  };
-  w.Ap = take((size_t)p->m * w.dp);
-  w.Wp = take((size_t)w.nW * p->d * w.mp);
-  if (for_backward) {
-    w.Atp = take((size_t)p->d * w.mp);
-    w.Wtp = take((size_t)w.nW * p->m * w.dp);
-    w.cZ = take((size_t)p->d * p->B);
-    w.cE = take((size_t)p->m * p->B);
-    w.cL = take((size_t)p->m * p->B);
-    w.dR = take((size_t)p->m * p->B);
-    w.part = take((size_t)SL_COUNT * w.ncolTiles * w.prow);
-  }
-  w.bytes = off;
-  return w;
 }
 
 static int validate(const dladmm_problem* p, int for_backward) {
@@ -160,27 +97,6 @@ static int check_device() {
     return DLADMM_ERR_DEVICE;
   }
   return DLADMM_OK;
-}
-
-// slab addressing -----------------------------------------------------------------------------------
-struct Slabs {
-  const dladmm_problem* p;
-  i64 zs, ms;   // slab sizes in elements
-  explicit Slabs(const dladmm_problem* q) : p(q), zs((i64)q->d * q->B), ms((i64)q->m * q->B) {}
-  int slot(int k) const { return p->last_only ? (k & 1) : k; }
-  const float* Zin(int k) const { return k == 0 ? p->Z0 : p->Z + zs * slot(k - 1); }   // Z_{k-1}
-  const float* Ein(int k) const { return k == 0 ? p->E0 : p->E + ms * slot(k - 1); }
-  const float* Lin(int k) const { return k == 0 ? p->L0 : p->L + ms * slot(k - 1); }
-  float* Zout(int k) const { return p->Z + zs * slot(k); }
-  float* Eout(int k) const { return p->E + ms * slot(k); }
-  float* Lout(int k) const { return p->L + ms * slot(k); }
-  float* Tslab(int k) const { return p->T + ms * slot(k); }                            // T_k, k = 0..K
-  uint8_t* mZ(int k) const { return p->maskZ ? p->maskZ + zs * slot(k) : nullptr; }
-  uint8_t* mE(int k) const { return p->maskE ? p->maskE + ms * slot(k) : nullptr; }
-};
-
-static const dladmm_bparam& betaL(const dladmm_problem* p, const dladmm_layer& l) {
-  return p->family == DLADMM_FAMILY_A ? l.beta1 : l.beta3;
 }
 
 // launch helpers --------------------------------------------------------------------------------------
@@ -260,65 +176,6 @@ static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_
 }
 
 // ---- backward ---------------------------------------------------------------------------------------
-static void add_job(ReduceJobs& jobs, int slot, const dladmm_bparam& q, int rows) {
-  if (q.grad == nullptr || q.ptr == nullptr || q.col_period != 0) return;   // per-slot params use atomics
-  ReduceJob& j = jobs.j[jobs.n++];
-  j.slot = slot;
-  j.scalar = q.row_stride == 0;
-  j.rows = rows;
-  j.grad = q.grad;
-}
-
-static void add_m1_jobs(const dladmm_problem* p, ReduceJobs& jobs, const dladmm_layer& l) {
-  add_job(jobs, SL_BL, betaL(p, l), p->m);
-  if (p->family == DLADMM_FAMILY_B) {
-    add_job(jobs, SL_TH2, l.theta2, p->m);
-    add_job(jobs, SL_SS2, l.ss2, p->m);
-    add_job(jobs, SL_B2, l.beta2, p->m);
-  } else if (p->family == DLADMM_FAMILY_A) {
-    add_job(jobs, SL_TH2, l.theta2, p->m);
-    add_job(jobs, SL_B2, l.beta2, p->m);
-  } else {
-    add_job(jobs, SL_SS2, l.ss2, p->m);
-    add_job(jobs, SL_B2, l.ss2_2, p->m);
-  }
-}
-
-static int launch_reduce(const ReduceJobs& jobs, const Workspace& w, cudaStream_t st) {
-  if (jobs.n == 0) return DLADMM_OK;
-  int maxrows = 1;
-  for (int i = 0; i < jobs.n; ++i)
-    if (!jobs.j[i].scalar) maxrows = std::max(maxrows, jobs.j[i].rows);
-  dim3 grid((maxrows + 7) / 8, jobs.n);
-  { LaunchScope ls(DLADMM_KIND_BWD_REDUCE, st); reduce_partials_kernel<<<grid, 256, 0, st>>>(jobs, w.part, w.ncolTiles, w.prow); }
-  DL_CUDA(cudaGetLastError());
-  return DLADMM_OK;
-}
-
-static M1Args make_m1(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& w, int j) {
-  Slabs s(p);
-  const dladmm_layer& l = p->layers[j];
-  M1Args a;
-  a.Tn = s.Tslab(j + 1);
-  a.Ek = s.Eout(j);
-  a.Ep = s.Ein(j);
-  a.Lp = s.Lin(j);
-  a.maskE = s.mE(j);
-  a.gE = g->gE ? g->gE + s.ms * j : nullptr;
-  a.gL = g->gL ? g->gL + s.ms * j : nullptr;
-  a.gT = g->gT ? g->gT + s.ms * (j + 1) : nullptr;
-  a.bL = make_bp(betaL(p, l));
-  a.b2 = make_bp(l.beta2);
-  a.ss2 = make_bp(l.ss2);
-  a.ss2_2 = make_bp(l.ss2_2);
-  a.th2 = make_bp(l.theta2);
-  a.dR = w.dR; a.cE = w.cE; a.cL = w.cL;
-  a.B = p->B;
-  a.lw = 0.f; a.lscale = nullptr;
-  if (g->loss_kind == 1 && g->loss_scale && g->loss_layer_weight) { a.lw = g->loss_layer_weight[j]; a.lscale = g->loss_scale; }
-  return a;
-}
-
 template <int FAM>
 static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& w, cudaStream_t st) {
   Slabs s(p);
@@ -382,8 +239,6 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
 }
 
 }  // namespace dladmm
-
-#include "umma_path.cuh"
 
 namespace dladmm {
 
@@ -459,7 +314,7 @@ int dladmm_query(int device, dladmm_caps* caps) {
   caps->cc_minor = prop.minor;
   caps->sm_count = prop.multiProcessorCount;
   caps->supported = prop.major == 10;
-  caps->has_tcgen05 = DLADMM_HAS_UMMA;
+  caps->has_tcgen05 = 1;
   caps->total_mem = (int64_t)prop.totalGlobalMem;
   return DLADMM_OK;
 }

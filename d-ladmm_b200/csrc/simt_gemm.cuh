@@ -261,7 +261,7 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceJobs 
       if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) jb.grad[0] += sm[0];
+    if (threadIdx.x == 0) atomicAdd(jb.grad, sm[0]);   // one add per (parameter, launch); atomic because a C-ABI caller may alias grads between slots
   } else {
     // one warp per row
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -269,7 +269,7 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceJobs 
     float s = 0.f;
     for (int ct = threadIdx.x & 31; ct < ncolTiles; ct += 32) s += base[(i64)ct * prow + row];
     s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) jb.grad[row] += s;
+    if ((threadIdx.x & 31) == 0) atomicAdd(jb.grad + row, s);
   }
 }
 

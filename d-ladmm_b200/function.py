@@ -112,17 +112,39 @@ def _check_inputs(spec, A, X, Z0, E0, L0, params):
                            (B, tuple(Z0.shape), tuple(E0.shape), tuple(L0.shape)))
 
 
+def _pad_cols(t, Bp):
+    """(.., B) -> contiguous (.., Bp) with zero columns appended (no copy when nothing is to be padded)."""
+    if t.shape[-1] == Bp:
+        return t.contiguous()
+    out = t.new_zeros(t.shape[:-1] + (Bp,))
+    out[..., :t.shape[-1]] = t
+    return out
+
+
+def padded_batch(spec, B):
+    """The tensor-core kernels move every (rows x B) array with TMA, which needs a 16-byte multiple pitch: batches with
+    B % 4 != 0 (the reference scripts' default -bs 25, main_syn_l1l1_scalar.py:20) are stored with a pitch of B rounded up
+    to 4 -- zero observation columns, which stay exactly zero through every layer and contribute nothing to any
+    parameter gradient -- and the caller gets views narrowed to B columns."""
+    if spec.precision == _lib.PRECISIONS["fp32"] or B % 4 == 0:
+        return B
+    return (B + 3) // 4 * 4
+
+
 def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_init=None, objective_alpha=None, extras=None):
     """Launch the K-layer forward.  Returns stacked (Z, E, L, T, maskZ, maskE).  `T_init` (m,B): T_0 supplied by the
     caller instead of A Z0 + E0 - X (single-layer steps from an arbitrary state).  `objective_alpha`: also compute the
     per-layer L1-L1 objective inside the product epilogues; `extras` (a dict) receives "objective" (K floats) and, in
-    training mode (`want_masks`), "Vsave" (the kept W V operands the backward reuses)."""
+    training mode (`want_masks`), "Vsave" (the kept W V operands the backward reuses) and "padded" (the inputs and
+    outputs at the padded pitch, see padded_batch; the returned Z, E, L, T are then views narrowed to B columns)."""
     lib = _lib.load()
     _check_inputs(spec, A, X, Z0, E0, L0, params)
-    X = X.contiguous()
-    A, Z0, E0, L0 = A.contiguous(), Z0.contiguous(), E0.contiguous(), L0.contiguous()
+    B_user = X.shape[1]
+    Bp = padded_batch(spec, B_user)
+    X, Z0, E0, L0 = _pad_cols(X, Bp), _pad_cols(Z0, Bp), _pad_cols(E0, Bp), _pad_cols(L0, Bp)
+    A = A.contiguous()
     params = [t.contiguous() for t in params]
-    m, d, K, B = spec.m, spec.d, spec.K, X.shape[1]
+    m, d, K, B = spec.m, spec.d, spec.K, Bp
     dev = X.device
     depth = 2 if last_only else K
     Z = torch.empty((depth, d, B), dtype=torch.float32, device=dev)
@@ -136,9 +158,9 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
             maskE = torch.empty((K, m, B), dtype=torch.uint8, device=dev)
     if T_init is not None:
         _require_cuda_f32("T_init", T_init)
-        T_init = T_init.contiguous()
-        if tuple(T_init.shape) != (m, B):
+        if tuple(T_init.shape) != (m, B_user):
             raise RuntimeError("T_init must be (m, B)")
+        T_init = _pad_cols(T_init, Bp)
     # the tensor-core path keeps every layer's W V operand for the backward (the FFMA path recomputes it in its loader)
     keep_v = want_masks and extras is not None and spec.precision != _lib.PRECISIONS["fp32"] and B % 4 == 0
     Vsave = torch.empty((K, m, B), dtype=torch.float32, device=dev) if keep_v else None
@@ -151,6 +173,9 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
         ws.record_stream(torch.cuda.current_stream(dev))
     if extras is not None:
         extras["Vsave"], extras["objective"] = Vsave, obj
+        extras["padded"] = (X, Z0, E0, L0, Z, E, L, T)
+    if Bp != B_user:
+        Z, E, L, T = Z[..., :B_user], E[..., :B_user], L[..., :B_user], T[..., :B_user]
     return Z, E, L, T, maskZ, maskE
 
 
@@ -194,7 +219,9 @@ class UnrolledLADMM(torch.autograd.Function):
         ctx.spec = spec
         ctx.nparams = len(params)
         ctx.has_maskE = maskE is not None
-        saved = [A, X, Z0, E0, L0, Z, E, L, T, maskZ, extras["Vsave"]] + ([maskE] if maskE is not None else []) + list(params)
+        ctx.B_user = X.shape[1]
+        Xp, Z0p, E0p, L0p, Zp, Ep, Lp, Tp = extras["padded"]       # the same tensors unless B % 4 != 0 (padded pitch)
+        saved = [A, Xp, Z0p, E0p, L0p, Zp, Ep, Lp, Tp, maskZ, extras["Vsave"]] + ([maskE] if maskE is not None else []) + list(params)
         ctx.save_for_backward(*saved)
         ctx.set_materialize_grads(False)
         return Z, E, L, T
@@ -217,14 +244,14 @@ class UnrolledLADMM(torch.autograd.Function):
         keep = []
         for name, g in (("gZ", gZ), ("gE", gE), ("gL", gL), ("gT", gT)):
             if g is not None:
-                g = g.contiguous()
                 _require_cuda_f32(name, g)
+                g = _pad_cols(g, X.shape[1])
                 keep.append(g)
                 setattr(cot, name, g.data_ptr())
         layers = _build_layers(spec, params, grads)
         dev = X.device
         with torch.cuda.device(dev):
-            p, ws = _problem(spec, A, X.contiguous(), Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True, Vsave=Vsave)
+            p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True, Vsave=Vsave)
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
             _sync_gradients(spec, flat)

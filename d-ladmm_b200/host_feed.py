@@ -42,7 +42,14 @@ class HostFeed(object):
         self._next_buf = (j + 1) % self._depth
         buf = self._bufs[j]
         if buf is None or buf.shape != host.shape:
+            # A fresh block comes from the CONSUMER stream's pool: kernels enqueued there may still be using the memory it
+            # was carved from, so the first copy must wait for that stream; and the block is written on the copy stream, so
+            # the allocator must not hand it out again (after the feed drops it) before the copy stream is done with it.
+            cur = torch.cuda.current_stream(self.device)
             buf = self._bufs[j] = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+            buf.record_stream(self._copy_stream)
+            self._copy_stream.wait_stream(cur)
+            self._released[j] = None
         with torch.cuda.stream(self._copy_stream):
             if self._released[j] is not None:
                 self._copy_stream.wait_event(self._released[j])     # do not overwrite a buffer a forward still reads

@@ -144,7 +144,7 @@ class DLADMMNet(nn.Module):
         for mod in self.modules():
             if isinstance(mod, nn.Linear):
                 At = self.A.t()
-                mod.weight = nn.Parameter((At + 1e-3 * torch.randn_like(At)) * scale)
+                mod.weight = nn.Parameter(((At + 1e-3 * torch.randn_like(At)) * scale).contiguous())
         self.to(self._device)
 
     # ---- reference surface ---------------------------------------------------------------------

@@ -1,0 +1,93 @@
+"""GPU: BASELINE configs[1] (full, K=20 training) and configs[2] (lasso / tied, K=15 forward + backward) at the
+reference's shape (m=250, d=500) and at a batch large enough that the persistent tcgen05 kernels run more than one
+round, cut their tail round into half tiles and (for `full`) take the per-row parameter-gradient reduction path --
+checked directly against the fp64 oracle (forward iterates, training loss, every parameter gradient), not against the
+library's own FFMA arithmetic.  Plus the 2-rank NCCL test of the in-backward gradient allreduce."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import dladmm_oracle as orc
+import dladmm_b200 as dl
+from _util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case(variant, m, d, B, K, seed):
+    torch.manual_seed(seed)
+    data = dl.gen_syn_data(B, m=m, d=d, seed=1126 + seed, dense_noise_sigma=(1.0 / m ** 0.5 if variant == "lasso" else None))
+    Z0 = torch.rand(d, B, device="cuda") / d                       # main_syn_l1l1_scalar.py:226
+    E0 = torch.zeros(m, B, device="cuda"); L0 = torch.zeros(m, B, device="cuda")
+    model = dl.VARIANT_CLASSES[variant](m, 1, d, B, data.A, Z0, E0, L0, K, precision="tf32x3")
+    return model, data, Z0, E0, L0
+
+
+def _oracle_grads_chunked(variant, sd, A, X, Z0, E0, L0, K, loss_fn, chunk=2048):
+    """fp64 autograd of the oracle over column chunks: the training losses are sums over columns, so the parameter
+    gradients of the chunks add up (keeps the autograd graph of a chunk at a few GB of host memory)."""
+    B = X.shape[1]
+    total, grads = 0.0, None
+    for a in range(0, B, chunk):
+        sl = slice(a, min(B, a + chunk))
+        c = lambda t: t[:, sl].contiguous()
+        l, g = orc.autograd_grads(variant, sd, A, c(X), c(Z0), c(E0), c(L0), K, lambda Z, E, L, T: loss_fn(Z, E, L, T, c(X)))
+        total += float(l)
+        grads = g if grads is None else {k: grads[k] + g[k] for k in g}
+    return total, grads
+
+
+@pytest.mark.parametrize("variant,K,B", [("full", 20, 10240), ("lasso", 15, 10240), ("tied", 15, 10112), ("scalar", 15, 20480)])
+def test_forward_backward_against_fp64_oracle_at_config_size(variant, K, B):
+    m, d = 250, 500
+    model, data, Z0, E0, L0 = _case(variant, m, d, B, K, seed=3)
+    w = [0.6 ** (K - 1 - k) for k in range(K)]
+    alpha = 0.01
+    lasso = variant == "lasso"
+    if lasso:    # main_syn_lasso_scalar.py:276-281: alpha*|Z_k|_1 + 0.5*|X - A Z_k|_2^2, mean over the batch
+        Z, E, L, T = model(data.X)
+        loss = sum(w[k] * (alpha * Z[k].abs().sum() + 0.5 * (E[k] - T[k + 1]).pow(2).sum()) for k in range(K)) / B
+        outs = (Z, E, L, T)
+    else:        # main_syn_l1l1_scalar.py:289-299 (fused)
+        loss, outs = model.l1l1_loss(data.X, alpha, w)
+    loss.backward()
+    d64 = lambda t: t.detach().double().cpu()
+    sd = {k: d64(v) for k, v in model.state_dict().items()}
+    A, X = d64(data.A), d64(data.X)
+    ref = orc.forward(variant, sd, A, X, d64(Z0), d64(E0), d64(L0), K)
+    for name, got, exp in (("Z", outs[0], ref[0]), ("E", outs[1], ref[1]), ("L", outs[2], ref[2])):
+        for k in range(K):
+            err = rel_l2(got[k].cpu(), exp[k], floor=1e-2 * (B ** 0.5))
+            assert err < 2e-5, (variant, name, k, err)
+
+    def loss_fn(Z, E, L, T, Xc):
+        if lasso:
+            return sum(w[k] * (alpha * Z[k].abs().sum() + 0.5 * (Xc - A.mm(Z[k])).pow(2).sum()) for k in range(K)) / B
+        return sum(w[k] * (alpha * Z[k].abs().sum() + (Xc - A.mm(Z[k])).abs().sum()) for k in range(K)) / B
+
+    lref, gref = _oracle_grads_chunked(variant, sd, A, X, d64(Z0), d64(E0), d64(L0), K, loss_fn)
+    assert abs(loss.item() - lref) < 2e-5 * abs(lref), (loss.item(), lref)
+    # scalar gradients can be sums that cancel to a small fraction of their terms: judge them against the largest
+    # gradient of their kind too.  Prox masks / sign(residual) within rounding of a threshold flip between fp32 and
+    # fp64 (a handful of 2.5 M elements), which moves a gradient by ~1e-3 relative; a wrong kernel is off by O(1).
+    G = max(float(v.norm()) for n, v in gref.items() if not n.startswith("fc"))
+    for n, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        floor = 1e-2 * G if not n.startswith("fc") else 1e-5
+        assert rel_l2(p.grad.cpu(), gref[n], floor=floor) < 5e-3, (variant, n, rel_l2(p.grad.cpu(), gref[n], floor=floor))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_in_backward_gradient_allreduce_two_ranks_nccl():
+    """model.sync_gradients(): .grad after backward is the global sum on both ranks and equals one process over all
+    columns (tools/check_grad_sync.py under torchrun, 2 ranks, NCCL)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "tools", "check_grad_sync.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("sync vs post-allreduce") == 2
