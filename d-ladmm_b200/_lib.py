@@ -6,10 +6,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdladmm.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
-PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_BF16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "bf16": PREC_BF16}
+# dladmm_metric: index of each per-layer metric in the (K, MET_COUNT) output of a forward with `metrics`
+METRICS = ("l1_z", "sqerr_z", "l1_res", "sq_res", "sqerr_e", "sqerr_az", "l1_e", "dot_lx", "dgap_l", "dgap_atl")
+MET_COUNT = len(METRICS)
 
 c_float_p = C.c_void_p   # device pointers are opaque to the host
 
@@ -32,7 +35,13 @@ class Problem(C.Structure):
                 ("Z", C.c_void_p), ("E", C.c_void_p), ("L", C.c_void_p), ("T", C.c_void_p),
                 ("maskZ", C.c_void_p), ("maskE", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("T_init", C.c_void_p),
-                ("Vsave", C.c_void_p), ("objective", C.c_void_p), ("objective_alpha", C.c_float), ("reserved2", C.c_int32)]
+                ("Vsave", C.c_void_p), ("objective", C.c_void_p), ("objective_alpha", C.c_float), ("objective_kind", C.c_int32),
+                ("start_half", C.c_int32), ("stop_half", C.c_int32), ("metrics", C.c_void_p)]
+
+
+class Metrics(C.Structure):
+    _fields_ = [("want", C.c_uint32), ("dual_alpha", C.c_float), ("Z_label", C.c_void_p), ("E_label", C.c_void_p),
+                ("X_clean", C.c_void_p), ("out", C.c_void_p)]
 
 
 class Cotangents(C.Structure):
@@ -59,12 +68,12 @@ class SgPair(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int32)]
 
 
-EXPORTS = ["dladmm_sg_norm", "dladmm_sg_select", "dladmm_workspace_bytes", "dladmm_forward", "dladmm_backward", "dladmm_gen_workspace_bytes",
+EXPORTS = ["dladmm_sg_norm", "dladmm_sg_select", "dladmm_sg_norm_elz", "dladmm_sg_select_update", "dladmm_workspace_bytes", "dladmm_forward", "dladmm_backward", "dladmm_gen_workspace_bytes",
            "dladmm_gen_syn", "dladmm_objective", "dladmm_query", "dladmm_last_error", "dladmm_launch_count",
            "dladmm_profile_start", "dladmm_profile_stop"]
 
 KIND_NAMES = ["prep", "gemm_t0", "gemm_z", "gemm_elt", "bwd_elem", "bwd_gemm_dz", "bwd_gemm_dw", "bwd_gemm_dv",
-              "bwd_reduce", "gen", "objective"]
+              "bwd_reduce", "gen", "objective", "metric_gemm", "safeguard", "fwd_persistent"]
 
 _lib = None
 
@@ -97,6 +106,12 @@ def load():
     lib.dladmm_sg_select.restype = C.c_int
     lib.dladmm_sg_select.argtypes = [C.c_int32, C.POINTER(SgPair), C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                      C.c_void_p]
+    lib.dladmm_sg_norm_elz.restype = C.c_int
+    lib.dladmm_sg_norm_elz.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    lib.dladmm_sg_select_update.restype = C.c_int
+    lib.dladmm_sg_select_update.argtypes = [C.c_int32, C.POINTER(SgPair), C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
+                                            C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dladmm_query.restype = C.c_int
     lib.dladmm_query.argtypes = [C.c_int, C.POINTER(Caps)]
     lib.dladmm_launch_count.restype = C.c_int64

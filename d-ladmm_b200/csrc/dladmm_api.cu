@@ -55,10 +55,26 @@ static int validate(const dladmm_problem* p, int for_backward) {
   DL_REQUIRE(p->abi_version == DLADMM_ABI_VERSION, "ABI version mismatch: got %d, library is %d", p->abi_version,
              DLADMM_ABI_VERSION);
   DL_REQUIRE(p->family >= 0 && p->family <= 2, "unknown family %d", p->family);
-  DL_REQUIRE(p->precision >= 0 && p->precision <= 2, "unknown precision %d", p->precision);
-  DL_REQUIRE(p->m > 0 && p->d > 0 && p->K > 0, "m, d, K must be positive (m=%d d=%d K=%d)", p->m, p->d, p->K);
+  DL_REQUIRE(p->precision >= 0 && p->precision <= 3, "unknown precision %d", p->precision);
+  DL_REQUIRE(p->m > 0 && p->d > 0 && p->K >= 0, "m, d must be positive and K non-negative (m=%d d=%d K=%d)", p->m, p->d, p->K);
+  DL_REQUIRE(p->K > 0 || !for_backward, "backward needs K > 0");
   DL_REQUIRE(p->B >= 0, "B must be non-negative");
-  DL_REQUIRE(p->layers != nullptr, "layers is NULL");
+  DL_REQUIRE(p->layers != nullptr || p->K == 0, "layers is NULL");
+  DL_REQUIRE((p->start_half == 0 || p->start_half == 1) && (p->stop_half == 0 || p->stop_half == 1), "start_half / stop_half must be 0 or 1");
+  DL_REQUIRE(!(p->start_half || p->stop_half) || (!for_backward && !p->last_only && p->K > 0),
+             "half-layer calls are forward-only, need K > 0 and every iterate (last_only = 0)");
+  DL_REQUIRE(!(p->start_half && p->T_init), "start_half does not use T_init");
+  DL_REQUIRE(p->objective_kind >= 0 && p->objective_kind <= 2, "unknown objective_kind %d", p->objective_kind);
+  if (p->metrics && p->metrics->want) {
+    const dladmm_metrics* mt = p->metrics;
+    DL_REQUIRE(!for_backward, "metrics are computed by the forward");
+    DL_REQUIRE(mt->out != nullptr && p->objective == nullptr, "metrics need `out` and exclude `objective`");
+    DL_REQUIRE(mt->want < (1u << DLADMM_MET_COUNT), "unknown metric bits %u", mt->want);
+    DL_REQUIRE(!((mt->want >> DLADMM_MET_SQERR_Z) & 1u) || mt->Z_label, "DLADMM_MET_SQERR_Z needs Z_label");
+    DL_REQUIRE(!((mt->want >> DLADMM_MET_SQERR_E) & 1u) || mt->E_label, "DLADMM_MET_SQERR_E needs E_label");
+    DL_REQUIRE(!((mt->want >> DLADMM_MET_SQERR_AZ) & 1u) || mt->X_clean, "DLADMM_MET_SQERR_AZ needs X_clean");
+    DL_REQUIRE(!(p->start_half || p->stop_half), "metrics are not offered for half-layer calls");
+  }
   DL_REQUIRE(p->A && (p->B == 0 || (p->X && p->Z0 && p->E0 && p->L0 && p->Z && p->E && p->L && p->T)),
              "A, X, Z0, E0, L0, Z, E, L, T must be non-NULL");
   for (int k = 0; k < p->K; ++k) {
@@ -149,8 +165,9 @@ static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_
   const int m = p->m, d = p->d;
   const i64 B = p->B;
   int rc;
-  // T_0 = A Z0 + E0 - X (or given by the caller)
-  if (p->T_init) {
+  // T_0 = A Z0 + E0 - X (or given by the caller); a call that starts with an E/T/L-step (start_half) has no T_0
+  if (p->start_half) {
+  } else if (p->T_init) {
     DL_CUDA(cudaMemcpyAsync(s.Tslab(0), p->T_init, sizeof(float) * (size_t)m * B, cudaMemcpyDeviceToDevice, st));
   } else {
     BPlain bl{p->Z0, B};
@@ -160,13 +177,15 @@ static int forward_simt(const dladmm_problem* p, const Workspace& w, cudaStream_
   for (int k = 0; k < p->K; ++k) {
     const dladmm_layer& l = p->layers[k];
     const float* Wk = w.Wp + (size_t)weight_index(p, k) * d * w.mp;
-    {
+    const bool zstep = !(p->start_half && k == 0), estep = !(p->stop_half && k == p->K - 1);
+    const float* Zk = zstep ? s.Zout(k) : p->Z0;                       // start_half: Z_0 := Z0 as given
+    if (zstep) {
       BVar bl{s.Lin(k), s.Tslab(k), make_bp(l.beta1), B};
-      EpiZ epi{s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
+      EpiZ epi{(k == 1 && p->start_half) ? p->Z0 : s.Zin(k), s.Zout(k), s.mZ(k), make_bp(l.theta1), make_bp(l.ss1), B};
       if ((rc = launch_simt(DLADMM_KIND_GEMM_Z, d, B, m, Wk, w.mp, bl, epi, nullptr, 0, 0, st))) return rc;
     }
-    {
-      BPlain bl{s.Zout(k), B};
+    if (estep) {
+      BPlain bl{Zk, B};
       EpiELT<FAM> epi{p->X, s.Ein(k), s.Lin(k), s.Eout(k), s.Lout(k), s.Tslab(k + 1), s.mE(k),
                       make_bp(l.beta2), make_bp(l.ss2), make_bp(l.ss2_2), make_bp(l.theta2), make_bp(betaL(p, l)), B};
       if ((rc = launch_simt(DLADMM_KIND_GEMM_ELT, m, B, d, w.Ap, w.dp, bl, epi, nullptr, 0, 0, st))) return rc;

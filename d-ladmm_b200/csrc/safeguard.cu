@@ -21,6 +21,57 @@ static __global__ void __launch_bounds__(256) sg_norm_kernel(int m, i64 B, float
   out[b] = sqrtf(s);
 }
 
+// Snorm_ELZ (test_syn_l1l1_newS_Acols.py:174-192) with (Znn-Zn)^T P2 (Znn-Zn) = ||Znn-Zn||^2/(beta ss1) - ||A(Znn-Zn)||^2 and
+// A(Znn-Zn) = Tnn - Tn: one thread per column, coalesced over the batch, no d x d operator.
+static __global__ void __launch_bounds__(256) sg_norm_elz_kernel(int m, int d, i64 B, float inv_bss1, const float* __restrict__ Tnn,
+                                                                 const float* __restrict__ Tn, const float* __restrict__ Znn,
+                                                                 const float* __restrict__ Zn, float* __restrict__ out) {
+  const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (b >= B) return;
+  float s1 = 0.f, s3 = 0.f, s2 = 0.f;
+  for (int i = 0; i < m; ++i) {
+    const i64 off = (i64)i * B + b;
+    const float t = Tnn[off], dt = t - Tn[off];
+    s1 += t * t;
+    s3 += dt * dt;
+  }
+  for (int i = 0; i < d; ++i) {
+    const i64 off = (i64)i * B + b;
+    const float dz = Znn[off] - Zn[off];
+    s2 += dz * dz;
+  }
+  out[b] = sqrtf(fmaxf(s1 + (inv_bss1 * s2 - s3), 0.f));
+}
+
+// keep + mu_k update + fallback count in one pass over the columns (mu_updater.py:18-72)
+static __global__ void __launch_bounds__(256) sg_keep_update_kernel(i64 B, const float* __restrict__ snorm, float* __restrict__ mu,
+                                                                    float one_minus_delta, int method, float param,
+                                                                    float* __restrict__ keep, float* __restrict__ fallbacks) {
+  const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
+  float fb = 0.f;
+  if (b < B) {
+    const float s = snorm[b], m0 = mu[b];
+    const bool k = s < one_minus_delta * m0;
+    keep[b] = k ? 1.f : 0.f;
+    fb = k ? 0.f : 1.f;
+    if (k && method != 0) {
+      float upd = s;                                               // RT
+      if (method == 1) upd = param * s + (1.f - param) * m0;        // EMA
+      else if (method == 2) upd = (1.f - param) * m0;               // GS
+      mu[b] = upd;
+    }
+  }
+  fb = warp_sum(fb);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = fb;
+  __syncthreads();
+  if (threadIdx.x == 0 && fallbacks) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += sm[i];
+    if (v != 0.f) atomicAdd(fallbacks, v);                          // integer-valued: exact in any order
+  }
+}
+
 // keep[b] = (snorm[b] < one_minus_delta * mu[b]) ; out = keep ? a : b, column-wise, for several (rows x B) arrays
 struct SelJob { const float* a; const float* b; float* out; int rows; };
 struct SelJobs { int n; SelJob j[6]; };
@@ -51,10 +102,35 @@ int dladmm_sg_norm(int32_t m, int64_t B, float beta, float c, const float* Tn, c
   DL_REQUIRE(m > 0 && B >= 0 && Tn && En && Ek && Ep && out, "sg_norm: bad arguments");
   if (B == 0) return DLADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+  { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
     sg_norm_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, B, beta, c, Tn, En, Ek, Ep, out); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
+}
+
+int dladmm_sg_norm_elz(int32_t m, int32_t d, int64_t B, float inv_beta_ss1, const float* Tnn, const float* Tn, const float* Znn,
+                       const float* Zn, float* out, void* stream) {
+  DL_REQUIRE(m > 0 && d > 0 && B >= 0 && Tnn && Tn && Znn && Zn && out, "sg_norm_elz: bad arguments");
+  if (B == 0) return DLADMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
+    sg_norm_elz_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, d, B, inv_beta_ss1, Tnn, Tn, Znn, Zn, out); }
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
+static int run_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* keep, cudaStream_t st);
+
+int dladmm_sg_select_update(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, float* mu,
+                            float one_minus_delta, int32_t method, float param, float* keep, float* fallbacks, void* stream) {
+  DL_REQUIRE(n_arrays >= 0 && n_arrays <= 6 && (n_arrays == 0 || pairs) && snorm && mu && keep, "sg_select_update: bad arguments");
+  DL_REQUIRE(method >= 0 && method <= 3, "sg_select_update: unknown mu updater %d", method);
+  if (B == 0) return DLADMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
+    sg_keep_update_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, snorm, mu, one_minus_delta, method, param, keep, fallbacks); }
+  DL_CUDA(cudaGetLastError());
+  return run_select(n_arrays, pairs, B, keep, st);
 }
 
 int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, const float* mu,
@@ -62,9 +138,15 @@ int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, c
   DL_REQUIRE(n_arrays >= 0 && n_arrays <= 6 && (n_arrays == 0 || pairs) && snorm && mu && keep, "sg_select: bad arguments");
   if (B == 0) return DLADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+  { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
     sg_keep_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, snorm, mu, one_minus_delta, keep); }
   DL_CUDA(cudaGetLastError());
+  return run_select(n_arrays, pairs, B, keep, st);
+}
+
+}  // extern "C"
+
+static int run_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* keep, cudaStream_t st) {
   if (n_arrays == 0) return DLADMM_OK;
   SelJobs jobs; jobs.n = n_arrays;
   int maxrows = 1;
@@ -75,10 +157,8 @@ int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, c
   }
   i64 blocks = ((i64)maxrows * B + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st);
+  { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
     sg_select_kernel<<<dim3((unsigned)blocks, n_arrays), 256, 0, st>>>(jobs, B, keep); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }
-
-}  // extern "C"

@@ -10,6 +10,7 @@
 // are register-prefetched one chunk ahead (prefetch()).
 #pragma once
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "epilogues.cuh"
 
 namespace dladmm {
@@ -54,6 +55,7 @@ struct UEpiT0 {
   typedef NoPre Pre;
   const float* __restrict__ E0; const float* __restrict__ X; const float* __restrict__ L0; float* __restrict__ T0;
   BP b1; float* __restrict__ V; i64 B; uint32_t in_mask;
+  __nv_bfloat16* __restrict__ Vh; i64 ldh;         // bf16 mode: the W V operand as bf16 (pitch ldh)
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = E0; p[1] = X; p[2] = L0; }
   const uint8_t* host_mask() const { return nullptr; }
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
@@ -71,7 +73,11 @@ struct UEpiT0 {
       const float e0 = slot[i * TILE_B + col], x = slot[SUBF(CHUNK) + i * TILE_B + col], l0 = slot[2 * SUBF(CHUNK) + i * TILE_B + col];
       const float t = fsub(fadd(v[i], e0), x);
       T0[off] = t;
-      V[off] = fadd(l0, fmul(st.b1.at(row, b), t));
+      if (V || Vh) {                                             // (K = 0: T_0 only, no layer to feed)
+        const float vv = fadd(l0, fmul(st.b1.at(row, b), t));
+        if (V) V[off] = vv;
+        if (Vh) Vh[(i64)row * ldh + b] = __float2bfloat16_rn(vv);
+      }
     }
   }
 };
@@ -81,19 +87,26 @@ template <bool PSCALAR>
 struct UEpiZ {
   static constexpr int WARPS = 8;
   static constexpr int CHUNK = 16;
-  static constexpr int NIN = 1;                    // Z_{k-1}
-  struct State { PV<PSCALAR> th1; float s1; float obj; };
+  static constexpr int NIN = 2;                    // Z_{k-1}, Z_label (metrics only)
+  struct State { PV<PSCALAR> th1; float s1; float obj; float sq; };
   typedef NoPre Pre;
   const float* __restrict__ Zp; float* __restrict__ Zk; uint8_t* __restrict__ maskZ;
   BP th1; BP ss1; i64 B; uint32_t in_mask;
-  float* obj_part;                                 // optional: per-warp partial sums of ||Z_k||_1 (fused objective)
-  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; }
+  float* obj_part;                                 // optional: per-warp partial sums of ||Z_k||_1 (fused objective / DLADMM_MET_L1_Z)
+  const float* __restrict__ Zlabel; float* sq_part;  // optional: per-warp partial sums of (Z_label - Z_k)^2 (DLADMM_MET_SQERR_Z)
+  __nv_bfloat16* __restrict__ Zh; i64 ldh;         // bf16 mode: Z_k as bf16, the operand of the A Z product
+  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; p[1] = sq_part ? Zlabel : nullptr; }
   const uint8_t* host_mask() const { return nullptr; }
-  __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; st.obj = 0.f; }
+  __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; st.obj = 0.f; st.sq = 0.f; }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
-    if (!obj_part) return;
-    const float s = warp_sum(st.obj);
-    if (lane == 0) obj_part[entry] = s;
+    if (obj_part) {
+      const float s = warp_sum(st.obj);
+      if (lane == 0) obj_part[entry] = s;
+    }
+    if (sq_part) {
+      const float s = warp_sum(st.sq);
+      if (lane == 0) sq_part[entry] = s;
+    }
   }
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
   template <bool FULL>
@@ -109,36 +122,64 @@ struct UEpiZ {
       unsigned bits;
       const float z = soft_act(fsub(slot[i * TILE_B + col], wv), st.th1.at(row, b), bits);
       Zk[off] = z;
+      if (Zh) Zh[(i64)row * ldh + b] = __float2bfloat16_rn(z);
       if (maskZ) maskZ[off] = (uint8_t)bits;
       if (obj_part) st.obj += fabsf(z);
+      if (sq_part) { const float dl = slot[SUBF(CHUNK) + i * TILE_B + col] - z; st.sq += dl * dl; }   // warp-uniform branch
     }
   }
 };
 
 // E_k, T_{k+1}, L_k from acc = A Z_k; then V_{k+1} = L_k + beta1_{k+1} * T_{k+1} unless this is the last layer
-template <int FAM, bool PSCALAR>
+// MET: also accumulate the per-layer metrics of dladmm_metrics that live on the (m x B) side (two more staged inputs, seven
+// running sums per thread) -- a separate instantiation so that the plain forward keeps its registers and its ring depth.
+constexpr int ELT_NMET = 7;                        // L1_RES, SQ_RES, SQERR_E, SQERR_AZ, L1_E, DOT_LX, DGAP_L
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(__expf(x)); }   // F.softplus, threshold 20
+
+template <int FAM, bool PSCALAR, bool MET = false>
 struct UEpiELT {
   static constexpr int WARPS = 8;
   static constexpr int CHUNK = 8;
-  static constexpr int NIN = 3;                    // X, L_{k-1}, E_{k-1} (family B only)
-  struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; float obj; };
+  static constexpr int NIN = MET ? 5 : 3;          // X, L_{k-1}, E_{k-1} (family B only) [, E_label, X_clean]
+  struct State { PV<PSCALAR> b2, ss2, ss2_2, th2, bL, b1n; float obj; float met[MET ? ELT_NMET : 1]; int o_el, o_xc; };
   typedef NoPre Pre;
-  float* obj_part;                                 // optional: per-warp partial sums of ||E_k - T_{k+1}||_1 = ||X - A Z_k||_1
+  float* obj_part;                                 // optional: per-warp partial sums of the residual term of the objective
+  int obj_kind;                                    // 2: 0.5*(X - A Z_k)^2 (LASSO), else |X - A Z_k| = |E_k - T_{k+1}|
+  const float* __restrict__ Elabel; const float* __restrict__ Xclean;
+  float* met_part; int met_stride;                 // MET: met_part[i * met_stride + entry], i < ELT_NMET
   const float* __restrict__ X; const float* __restrict__ Ep; const float* __restrict__ Lp;
   float* __restrict__ Ek; float* __restrict__ Lk; float* __restrict__ Tn; uint8_t* __restrict__ maskE;
   BP b2, ss2, ss2_2, th2, bL;
   int has_next; BP b1n; float* __restrict__ V;
+  __nv_bfloat16* __restrict__ Vh; i64 ldh;         // bf16 mode: V_{k+1} as bf16 (V itself is then only kept for a backward)
   i64 B; uint32_t in_mask;
-  void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = X; p[1] = Lp; p[2] = FAM == DLADMM_FAMILY_B ? Ep : nullptr; }
+  void host_inputs(const float* (&p)[MAX_EIN]) const {
+    p[0] = X; p[1] = Lp; p[2] = FAM == DLADMM_FAMILY_B ? Ep : nullptr;
+    if (MET) { p[3] = Elabel; p[4] = Xclean; }
+  }
   const uint8_t* host_mask() const { return nullptr; }
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
     st.obj = 0.f;
+    if (MET) {
+#pragma unroll
+      for (int i = 0; i < ELT_NMET; ++i) st.met[i] = 0.f;
+      st.o_el = ((in_mask >> 3) & 1u) ? __popc(in_mask & 7u) * SUBF(CHUNK) : -1;
+      st.o_xc = ((in_mask >> 4) & 1u) ? __popc(in_mask & 15u) * SUBF(CHUNK) : -1;
+    }
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
-    if (!obj_part) return;
-    const float s = warp_sum(st.obj);
-    if (lane == 0) obj_part[entry] = s;
+    if (obj_part) {
+      const float s = warp_sum(st.obj);
+      if (lane == 0) obj_part[entry] = s;
+    }
+    if (MET && met_part) {
+#pragma unroll
+      for (int i = 0; i < ELT_NMET; ++i) {
+        const float s = warp_sum(st.met[i]);
+        if (lane == 0) met_part[(size_t)i * met_stride + entry] = s;
+      }
+    }
   }
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
   template <bool FULL>
@@ -169,9 +210,49 @@ struct UEpiELT {
       const float t = fsub(fadd(acc, e), x);
       const float l = fadd(lp, fmul(st.bL.at(row, b), t));
       Ek[off] = e; Tn[off] = t; Lk[off] = l;
-      if (obj_part) st.obj += fabsf(fsub(e, t));
+      if (obj_part) { const float r = fsub(e, t); st.obj += obj_kind == 2 ? 0.5f * r * r : fabsf(r); }
+      if (MET) {
+        const float r = fsub(e, t);
+        st.met[0] += fabsf(r); st.met[1] += r * r;
+        if (st.o_el >= 0) { const float q = slot[st.o_el + i * TILE_B + col] - e; st.met[2] += q * q; }
+        if (st.o_xc >= 0) { const float q = slot[st.o_xc + i * TILE_B + col] - acc; st.met[3] += q * q; }
+        st.met[4] += fabsf(e); st.met[5] += l * x;
+        st.met[6] += softplus_t(l - 1.f) + softplus_t(-l - 1.f);
+      }
       if (FAM != DLADMM_FAMILY_C && maskE) maskE[off] = (uint8_t)bits;
-      if (has_next) V[off] = fadd(l, fmul(st.b1n.at(row, b), t));
+      if (has_next) {
+        const float vv = fadd(l, fmul(st.b1n.at(row, b), t));
+        if (V) V[off] = vv;
+        if (Vh) Vh[(i64)row * ldh + b] = __float2bfloat16_rn(vv);
+      }
+    }
+  }
+};
+
+// sum over (d x B) of softplus(acc - a) + softplus(-acc - a) with acc = A^T L_k (main_lena.py:145-147, 224): reduction only
+struct UEpiDgap {
+  static constexpr int WARPS = 8;
+  static constexpr int CHUNK = 16;
+  static constexpr int NIN = 0;
+  struct State { float s; };
+  typedef NoPre Pre;
+  float a; float* part; uint32_t in_mask;
+  void host_inputs(const float* (&)[MAX_EIN]) const {}
+  const uint8_t* host_mask() const { return nullptr; }
+  __device__ __forceinline__ void begin(State& st) const { st.s = 0.f; }
+  __device__ __forceinline__ void end(State& st, int entry, int lane) const {
+    const float s = warp_sum(st.s);
+    if (lane == 0) part[entry] = s;
+  }
+  __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
+  template <bool FULL>
+  __device__ __forceinline__ void apply(State& st, const float* __restrict__, int, const Pre&, int row0, i64, bool valid,
+                                        const float (&v)[CHUNK], int n_feat, i64) const {
+    if (!valid) return;
+#pragma unroll
+    for (int i = 0; i < CHUNK; ++i) {
+      if (!FULL && row0 + i >= n_feat) continue;
+      st.s += softplus_t(v[i] - a) + softplus_t(-v[i] - a);
     }
   }
 };

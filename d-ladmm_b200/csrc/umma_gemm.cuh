@@ -18,6 +18,11 @@
 // it), so no split copy of an activation ever exists in HBM.  (Splitting the weights in shared memory as well was measured
 // slower: shared-memory bandwidth -- TMA writes + split + three operand reads per k-step -- is what bounds this kernel.)
 //
+// BF16 mode (NPASS == 2, DLADMM_PREC_BF16): kind::f16 on bf16 operands, one pass, K = 16 per instruction.  The activation
+// operand is a bf16 copy (pitch multiple of 8) that the PRODUCING epilogue wrote next to its fp32 output, loaded as boxes of
+// (64 batch columns x KC rows) with the plain 128-byte swizzle (MN-major canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)),
+// cute/atom/mma_traits_sm100.hpp); weights are converted once per call.  No splitter work.
+//
 // Warp roles (480 threads): warp 0 = TMA producer (operands), warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; two warps per quadrant split the feature rows),
 // warps 10..13 = operand splitters (3xTF32 only), warp 14 = TMA producer of the epilogue-input staging ring.  Persistent over (batch tile, feature tile) pairs,
@@ -119,6 +124,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void umma_op(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF) umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
+}
 // arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -194,8 +213,9 @@ __device__ __forceinline__ bool elect_one() {
 
 // ---- descriptors ---------------------------------------------------------------------------------------
 // instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// a/b format field: kind::tf32 -> 2 (TF32); kind::f16 -> 0 (F16), 1 (BF16)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, uint32_t ab_format = 2u) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): addresses/offsets in 16-byte units
@@ -269,9 +289,10 @@ constexpr uint32_t EIN_MASK_BIT = 1u << 31;                 // in_mask bit: the 
 
 template <int NPASS, int KC>
 struct SmemPlan {
+  static constexpr int EB = NPASS == 2 ? 2 : 4;                      // operand element bytes (bf16 mode: 2)
   static constexpr int NOPS = NPASS == 3 ? 2 : 1;                    // big (+ small)
-  static constexpr int A_BYTES = TILE_B * KC * 4;                    // one operand part
-  static constexpr int B_BYTES = TILE_N * KC * 4;
+  static constexpr int A_BYTES = TILE_B * KC * EB;                   // one operand part
+  static constexpr int B_BYTES = TILE_N * KC * EB;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | A small] [B big | B small]
   static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
   static constexpr int STAGES = 3;
@@ -305,8 +326,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int EPI_WARPS = Epi::WARPS, EPI_PARTS = EPI_WARPS / 4;
   constexpr int SPLIT_WARP0 = EPI_WARP0 + EPI_WARPS, EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS;
   static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
-  constexpr uint32_t B_LAYOUT = KC == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
-  constexpr uint32_t B_SBO = 8 * KC * 4;            // 8 rows of KC floats
+  constexpr bool BF = NPASS == 2;                   // bf16 operands (kind::f16)
+  constexpr int EB = Plan::EB;
+  constexpr int MMA_K = 32 / EB;                    // 8 (tf32) or 16 (bf16): 32 bytes of K per instruction
+  static_assert(KC * EB == 128 || KC * EB == 64, "weight rows of one chunk are 64 or 128 bytes");
+  constexpr uint32_t B_LAYOUT = KC * EB == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+  constexpr uint32_t B_SBO = 8 * KC * EB;           // 8 rows of KC elements
+  constexpr int A_BOX_COLS = 128 / EB;              // batch columns of one activation box: 128-byte rows
   constexpr int CHK = Epi::CHUNK;
   constexpr int SUB_BYTES = CHK * TILE_B * 4;       // one staged array of one chunk
   extern __shared__ uint8_t smem_raw[];
@@ -371,9 +397,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           UMMA_TR(gs, trp, 0); 
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
           mbar_expect_tx(&full[s], Plan::TX_BYTES);
-          // activation (raw fp32): 4 boxes of (32 batch columns x KC rows), 128 B per row
+          // activation (raw fp32 / bf16): boxes of (32 / 64 batch columns x KC rows), 128 B per row
 #pragma unroll
-          for (int g = 0; g < TILE_B / 32; ++g) tma_load_2d(st + g * (KC * 128), &tmA, &full[s], b0 + g * 32, kc * KC);
+          for (int g = 0; g < TILE_B / A_BOX_COLS; ++g)
+            tma_load_2d(st + g * (KC * 128), &tmA, &full[s], b0 + g * A_BOX_COLS, kc * KC);
           // weights, pre-split by the prep kernel: one box of (KC k x 256 rows) per part
           uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES;
           tma_load_2d(b_dst, &tmB_big, &full[s], kc * KC, j0);
@@ -387,12 +414,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, one elected lane issues; descriptors are precomputed, only `lo` moves =====
-    constexpr uint32_t idesc_full = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0);
-    constexpr uint32_t idesc_half = make_idesc(TILE_B, TILE_N / 2, 1, 0);
+    constexpr uint32_t idesc_full = make_idesc(TILE_B, TILE_N, /*A MN-major*/ 1, /*B K-major*/ 0, BF ? 1u : 2u);
+    constexpr uint32_t idesc_half = make_idesc(TILE_B, TILE_N / 2, 1, 0, BF ? 1u : 2u);
     // A (MN-major, 128B swizzle / 32B atoms): rows of 32 batch columns (128 B); one k-step = 8 rows = 2 atoms (SBO = 512 B
     // apart); batch groups of 32 are KC*128 B apart (LBO).  B (K-major): rows of KC floats; 8-row groups B_SBO apart;
     // a k-step advances 32 B inside the swizzled row.
-    constexpr uint32_t a_hi = desc_hi(A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
+    // (bf16: 64 batch columns per 128-byte row, plain 128B swizzle, atoms of 8 rows = 1024 B; one k-step = 16 rows = 2 atoms)
+    constexpr uint32_t a_hi = BF ? desc_hi(1024, LAYOUT_SW128) : desc_hi(A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
+    constexpr uint32_t A_KSTEP = MMA_K * 128;         // bytes between consecutive k-steps of the activation tile
     constexpr uint32_t b_hi = desc_hi(B_SBO, B_LAYOUT);
     const uint32_t st0 = smem_u32(smem);
     const uint32_t a_lo0 = desc_lo(st0, KC * 128);
@@ -414,8 +443,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           UMMA_TR(gs, trm, 4);
 #pragma unroll
-          for (int ks = 0; ks < KC / UMMA_K; ++ks) {
-            const uint64_t da_big = desc_at(a_hi, a_lo + ks * (1024 >> 4));
+          for (int ks = 0; ks < KC / MMA_K; ++ks) {
+            const uint64_t da_big = desc_at(a_hi, a_lo + ks * (A_KSTEP >> 4));
             const uint64_t db_big = desc_at(b_hi, b_lo + ks * (32 >> 4));
             const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
             if (NPASS == 3) {
@@ -423,7 +452,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_tf32(d_tmem, da_big, db_small, idesc, first);
               umma_tf32(d_tmem, da_big, db_big, idesc, 1u);
             } else {
-              umma_tf32(d_tmem, da_big, db_big, idesc, first);
+              umma_op<BF>(d_tmem, da_big, db_big, idesc, first);
             }
           }
         }
@@ -435,8 +464,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           if (NPASS == 3) {
 #pragma unroll
-            for (int ks = 0; ks < KC / UMMA_K; ++ks) {
-              const uint64_t da_small = desc_at(a_hi, a_lo + (Plan::A_BYTES >> 4) + ks * (1024 >> 4));
+            for (int ks = 0; ks < KC / MMA_K; ++ks) {
+              const uint64_t da_small = desc_at(a_hi, a_lo + (Plan::A_BYTES >> 4) + ks * (A_KSTEP >> 4));
               const uint64_t db_big = desc_at(b_hi, b_lo + ks * (32 >> 4));
               umma_tf32(d_tmem, da_small, db_big, idesc, 1u);
             }
@@ -638,6 +667,25 @@ inline int make_tmap_2d(CUtensorMap* out, const float* base, i64 rows, i64 cols,
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld pitch=%lld box=%dx%d", (int)r, rows, cols, pitch, box_cols,
               box_rows);
+    return DLADMM_ERR_CUDA;
+  }
+  return DLADMM_OK;
+}
+
+// 2D bf16 row-major matrix (rows x cols, pitch in ELEMENTS, a multiple of 8)
+inline int make_tmap_2d_bf16(CUtensorMap* out, const void* base, i64 rows, i64 cols, i64 pitch, int box_cols, int box_rows,
+                             CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DLADMM_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16) failed (%d) rows=%lld cols=%lld pitch=%lld box=%dx%d", (int)r, rows, cols, pitch,
+              box_cols, box_rows);
     return DLADMM_ERR_CUDA;
   }
   return DLADMM_OK;

@@ -31,9 +31,15 @@ struct UWorkspace {
   float *Wb, *Ws;      // nW x (d256 x mp): features of the W V product on the N side, K = m
   float *V;            // (m x B) operand V_k = L_{k-1} + beta1_k T_k of the next W V product
   float *objp;         // fused objective: [K][2][OBJ_ENTRIES] per-warp partial sums (Z part, E - T part)
+  float *metp;         // fused metrics: [K][DLADMM_MET_COUNT][OBJ_ENTRIES] per-warp partial sums
+  float *Atb, *Ats;    // A^T (d256 x mp), only for the dual-gap metric (DLADMM_MET_DGAP_ATL)
+  __nv_bfloat16 *Vh, *Zh;   // bf16 mode: the operands of the two products, (m x ldh) and 2 x (d x ldh) (Z_k alternates)
+  __nv_bfloat16 *Lh;        // bf16 mode + dual-gap metric: L_k as the operand of A^T L_k
+  i64 ldh;             // pitch of the bf16 operand copies (B rounded up to 8: TMA needs a 16-byte multiple)
   size_t bytes;
   int m256, d256, mp, dp, nW;
 };
+static inline bool wants_metric(const dladmm_problem* p, int i) { return p->metrics && ((p->metrics->want >> i) & 1u); }
 constexpr int OBJ_ENTRIES = 256 * umma::MAX_EPI_WARPS;   // upper bound of (grid x epilogue warps)
 
 static UWorkspace ucarve(const dladmm_problem* p, char* base) {
@@ -56,6 +62,15 @@ static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   w.Ws = take((size_t)w.nW * w.d256 * w.mp);
   w.V = take((size_t)p->m * p->B);
   w.objp = take(p->objective ? (size_t)p->K * 2 * OBJ_ENTRIES : 0);
+  w.metp = take((p->metrics && p->metrics->want) ? (size_t)p->K * DLADMM_MET_COUNT * OBJ_ENTRIES : 0);
+  const bool atl = wants_metric(p, DLADMM_MET_DGAP_ATL);
+  w.Atb = take(atl ? (size_t)w.d256 * w.mp : 0);
+  w.Ats = take(atl ? (size_t)w.d256 * w.mp : 0);
+  w.ldh = round_up64(p->B, 8);
+  const bool bf = p->precision == DLADMM_PREC_BF16;
+  w.Vh = (__nv_bfloat16*)take(bf ? (size_t)(p->m * w.ldh + 1) / 2 : 0);
+  w.Zh = (__nv_bfloat16*)take(bf ? (size_t)(2 * p->d * w.ldh + 1) / 2 : 0);
+  w.Lh = (__nv_bfloat16*)take(bf && atl ? (size_t)(p->m * w.ldh + 1) / 2 : 0);
   w.bytes = off;
   return w;
 }
@@ -115,35 +130,12 @@ static __global__ void __launch_bounds__(256) prep_split_kernel(SplitJobs jobs, 
       const float b = umma::tf32_rna(v);
       jb.big[(i64)r * Cpad + c] = b;
       jb.small[(i64)r * Cpad + c] = v - b;
+    } else if (NPASS == 2) {
+      reinterpret_cast<__nv_bfloat16*>(jb.big)[(i64)r * Cpad + c] = __float2bfloat16_rn(v);
     } else {
       jb.big[(i64)r * Cpad + c] = v;
     }
   }
-}
-
-template <int NPASS>
-static int uprepare_weights(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
-  {
-    SplitJobs jobs; jobs.n = 1;
-    jobs.j[0].src = p->A; jobs.j[0].big = w.Ab; jobs.j[0].small = w.As;
-    dim3 grid((w.dp + 31) / 32, (w.m256 + 31) / 32, 1);
-    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->m, p->d, w.m256, w.dp); }
-    DL_CUDA(cudaGetLastError());
-  }
-  std::vector<const float*> uniq = WeightMap(p).uniq;
-  for (size_t base = 0; base < uniq.size(); base += 32) {
-    SplitJobs jobs; jobs.n = (int)std::min<size_t>(32, uniq.size() - base);
-    for (int i = 0; i < jobs.n; ++i) {
-      size_t idx = base + i;
-      jobs.j[i].src = uniq[idx];
-      jobs.j[i].big = w.Wb + idx * (size_t)w.d256 * w.mp;
-      jobs.j[i].small = w.Ws + idx * (size_t)w.d256 * w.mp;
-    }
-    dim3 grid((w.mp + 31) / 32, (w.d256 + 31) / 32, jobs.n);
-    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->d, p->m, w.d256, w.mp); }
-    DL_CUDA(cudaGetLastError());
-  }
-  return DLADMM_OK;
 }
 
 // dst (Rpad x Cpad) = src^T, src is (C x R) dense; zero padded; tf32 split as above
@@ -168,10 +160,53 @@ static __global__ void __launch_bounds__(256) prep_split_t_kernel(SplitJobs jobs
       const float b = umma::tf32_rna(v);
       jb.big[(i64)r * Cpad + c] = b;
       jb.small[(i64)r * Cpad + c] = v - b;
+    } else if (NPASS == 2) {
+      reinterpret_cast<__nv_bfloat16*>(jb.big)[(i64)r * Cpad + c] = __float2bfloat16_rn(v);
     } else {
       jb.big[(i64)r * Cpad + c] = v;
     }
   }
+}
+
+// (rows x B) fp32 -> bf16 with pitch ldh: operands of the bf16 products that no epilogue of ours produced (Z0, T_init's V)
+static __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ src, int rows, i64 B, __nv_bfloat16* __restrict__ dst, i64 ldh) {
+  const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (i64)rows * B) return;
+  const i64 r = idx / B, c = idx % B;
+  dst[r * ldh + c] = __float2bfloat16_rn(src[idx]);
+}
+
+template <int NPASS>
+static int uprepare_weights(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st, bool with_At = false) {
+  if (with_At) {     // A^T (d256 x mp) for the dual-gap metric's A^T L_k product
+    SplitJobs jobs; jobs.n = 1;
+    jobs.j[0].src = p->A; jobs.j[0].big = w.Atb; jobs.j[0].small = w.Ats;
+    dim3 grid((w.mp + 31) / 32, (w.d256 + 31) / 32, 1);
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_t_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->d, p->m, w.d256, w.mp); }
+    DL_CUDA(cudaGetLastError());
+  }
+  {
+    SplitJobs jobs; jobs.n = 1;
+    jobs.j[0].src = p->A; jobs.j[0].big = w.Ab; jobs.j[0].small = w.As;
+    dim3 grid((w.dp + 31) / 32, (w.m256 + 31) / 32, 1);
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->m, p->d, w.m256, w.dp); }
+    DL_CUDA(cudaGetLastError());
+  }
+  std::vector<const float*> uniq = WeightMap(p).uniq;
+  for (size_t base = 0; base < uniq.size(); base += 32) {
+    SplitJobs jobs; jobs.n = (int)std::min<size_t>(32, uniq.size() - base);
+    for (int i = 0; i < jobs.n; ++i) {
+      size_t idx = base + i;
+      jobs.j[i].src = uniq[idx];
+      jobs.j[i].big = NPASS == 2 ? (float*)((__nv_bfloat16*)w.Wb + idx * (size_t)w.d256 * w.mp)      // bf16 array, element stride
+                                 : w.Wb + idx * (size_t)w.d256 * w.mp;
+      jobs.j[i].small = w.Ws + idx * (size_t)w.d256 * w.mp;
+    }
+    dim3 grid((w.mp + 31) / 32, (w.d256 + 31) / 32, jobs.n);
+    { LaunchScope ls(DLADMM_KIND_PREP, st); prep_split_kernel<NPASS><<<grid, 256, 0, st>>>(jobs, p->d, p->m, w.d256, w.mp); }
+    DL_CUDA(cudaGetLastError());
+  }
+  return DLADMM_OK;
 }
 
 // V_k = L_{k-1} + beta1_k * T_k (backward recomputation of the dW operand)
@@ -244,20 +279,29 @@ static int device_sm_count() {
 
 // C[j,b] = sum_k Wt[j,k] Act[k,b] with a fused epilogue.  act_* are (Kdim x B) batch-contiguous; w_* are prepared
 // (n_pad x k_pad) K-major arrays.
+// NPASS: 3 = 3xTF32, 1 = TF32, 2 = BF16 (act / w_big are then bf16 arrays; act has pitch `act_pitch` elements).
+template <int NPASS> struct KChunk { static constexpr int value = NPASS == 3 ? 16 : (NPASS == 2 ? 64 : 32); };
+
 template <class Epi, int NPASS>
-static int launch_umma(int kind, const float* act, int Kdim, const float* w_big, const float* w_small,
-                       int n_pad, int k_pad, int n_feat, i64 B, Epi epi, cudaStream_t st, int grid_override = 0) {
-  constexpr int KC = NPASS == 3 ? 16 : 32;
+static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, const void* w_small,
+                       int n_pad, int k_pad, int n_feat, i64 B, Epi epi, cudaStream_t st, int grid_override = 0, i64 act_pitch = 0) {
+  constexpr int KC = KChunk<NPASS>::value;
   using Plan = umma::SmemPlan<NPASS, KC>;
   CUtensorMap tA, tBb, tBs;
   int rc;
-  if ((rc = umma::make_tmap_2d(&tA, act, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-  const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if ((rc = umma::make_tmap_2d(&tBb, w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
-  if (NPASS == 3) {
-    if ((rc = umma::make_tmap_2d(&tBs, w_small, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
-  } else {
+  if (NPASS == 2) {
+    if ((rc = umma::make_tmap_2d_bf16(&tA, act, Kdim, B, act_pitch ? act_pitch : B, 64, KC, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = umma::make_tmap_2d_bf16(&tBb, w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     tBs = tBb;
+  } else {
+    if ((rc = umma::make_tmap_2d(&tA, (const float*)act, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    if ((rc = umma::make_tmap_2d(&tBb, (const float*)w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
+    if (NPASS == 3) {
+      if ((rc = umma::make_tmap_2d(&tBs, (const float*)w_small, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
+    } else {
+      tBs = tBb;
+    }
   }
   // epilogue inputs staged by TMA: one (CHUNK rows x 128 columns) box per present array
   umma::EMaps em;                          // per call, on the stack: the launch copies it into the kernel parameters

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLADMM_ABI_VERSION 4
+#define DLADMM_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define DLADMM_API __attribute__((visibility("default")))
@@ -57,8 +57,40 @@ typedef enum dladmm_family { DLADMM_FAMILY_A = 0, DLADMM_FAMILY_B = 1, DLADMM_FA
 typedef enum dladmm_precision {
   DLADMM_PREC_FP32 = 0,     /* CUDA-core FFMA, fp32 products and accumulation */
   DLADMM_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3 passes (big*big + big*small + small*big), fp32 accumulate in TMEM */
-  DLADMM_PREC_TF32 = 2      /* tcgen05 kind::tf32, single pass (stated-tolerance option) */
+  DLADMM_PREC_TF32 = 2,     /* tcgen05 kind::tf32, single pass (stated-tolerance option: ~1e-3 relative per product) */
+  DLADMM_PREC_BF16 = 3      /* tcgen05 kind::f16 on bf16 operands, single pass, fp32 accumulate (stated-tolerance option:
+                               ~4e-3 relative per product).  Iterates stay fp32 in HBM (the reference's API); operands are
+                               rounded to bf16 in shared memory by the consumer, weights once per call. */
 } dladmm_precision;
+
+/* Per-layer metrics accumulated inside the product epilogues (ABI v5): out[k * DLADMM_MET_COUNT + i] = sum over the
+ * batch (and over the rows of the array named) for layer k.  What the reference's drivers compute script-side:
+ *   training objectives  main_syn_l1l1_scalar.py:289-299 (L1_Z, L1_RES), main_syn_lasso_scalar.py:276-281 (L1_Z, SQ_RES),
+ *                        main_lena.py:221-228 (L1_Z, L1_E, DGAP_ATL, DGAP_L, DOT_LX)
+ *   evaluation metrics   test_syn_l1l1_scalar.py:486-546 (NMSE: SQERR_Z, SQERR_E), main_lena.py:262-267 (PSNR: SQERR_AZ) */
+typedef enum dladmm_metric {
+  DLADMM_MET_L1_Z = 0,      /* sum |Z_k|                                                        */
+  DLADMM_MET_SQERR_Z = 1,   /* sum (Z_label - Z_k)^2     needs Z_label                          */
+  DLADMM_MET_L1_RES = 2,    /* sum |X - A Z_k|           (taken as |E_k - T_{k+1}|)              */
+  DLADMM_MET_SQ_RES = 3,    /* sum (X - A Z_k)^2                                                */
+  DLADMM_MET_SQERR_E = 4,   /* sum (E_label - E_k)^2     needs E_label                          */
+  DLADMM_MET_SQERR_AZ = 5,  /* sum (X_clean - A Z_k)^2   needs X_clean; A Z_k is the accumulator */
+  DLADMM_MET_L1_E = 6,      /* sum |E_k|                                                        */
+  DLADMM_MET_DOT_LX = 7,    /* sum L_k * X                                                      */
+  DLADMM_MET_DGAP_L = 8,    /* sum softplus(L_k - 1) + softplus(-L_k - 1)                       */
+  DLADMM_MET_DGAP_ATL = 9,  /* sum softplus(A^T L_k - a) + softplus(-A^T L_k - a), a = dual_alpha: one extra (d x m)(m x B)
+                               product per layer, computed only when `want` has this bit (tensor-core precisions only) */
+  DLADMM_MET_COUNT = 10
+} dladmm_metric;
+
+typedef struct dladmm_metrics {
+  uint32_t want;            /* bit i set: metric i is needed (others may be left unspecified in `out`) */
+  float dual_alpha;
+  const float* Z_label;     /* (d,B) or NULL */
+  const float* E_label;     /* (m,B) or NULL */
+  const float* X_clean;     /* (m,B) or NULL */
+  float* out;               /* device, K * DLADMM_MET_COUNT floats, overwritten by the forward (`objective` must be NULL) */
+} dladmm_metrics;
 
 /* A learnable parameter broadcast against a (rows x B) activation.
  *   value(row, col) = ptr[row * row_stride + (col_period ? col % col_period : 0)]
@@ -91,7 +123,7 @@ typedef struct dladmm_problem {
   int32_t abi_version;    /* DLADMM_ABI_VERSION */
   int32_t family;         /* dladmm_family */
   int32_t precision;      /* dladmm_precision */
-  int32_t m, d, K;        /* A is (m,d); K unrolled layers */
+  int32_t m, d, K;        /* A is (m,d); K unrolled layers.  K = 0 (ABI v5): only T[0] = A Z0 + E0 - X is computed */
   int64_t B;              /* columns (problem instances) in this call; every (rows x B) array has pitch B */
   int32_t last_only;      /* 0: Z/E/L hold K slabs and T holds K+1 (reference API, a10);
                              1: inference only, slabs are reused modulo 2 (Z/E/L: 2 slabs, T: 2 slabs);
@@ -125,7 +157,14 @@ typedef struct dladmm_problem {
                              Z_k and E_k - T_{k+1} -- the iterates are not read again.  Works with last_only = 1 too
                              (tensor-core precisions). */
   float objective_alpha;
-  int32_t reserved2;
+  int32_t objective_kind; /* ABI v5: 0/1: L1 residual as above; 2: 0.5*||X - A Z_k||_2^2 in place of the L1 residual
+                             (the LASSO objective, main_syn_lasso_scalar.py:276-281) */
+  /* ABI v5: half-layer entry points (the E -> L -> Z ordering of main_syn_scalar_newS_layerwise.py:82-112 and its
+   * safeguard, test_syn_l1l1_newS_Acols.py:136-277, advance "E/L-step of layer k-1, then Z-step of layer k"). */
+  int32_t start_half;     /* 1: layer 0 has no Z-step: Z_0 := Z0 as given (Z slab 0 is not written, Z0 is read in its place);
+                             the call starts with the E/T/L-step of layer 0.  T_init and T[0] are unused. */
+  int32_t stop_half;      /* 1: the E/T/L-step of the last layer is not executed (E, L slab K-1 and T slab K are not written) */
+  const dladmm_metrics* metrics;   /* optional (HOST struct), forward only */
 } dladmm_problem;
 
 /* Upstream cotangents for backward; each may be NULL (= zero).  Shapes as the forward outputs. */
@@ -138,7 +177,8 @@ typedef struct dladmm_cotangents {
    *   loss = scale0 * sum_k w_k * sum_b ( alpha*||Z_k[:,b]||_1 + ||X[:,b] - A Z_k[:,b]||_1 )
    * i.e. the per-layer L1-L1 objective of main_syn_l1l1_scalar.py:289-299 with X - A Z_k taken as E_k - T_{k+1}.
    * loss_scale points to ONE device float = d(final loss)/d(loss) * scale0 (e.g. upstream gradient / B). */
-  int32_t loss_kind;                /* 0: none, 1: L1-L1 objective */
+  int32_t loss_kind;                /* 0: none, 1: L1-L1 objective, 2 (ABI v5): LASSO objective, the residual term being
+                                       0.5*||X - A Z_k[:,b]||_2^2 (main_syn_lasso_scalar.py:276-281) */
   float loss_alpha;
   const float* loss_layer_weight;   /* HOST array of K floats w_k */
   const float* loss_scale;          /* DEVICE pointer to one float */
@@ -203,6 +243,20 @@ DLADMM_API int dladmm_sg_norm(int32_t m, int64_t B, float beta, float c, const f
 DLADMM_API int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, const float* mu,
                                 float one_minus_delta, float* keep, void* stream);
 
+/* Safeguard of the E -> L -> Z ordering (Snorm_ELZ, test_syn_l1l1_newS_Acols.py:174-192) without the d x d matrix
+ * P2 = I/(beta ss1) - A^T A:  out[b] = sqrt( ||Tnn[:,b]||^2 + inv_beta_ss1 * ||Znn[:,b] - Zn[:,b]||^2 - ||Tnn[:,b] - Tn[:,b]||^2 )
+ * with Tn = A Zn + En - X and Tnn = A Znn + En - X (so Tnn - Tn = A (Znn - Zn)).  Tn, Tnn are (m,B); Zn, Znn (d,B). */
+DLADMM_API int dladmm_sg_norm_elz(int32_t m, int32_t d, int64_t B, float inv_beta_ss1, const float* Tnn, const float* Tn,
+                                  const float* Znn, const float* Zn, float* out, void* stream);
+
+/* mu_k updaters of mu_updater.py:18-72 fused with the selection: as dladmm_sg_select, then per column
+ *   method 1 (EMA): upd = param*snorm + (1-param)*mu;  2 (GS): upd = (1-param)*mu;  3 (RT): upd = snorm;
+ *   mu[b] = keep[b] ? upd : mu[b]   (in place; method 0 leaves mu alone), and *fallbacks (one device float, accumulated)
+ *   += number of columns with keep == 0.  One launch for keep + mu + count, one for the copies. */
+DLADMM_API int dladmm_sg_select_update(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, float* mu,
+                                       float one_minus_delta, int32_t method, float param, float* keep, float* fallbacks,
+                                       void* stream);
+
 DLADMM_API int dladmm_query(int device, dladmm_caps* caps);
 
 /* Measurement hooks (bench.py).  Kernel kinds for the per-kind timers: */
@@ -218,7 +272,10 @@ typedef enum dladmm_kernel_kind {
   DLADMM_KIND_BWD_REDUCE = 8,  /* second stage of parameter-gradient reductions */
   DLADMM_KIND_GEN = 9,         /* synthetic data generator */
   DLADMM_KIND_OBJECTIVE = 10,
-  DLADMM_KIND_COUNT = 11
+  DLADMM_KIND_METRIC_GEMM = 11, /* A^T L_k product of the dual-gap metric */
+  DLADMM_KIND_SAFEGUARD = 12,   /* safeguard norms / selection */
+  DLADMM_KIND_FWD_PERSISTENT = 13, /* all-layer persistent forward kernel */
+  DLADMM_KIND_COUNT = 14
 } dladmm_kernel_kind;
 
 /* Total kernels this library has launched in this process (monotonic). */

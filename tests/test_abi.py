@@ -43,7 +43,7 @@ def _struct_fields(name):
 @pytest.mark.parametrize("cname,cls", [("dladmm_bparam", _lib.BParam), ("dladmm_layer", _lib.Layer),
                                        ("dladmm_problem", _lib.Problem), ("dladmm_cotangents", _lib.Cotangents),
                                        ("dladmm_caps", _lib.Caps), ("dladmm_gen_desc", _lib.GenDesc),
-                                       ("dladmm_sg_pair", _lib.SgPair)])
+                                       ("dladmm_sg_pair", _lib.SgPair), ("dladmm_metrics", _lib.Metrics)])
 def test_ctypes_structs_mirror_header(cname, cls):
     assert _struct_fields(cname) == [f[0] for f in cls._fields_]
 
@@ -79,7 +79,7 @@ def test_ctypes_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
         pytest.skip("gcc not available")
     structs = [("dladmm_bparam", _lib.BParam), ("dladmm_layer", _lib.Layer), ("dladmm_problem", _lib.Problem),
                ("dladmm_cotangents", _lib.Cotangents), ("dladmm_caps", _lib.Caps), ("dladmm_gen_desc", _lib.GenDesc),
-               ("dladmm_sg_pair", _lib.SgPair)]
+               ("dladmm_sg_pair", _lib.SgPair), ("dladmm_metrics", _lib.Metrics)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dladmm.h"', "int main(void) {",
              '  printf("abi %d\\n", DLADMM_ABI_VERSION);']
     for cname, cls in structs:
