@@ -120,8 +120,8 @@ def _dist_env():
 # CPU arm: the reference's algorithm on host cores (oracle port of the reference's ATen op sequence)
 # ---------------------------------------------------------------------------------------------------
 def cpu_forward_rate(sample_cols, reps, seed=1126):
+    """-> (seconds per timed forward, threads, kind): the reference's DLADMMNet (or the oracle port, see _RefModel) on the host cores"""
     import torch
-    import dladmm_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(M, D, generator=g)
@@ -131,16 +131,15 @@ def cpu_forward_rate(sample_cols, reps, seed=1126):
     X = A.mm(Zs) + Es
     Z0 = torch.rand(D, sample_cols, generator=g) / D
     E0 = torch.zeros(M, sample_cols); L0 = torch.zeros(M, sample_cols)
-    sd = orc.default_state_dict(VARIANT, A, K_LAYERS, sample_cols, generator=g)
+    rm = _RefModel(VARIANT, M, D, K_LAYERS, sample_cols, A, Z0, E0, L0, "cpu", seed)
     times = []
     with torch.no_grad():
-        orc.forward(VARIANT, sd, A, X[:, :512].contiguous(), Z0[:, :512].contiguous(), E0[:, :512].contiguous(),
-                    L0[:, :512].contiguous(), K_LAYERS)                    # warm-up
+        rm.forward(X)                                                      # warm-up
         for _ in range(reps):
             t0 = time.perf_counter()
-            orc.forward(VARIANT, sd, A, X, Z0, E0, L0, K_LAYERS)
+            rm.forward(X)
             times.append(time.perf_counter() - t0)
-    return times, torch.get_num_threads()
+    return times, torch.get_num_threads(), rm.kind
 
 
 def run_reference(args):
@@ -148,7 +147,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     sample = CPU_SAMPLE_COLS
-    times, threads = cpu_forward_rate(sample, args.warmup + args.steps)
+    times, threads, kind = cpu_forward_rate(sample, args.warmup + args.steps)
     timed = times[args.warmup:]
     total = sum(timed)
     value = sample * len(timed) / total
@@ -158,13 +157,163 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C1 scalar D-LADMM forward, m=250 d=500 K=15, all iterates returned",
                    "columns_per_step": sample, "variant": VARIANT},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": "%d-column forward per step (full workload is %d columns per GPU)" % (sample, B_PER_GPU)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def _reference_kind():
+    """"reference" when the literal reference classes can be loaded here (/root/reference in the build container, the files
+    oracle/fetch_ref.py staged under oracle/_ref/ on the GPU box), else "port" (oracle/dladmm_oracle.py, the same ATen ops)."""
+    try:
+        import load_reference as lr
+        return "reference" if lr.reference_available() else "port"
+    except Exception:
+        return "port"
+
+
+class _RefModel(object):
+    """The reference's DLADMMNet for `variant` on `device` ("cpu": .cuda() patched to identity; "cuda": unmodified, stock
+    PyTorch eager on the B200), or the oracle port of the same op sequence when the class cannot be loaded."""
+
+    def __init__(self, variant, m, d, K, B, A, Z0, E0, L0, device, seed=1126):
+        import torch
+        import dladmm_oracle as orc
+        self.variant, self.K, self.kind, self.device = variant, K, _reference_kind(), device
+        self.A = A.to(device)
+        torch.manual_seed(seed)
+        if self.kind == "reference":
+            import load_reference as lr
+            cls = lr.load_class(variant)
+            args = dict(m=m, n=10000, d=d, batch_size=B, A=A.cpu(), Z0=Z0.cpu(), E0=E0.cpu(), L0=L0.cpu(), layers=K)
+            if device == "cpu":
+                with lr.cuda_is_identity():
+                    self.model = cls(**args)
+            else:
+                self.model = cls(**args).cuda()
+            self.lr = lr
+        else:
+            self.sd = {k: v.to(device).requires_grad_(True) for k, v in orc.default_state_dict(variant, A.cpu(), K, B).items()}
+            self.state = [t.to(device) for t in (Z0, E0, L0)]
+            self.orc = orc
+
+    def forward(self, x):
+        if self.kind == "reference":
+            if self.device == "cpu":
+                with self.lr.cuda_is_identity():
+                    return self.model(x)
+            return self.model(x)
+        return self.orc.forward(self.variant, self.sd, self.A, x, self.state[0], self.state[1], self.state[2], self.K)
+
+    def params(self):
+        return list(self.model.parameters()) if self.kind == "reference" else list(self.sd.values())
+
+    def train_step(self, x, alpha=0.001):
+        """forward + the script's training loss + backward (main_syn_l1l1_scalar.py:283-301 / main_syn_lasso_scalar.py:268-285)"""
+        import torch
+        for p in self.params():
+            p.grad = None
+        out = self.forward(x)
+        Z = out[0]
+        total = 0.0
+        for k in range(self.K):
+            res = x - torch.mm(self.A, Z[k])
+            r = 0.5 * torch.sum(res ** 2.0, dim=0).mean() if self.variant == "lasso" else torch.sum(torch.abs(res), dim=0).mean()
+            total = total + (alpha * torch.sum(torch.abs(Z[k]), dim=0).mean() + r) * (0.6 ** 3 if k < self.K - 1 else 1.0)
+        total.backward()
+        return total
+
+
+def eager_b200_leg(dev, A, X, budget_s=25.0):
+    """The reference's own classes under stock PyTorch eager ON THE B200 ("the real bar to beat"): forward under
+    no_grad and forward + script loss + backward, wall clock per call with a synchronize on both sides, median of 3."""
+    import torch
+    out = {"kind": _reference_kind(), "what": "unmodified reference DLADMMNet, PyTorch %s eager on the same GPU, fp32 (TF32 off), "
+                                              "wall clock per call incl. host launch overhead" % torch.__version__, "cases": []}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t_leg = time.time()
+    cases = [("scalar", 15, 25, True), ("scalar", 15, 4096, True), ("scalar", 15, 65536, True), ("full", 20, 20, True),
+             ("full", 20, 4096, True), ("lasso", 15, 20, True), ("lasso", 15, 4096, True)]
+    for variant, K, B, with_bwd in cases:
+        if time.time() - t_leg > budget_s:
+            break
+        g = torch.Generator().manual_seed(5)
+        Z0 = torch.rand(D, B, generator=g) / D
+        E0 = torch.zeros(M, B); L0 = torch.zeros(M, B)
+        rm = _RefModel(variant, M, D, K, B, A.cpu(), Z0, E0, L0, "cuda")
+        x = X[:, :B].contiguous()
+
+        def timed(fn, n=3):
+            ts = []
+            for i in range(n + 1):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize(dev)
+                ts.append(time.perf_counter() - t0)
+            ts = sorted(ts[1:])
+            return ts[len(ts) // 2]
+
+        def fwd():
+            with torch.no_grad():
+                return rm.forward(x)
+        row = {"variant": variant, "K": K, "columns": B, "fwd_ms": 1e3 * timed(fwd)}
+        row["fwd_instances_per_s"] = B / (row["fwd_ms"] * 1e-3)
+        if with_bwd and B <= 65536:
+            row["train_ms"] = 1e3 * timed(lambda: rm.train_step(x))
+            row["train_samples_per_s"] = B / (row["train_ms"] * 1e-3)
+        out["cases"].append(row)
+        del rm
+        torch.cuda.empty_cache()
+    return out
+
+
+def small_batch_leg(dl, dev, A, X, precision):
+    """The reference scripts' own regime (bs 20-25) and up: wall clock of one K=15 forward call (host enqueue + device),
+    median of 20 after warm-up."""
+    import torch
+    rows = []
+    for B in (25, 256, 1024, 4096):
+        z = lambda r: torch.zeros(r, B, device=dev)
+        mdl = dl.VARIANT_CLASSES[VARIANT](M, 10000, D, B, A, torch.rand(D, B, device=dev) / D, z(M), z(M), K_LAYERS,
+                                          precision=precision, device=dev)
+        x = X[:, :B].contiguous()
+        ts = []
+        with torch.no_grad():
+            for i in range(25):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                mdl(x)
+                torch.cuda.synchronize(dev)
+                ts.append(time.perf_counter() - t0)
+        ts = sorted(ts[5:])
+        rows.append({"columns": B, "fwd_ms": 1e3 * ts[len(ts) // 2], "fwd_instances_per_s": B / ts[len(ts) // 2]})
+    return {"what": "one DLADMMNet.forward(x) call, scalar K=15 m=250 d=500, wall clock incl. host enqueue", "cases": rows}
+
+
+def safeguard_leg(dl, dev, A, X, precision, B=4096, K=20):
+    """Safeguarded evaluation (test_syn_l1l1_scalar.py:179-317): classical + learned + safeguard step per layer, EMA updater."""
+    import torch
+    z = lambda r: torch.zeros(r, B, device=dev)
+    torch.manual_seed(3)
+    mdl = dl.VARIANT_CLASSES["scalar"](M, 10000, D, B, A, z(D), z(M), z(M), K, precision=precision, device=dev)
+    x = X[:, :B].contiguous()
+    kw = dict(delta=0.0, mu_k_method="EMA", mu_k_param=0.5, alpha=0.01)
+    mdl.forward_safeguarded(x, True, True, **kw)
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = mdl.forward_safeguarded(x, True, True, **kw)
+        torch.cuda.synchronize(dev)
+        ts.append(time.perf_counter() - t0)
+    t = sorted(ts)[1]
+    return {"what": "DLADMMNet.forward_safeguarded(x, use_learned, use_safeguard), scalar K=%d, %d columns, EMA mu updater" % (K, B),
+            "ms": 1e3 * t, "value": B / t, "unit": UNIT, "fallback_columns_per_layer": out[4]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -276,44 +425,109 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    # ---- optional training throughput (forward + backward + parameter gradients) ----------------------
-    train = None
-    if args.train_columns > 0:
-        Bt = args.train_columns
-        tm = dl.VARIANT_CLASSES[VARIANT](M, 10000, D, Bt, A_host, Z0[:, :Bt].contiguous(), E0[:, :Bt].contiguous(),
-                                         L0[:, :Bt].contiguous(), K_LAYERS, precision=precision, device=dev)
+    # ---- training throughput (forward + fused loss + backward + parameter gradients) ---------------------------------
+    #   scalar K=15 (C1/C3 shape), full K=20 (BASELINE configs[1]), lasso K=15 (configs[2])
+    def train_leg(variant, Kt, Bt, nst):
+        tm = dl.VARIANT_CLASSES[variant](M, 10000, D, Bt, A_host, Z0[:, :Bt].contiguous(), E0[:, :Bt].contiguous(),
+                                         L0[:, :Bt].contiguous(), Kt, precision=precision, device=dev)
         Xt = X[:, :Bt].contiguous()
         if world > 1:
             tm.sync_gradients(True)
-
-        wts = [0.6 ** 3] * (K_LAYERS - 1) + [1.0]
+        wts = [0.6 ** 3] * (Kt - 1) + [1.0]
+        loss_fn = tm.lasso_loss if variant == "lasso" else tm.l1l1_loss     # main_syn_lasso_scalar.py:276-281 / main_syn_l1l1_scalar.py:289-299
 
         def step_train():
             tm.zero_grad(set_to_none=True)
-            loss, _ = tm.l1l1_loss(Xt, 0.001, wts)       # main_syn_l1l1_scalar.py:289-299, fused
+            loss, _ = loss_fn(Xt, 0.001, wts)
             loss.backward()                              # world > 1: the backward allreduces the gradient buffer in place
         for _ in range(2):
             step_train()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nst = max(2, args.steps // 2)
         t0.record()
         for _ in range(nst):
             step_train()
         t1.record()
         barrier()
-        ms_train = t0.elapsed_time(t1)
+        ms = t0.elapsed_time(t1) / nst
         _lib.profile_start()
         step_train()
         tprof = _lib.profile_stop()
-        train = {"columns_per_gpu": Bt, "ms_per_step": ms_train / nst,
-                 "kernel_ms_per_step": {k: v[0] for k, v in tprof.items() if v[1] > 0}}
+        if world > 1:     # every rank must hold the same (globally summed) gradients after the in-backward allreduce
+            chk = torch.stack([p.grad.double().sum() for p in tm.parameters()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi), "parameter gradients differ between ranks after sync_gradients"
+        return {"variant": variant, "K": Kt, "columns_per_gpu": Bt, "ms_per_step": ms,
+                "kernel_ms": {k: v[0] for k, v in tprof.items() if v[1] > 0},
+                "kernel_launches": {k: v[1] for k, v in tprof.items() if v[1] > 0}}
+
+    trains = []
+    if args.train_columns > 0:
+        nst = max(2, args.steps // 2)
+        trains.append(train_leg(VARIANT, K_LAYERS, args.train_columns, nst))
+        if not args.quick:
+            trains.append(train_leg("full", 20, args.train_columns, 2))
+            trains.append(train_leg("lasso", 15, args.train_columns, 2))
+        torch.cuda.empty_cache()
+    train = trains[0] if trains else None
+
+    # ---- other precision modes and API shapes of the C1 forward (3 steps each) ----------------------------------------
+    variants_ms = {}
+    if not args.quick:
+        for label, prec, kw in (("tf32", "tf32", {}), ("bf16", "bf16", {}), (precision + "_last_only", precision, {"last_only": True})):
+            mm = dl.VARIANT_CLASSES[VARIANT](M, 10000, D, B, A_host, Z0, E0, L0, K_LAYERS, precision=prec, device=dev)
+            mm.load_state_dict(model.state_dict())
+
+            def stepv():
+                with torch.no_grad():
+                    return mm(X, **kw)
+            for _ in range(2):
+                stepv()
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(3):
+                stepv()
+            t1.record()
+            barrier()
+            variants_ms[label] = t0.elapsed_time(t1) / 3
+            del mm
+        torch.cuda.empty_cache()
+
+    # ---- end to end with the FINAL iterate brought back to the host (what an inference caller wants) -------------------
+    e2e_z = None
+    if not args.quick:
+        z_host = [torch.empty((D, B), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+        def run_e2e_z(nsteps):
+            feed = dl.HostFeed((X_host for _ in range(nsteps)), dev)
+            done = [None, None]
+            for i, x_dev in enumerate(feed):
+                with torch.no_grad():
+                    Zl = model(x_dev, last_only=True)[0]
+                if done[i & 1] is not None:
+                    done[i & 1].synchronize()                 # the pinned buffer of step i-2 has been read
+                z_host[i & 1].copy_(Zl[0], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(); done[i & 1] = ev
+            for ev in done:
+                if ev is not None:
+                    ev.synchronize()
+            return feed.bytes_copied
+        run_e2e_z(2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hb = run_e2e_z(args.steps)
+        e1.record()
+        barrier()
+        e2e_z = {"ms_per_step": e0.elapsed_time(e1) / args.steps, "h2d_bytes_per_step": int(hb // args.steps),
+                 "d2h_bytes_per_step": int(4 * D * B)}
+        del z_host
 
     # ---- optional: the large-scale shape (BASELINE configs[4] "C5": A 1000x2000, K=40), tensor-bound regime ---------
     c5 = None
     if args.c5_columns > 0:
-        if args.train_columns > 0:
-            del tm, Xt
         torch.cuda.empty_cache()
         m5, d5, K5, B5 = 1000, 2000, 40, args.c5_columns
         data5 = dl.gen_syn_data(B5, m=m5, d=d5, p=0.1, sigma=1.0, seed=1126, device=dev, col_offset=rank * B5)
@@ -337,15 +551,78 @@ def run_ours(args):
             t1.record()
             barrier()
             c5[label] = t0.elapsed_time(t1) / n5
+        # BASELINE configs[4] at its stated size: 1 048 576 instances in total, sharded over the ranks (STRONG scaling), each
+        # rank walking its share in chunks of up to 131 072 columns; final iterate + fused per-layer objective (last_only)
+        if args.c5_total > 0:
+            share = args.c5_total // world
+            chunk = min(131072, share)
+            nchunk = (share + chunk - 1) // chunk
+            datac = dl.gen_syn_data(chunk, m=m5, d=d5, p=0.1, sigma=1.0, seed=1126, device=dev, col_offset=rank * share)
+            zc = lambda r: torch.zeros(r, chunk, device=dev)
+            torch.manual_seed(1126)
+            modelc = dl.VARIANT_CLASSES[VARIANT](m5, 10000, d5, chunk, data5.A, torch.rand(d5, chunk, device=dev) / d5, zc(m5), zc(m5), K5,
+                                                 precision=precision, device=dev)
+            modelc.load_state_dict(model5.state_dict())
+            objs = torch.zeros(K5, device=dev, dtype=torch.float64)
+
+            def pass_1m():
+                for _ in range(nchunk):       # (synthetic: every chunk of a rank reuses the same generated columns)
+                    obj, _o = modelc.forward_objective(datac.X, 0.001, last_only=True)
+                    objs.add_(obj.double())
+            pass_1m() if nchunk <= 2 else modelc.forward_objective(datac.X, 0.001, last_only=True)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            pass_1m()
+            t1.record()
+            barrier()
+            c5["total_1m_ms"] = t0.elapsed_time(t1)
+            c5["total_1m_chunks"] = nchunk
+            c5["total_1m_chunk_columns"] = chunk
+            del modelc, datac
+        # training at the C5 shape (320 MB of weight gradients per step: the case where the allreduce matters)
+        if args.c5_train_columns > 0:
+            Bt5 = args.c5_train_columns
+            torch.cuda.empty_cache()
+            zt = lambda r: torch.zeros(r, Bt5, device=dev)
+            tm5 = dl.VARIANT_CLASSES[VARIANT](m5, 10000, d5, Bt5, data5.A, torch.rand(d5, Bt5, device=dev) / d5, zt(m5), zt(m5), K5,
+                                              precision=precision, device=dev)
+            if world > 1:
+                tm5.sync_gradients(True)
+            Xt5 = data5.X[:, :Bt5].contiguous()
+
+            def step5t():
+                tm5.zero_grad(set_to_none=True)
+                loss, _ = tm5.l1l1_loss(Xt5, 0.001)
+                loss.backward()
+            step5t()
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(2):
+                step5t()
+            t1.record()
+            barrier()
+            c5["train_ms"] = t0.elapsed_time(t1) / 2
+            c5["train_columns"] = Bt5
+            del tm5, Xt5
         del model5, data5
         torch.cuda.empty_cache()
 
     # ---- max over ranks -------------------------------------------------------------------------------
+    extra_keys = [("train%d" % i, t["ms_per_step"]) for i, t in enumerate(trains)] + sorted(variants_ms.items())
+    if e2e_z:
+        extra_keys.append(("e2e_z", e2e_z["ms_per_step"]))
+    if c5:
+        extra_keys += [(k, c5[k]) for k in ("total_1m_ms", "train_ms") if k in c5]
     stats = torch.tensor([ms_total, ms_e2e, train["ms_per_step"] if train else 0.0,
-                          c5["all_iterates"] if c5 else 0.0, c5["last_only"] if c5 else 0.0], device=dev, dtype=torch.float64)
+                          c5["all_iterates"] if c5 else 0.0, c5["last_only"] if c5 else 0.0] + [v for _, v in extra_keys],
+                         device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_train_step, ms_c5_all, ms_c5_last = [float(v) for v in stats.tolist()]
+    vals = [float(v) for v in stats.tolist()]
+    ms_total, ms_e2e, ms_train_step, ms_c5_all, ms_c5_last = vals[:5]
+    extra = {k: v for (k, _), v in zip(extra_keys, vals[5:])}
 
     if rank == 0:
         peaks = _peaks()
@@ -358,7 +635,7 @@ def run_ours(args):
         dom_ms, dom_n = kinds[dom]
         gemm_kinds = ("gemm_t0", "gemm_z", "gemm_elt")
         flops_per_launch = F_GEMM_PER_COL * B
-        mma_passes = {"fp32": 1, "tf32": 1, "tf32x3": 3}[precision]
+        mma_passes = {"fp32": 1, "tf32": 1, "tf32x3": 3, "bf16": 1}[precision]
         # algorithmic HBM bytes per launch of each fused product kernel: the activation
         # operand + the epilogue inputs read + the outputs written (weights are L2-resident, 3xTF32 splits never
         # leave shared memory, prox masks are not written in inference)
@@ -396,7 +673,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "tf32": "tf32"}[precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[precision], "data": "synthetic",
             "config": {"workload": "C1 scalar D-LADMM forward (main_syn_l1l1_scalar.py), m=250 d=500 K=15, "
                                    "%d instances per GPU, all K iterates of Z,E,L,T returned (reference API)" % B,
                        "variant": VARIANT, "precision": precision, "columns_per_gpu": B,
@@ -414,15 +691,41 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if train:
-            line["train"] = {"metric": "dladmm_train_samples_per_sec", "value": world * train["columns_per_gpu"] / (ms_train_step * 1e-3),
-                             "unit": "samples/s", "columns_per_gpu": train["columns_per_gpu"], "ms_per_step": ms_train_step,
-                             "library_kernel_ms_per_step": train["kernel_ms_per_step"],
-                             "what": "DLADMMNet.l1l1_loss(x).backward(): forward + fused L1-L1 objective + backward + parameter gradients%s, scalar K=15" % (" + NCCL allreduce" if world > 1 else "")}
+        tp = peaks["tf32_tflops"] / mma_passes
+
+        def train_block(t, ms):
+            Kt, Bt = t["K"], t["columns_per_gpu"]
+            f_train = 2.0 * M * D * (5 * Kt + 1)                          # F_fwd + F_bwd per sample
+            per_launch = {}
+            for kind in ("gemm_z", "gemm_elt", "bwd_gemm_dz", "bwd_gemm_dw", "bwd_gemm_dv"):
+                if kind in t["kernel_ms"]:
+                    avg = t["kernel_ms"][kind] / t["kernel_launches"][kind]
+                    per_launch[kind] = {"avg_launch_ms": avg, "tflops": F_GEMM_PER_COL * Bt / (avg * 1e-3) / 1e12,
+                                        "frac_of_tensor_peak": F_GEMM_PER_COL * Bt / (avg * 1e-3) / 1e12 / tp}
+            dom_t = max(per_launch, key=lambda k: t["kernel_ms"][k]) if per_launch else None
+            ach = Bt * f_train / (ms * 1e-3) / 1e12
+            return {"metric": "dladmm_train_samples_per_sec", "variant": t["variant"], "K": Kt,
+                    "value": world * Bt / (ms * 1e-3), "unit": "samples/s", "columns_per_gpu": Bt, "ms_per_step": ms,
+                    "library_kernel_ms_per_step": t["kernel_ms"],
+                    "roofline": {"bound": "tensor", "achieved": ach, "peak": tp, "unit": "TFLOP/s", "frac": ach / tp,
+                                 "algorithmic_flops_per_sample": f_train, "dominant_kernel": dom_t, "per_kernel": per_launch,
+                                 "what": "whole training step per GPU against the %s tensor peak; per_kernel = one launch of each product kernel" % precision},
+                    "what": "DLADMMNet.%s(x).backward(): forward + fused objective + backward + parameter gradients%s"
+                            % ("lasso_loss" if t["variant"] == "lasso" else "l1l1_loss", " + in-backward NCCL allreduce (rank-equality asserted)" if world > 1 else "")}
+        if trains:
+            line["train"] = train_block(trains[0], ms_train_step)
+            for i, t in enumerate(trains[1:], 1):
+                line["train_" + t["variant"]] = train_block(t, extra["train%d" % i])
+        if variants_ms:
+            line["c1_forward_other_modes"] = {k: {"ms_per_step": extra[k], "value": world * B / (extra[k] * 1e-3)} for k in variants_ms}
+            line["c1_forward_other_modes"]["what"] = ("the same C1 forward with single-pass TF32 / bf16 operands (stated-tolerance modes, all "
+                                                      "iterates returned) and with last_only=True in the headline precision")
+        if e2e_z:
+            line["e2e_final_z"] = dict(e2e_z, ms_per_step=extra["e2e_z"], value=world * B / (extra["e2e_z"] * 1e-3), unit=UNIT,
+                                       api="HostFeed -> DLADMMNet.forward(x, last_only=True) -> final Z copied to pinned host memory every step")
         if c5:
             f5 = 2.0 * 1000 * 2000 * (2 * 40 + 1)                  # algorithmic flops per instance (324 MFLOP)
             B5 = c5["columns_per_gpu"]
-            tp = peaks["tf32_tflops"] / mma_passes
             line["c5"] = {
                 "workload": "large-scale shape of BASELINE configs[4]: scalar D-LADMM forward, m=1000 d=2000 K=40, %d instances per GPU" % B5,
                 "unit": UNIT, "tensor_peak_tflops": tp,
@@ -432,11 +735,34 @@ def run_ours(args):
                 "last_only": {"ms_per_step": ms_c5_last, "value": world * B5 / (ms_c5_last * 1e-3),
                               "algorithmic_tflops_per_gpu": B5 * f5 / (ms_c5_last * 1e-3) / 1e12,
                               "frac_of_tensor_peak": B5 * f5 / (ms_c5_last * 1e-3) / 1e12 / tp},
+                "roofline": {"bound": "tensor", "achieved": B5 * f5 / (ms_c5_all * 1e-3) / 1e12, "peak": tp, "unit": "TFLOP/s",
+                             "frac": B5 * f5 / (ms_c5_all * 1e-3) / 1e12 / tp,
+                             "hbm_gbs_all_iterates": 4.0 * (40 * (2000 + 3 * 1000) + 2 * 1000) * B5 / (ms_c5_all * 1e-3) / 1e9},
             }
+            if "total_1m_ms" in extra:
+                tot = args.c5_total // world * world
+                line["c5"]["total_1m"] = {"instances_total": tot, "scaling": "strong", "ms": extra["total_1m_ms"],
+                                          "value": tot / (extra["total_1m_ms"] * 1e-3), "unit": UNIT,
+                                          "chunks_per_rank": c5["total_1m_chunks"], "chunk_columns": c5["total_1m_chunk_columns"],
+                                          "algorithmic_tflops_per_gpu": tot / world * f5 / (extra["total_1m_ms"] * 1e-3) / 1e12,
+                                          "frac_of_tensor_peak": tot / world * f5 / (extra["total_1m_ms"] * 1e-3) / 1e12 / tp,
+                                          "what": "BASELINE configs[4] at its stated size: %d instances split over %d GPU(s), final iterate + fused "
+                                                  "per-layer objective (last_only), no data-path collective" % (tot, world)}
+            if "train_ms" in extra:
+                f5t = 2.0 * 1000 * 2000 * (5 * 40 + 1)
+                Bt5 = c5["train_columns"]
+                line["c5"]["train"] = {"columns_per_gpu": Bt5, "ms_per_step": extra["train_ms"], "value": world * Bt5 / (extra["train_ms"] * 1e-3),
+                                       "unit": "samples/s", "algorithmic_tflops_per_gpu": Bt5 * f5t / (extra["train_ms"] * 1e-3) / 1e12,
+                                       "frac_of_tensor_peak": Bt5 * f5t / (extra["train_ms"] * 1e-3) / 1e12 / tp,
+                                       "gradient_bytes_allreduced": int(4 * 40 * (1000 * 2000 + 6)) if world > 1 else 0}
+        if world == 1 and not args.quick:
+            line["eager_b200"] = eager_b200_leg(dev, A_host, X)
+            line["small_batch"] = small_batch_leg(dl, dev, A_host, X, precision)
+            line["safeguard"] = safeguard_leg(dl, dev, A_host, X, precision)
         if world == 1 and not args.no_cpu_baseline:
-            times, threads = cpu_forward_rate(CPU_SAMPLE_COLS, 1 + CPU_SAMPLE_REPS)
+            times, threads, kind = cpu_forward_rate(CPU_SAMPLE_COLS, 1 + CPU_SAMPLE_REPS)
             cpu_val = CPU_SAMPLE_COLS * CPU_SAMPLE_REPS / sum(times[1:])
-            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": "%d timed forwards of %d columns (same m,d,K, all iterates; %.1f s of host time) after 1 warm-up"
                                               % (CPU_SAMPLE_REPS, CPU_SAMPLE_COLS, sum(times[1:]))}
         print(json.dumps(line))
@@ -451,15 +777,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32x3", "tf32", "bf16"])
     ap.add_argument("--columns", type=int, default=B_PER_GPU, help="problem instances per GPU")
     ap.add_argument("--train-columns", type=int, default=65536, help="columns per GPU for the training leg (0 = skip)")
     ap.add_argument("--c5-columns", type=int, default=32768,
                     help="columns per GPU for the m=1000 d=2000 K=40 leg (BASELINE configs[4]); 0 = skip")
+    ap.add_argument("--c5-total", type=int, default=1048576,
+                    help="total instances of the strong-scaling C5 leg, split over the ranks (0 = skip)")
+    ap.add_argument("--c5-train-columns", type=int, default=8192, help="columns per GPU of the C5 training leg (0 = skip)")
+    ap.add_argument("--quick", action="store_true", help="headline legs only (forward, e2e, scalar training, C5 forward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.quick:
+        args.c5_total = args.c5_train_columns = 0
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -108,7 +108,7 @@ def load():
                                      C.c_void_p]
     lib.dladmm_sg_norm_elz.restype = C.c_int
     lib.dladmm_sg_norm_elz.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dladmm_sg_select_update.restype = C.c_int
     lib.dladmm_sg_select_update.argtypes = [C.c_int32, C.POINTER(SgPair), C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
                                             C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]

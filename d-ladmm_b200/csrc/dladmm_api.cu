@@ -75,7 +75,7 @@ static int validate(const dladmm_problem* p, int for_backward) {
     DL_REQUIRE(!((mt->want >> DLADMM_MET_SQERR_AZ) & 1u) || mt->X_clean, "DLADMM_MET_SQERR_AZ needs X_clean");
     DL_REQUIRE(!(p->start_half || p->stop_half), "metrics are not offered for half-layer calls");
   }
-  DL_REQUIRE(p->A && (p->B == 0 || (p->X && p->Z0 && p->E0 && p->L0 && p->Z && p->E && p->L && p->T)),
+  DL_REQUIRE(p->A && (p->B == 0 || (p->X && p->Z0 && p->E0 && p->L0 && p->T && (p->K == 0 || (p->Z && p->E && p->L)))),
              "A, X, Z0, E0, L0, Z, E, L, T must be non-NULL");
   for (int k = 0; k < p->K; ++k) {
     const dladmm_layer& l = p->layers[k];
@@ -217,7 +217,7 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
     // BG1: dZ_k = gZ_k + carried + A^T dR ; dx1 -> cZ
     {
       BPlain bl{w.dR, B};
-      const bool lossz = g->loss_kind == 1 && g->loss_scale && g->loss_layer_weight;
+      const bool lossz = g->loss_kind != 0 && g->loss_scale && g->loss_layer_weight;
       EpiBG1 epi{g->gZ ? g->gZ + s.zs * k : nullptr, k == K - 1 ? nullptr : w.cZ, s.mZ(k), make_bp(l.theta1), w.cZ, B,
                  s.Zout(k), lossz ? g->loss_alpha * g->loss_layer_weight[k] : 0.f, lossz ? g->loss_scale : nullptr};
       if ((rc = launch_simt(DLADMM_KIND_BWD_GEMM_DZ, d, B, m, w.Atp, w.mp, bl, epi, w.part, w.ncolTiles, w.prow, st))) return rc;
@@ -263,16 +263,19 @@ namespace dladmm {
 
 // ---- objective --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) objective_kernel(const float* __restrict__ Z, const float* __restrict__ E,
-                                                        const float* __restrict__ T, i64 zs, i64 ms, float alpha,
+                                                        const float* __restrict__ T, i64 zs, i64 ms, float alpha, int kind,
                                                         float* __restrict__ out) {
-  // grid.y = layer k; out[k] += alpha*sum|Z_k| + sum|E_k - T_{k+1}|
+  // grid.y = layer k; out[k] += alpha*sum|Z_k| + sum|E_k - T_{k+1}|   (kind 2: 0.5*(E_k - T_{k+1})^2 in place of the L1 residual)
   const int k = blockIdx.y;
   const float* z = Z + zs * k;
   const float* e = E + ms * k;
   const float* t = T + ms * (k + 1);
   float s = 0.f;
   for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < zs; i += (i64)gridDim.x * 256) s += alpha * fabsf(z[i]);
-  for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < ms; i += (i64)gridDim.x * 256) s += fabsf(e[i] - t[i]);
+  for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < ms; i += (i64)gridDim.x * 256) {
+    const float r = e[i] - t[i];
+    s += kind == 2 ? 0.5f * r * r : fabsf(r);
+  }
   __shared__ float sm[8];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256) objective_kernel(const float* __restrict_
 
 using namespace dladmm;
 
-static int run_objective(const dladmm_problem* p, float alpha, float* out, cudaStream_t st);
+static int run_objective(const dladmm_problem* p, float alpha, int kind, float* out, cudaStream_t st);
 
 extern "C" {
 
@@ -339,7 +342,7 @@ int dladmm_query(int device, dladmm_caps* caps) {
 }
 
 size_t dladmm_workspace_bytes(const dladmm_problem* p, int for_backward) {
-  if (!p || !p->layers || p->K <= 0) return 0;
+  if (!p || p->K < 0 || (p->K > 0 && !p->layers)) return 0;
   dladmm_problem q = *p;
   q.workspace = nullptr;
   Workspace w = carve(&q, for_backward);
@@ -352,6 +355,8 @@ int dladmm_forward(const dladmm_problem* p, void* stream) {
   if (rc) return rc;
   if (p->B == 0) {
     if (p->objective) DL_CUDA(cudaMemsetAsync(p->objective, 0, sizeof(float) * p->K, (cudaStream_t)stream));
+    if (p->metrics && p->metrics->want && p->metrics->out)
+      DL_CUDA(cudaMemsetAsync(p->metrics->out, 0, sizeof(float) * p->K * DLADMM_MET_COUNT, (cudaStream_t)stream));
     return DLADMM_OK;
   }
   if (p->workspace_bytes < dladmm_workspace_bytes(p, 0)) {
@@ -364,6 +369,10 @@ int dladmm_forward(const dladmm_problem* p, void* stream) {
   // tensor-core precisions need a 16-byte pitch for TMA (B % 4 == 0); other batch sizes run the FFMA kernels,
   // which are fp32 throughout (never less accurate than the precision asked for)
   if (umma_eligible(p)) return umma_forward(p, (char*)p->workspace + w.bytes, st);
+  if (p->metrics && p->metrics->want) {
+    set_error("metrics need a tensor-core precision (the FFMA path has no fused metric epilogues)");
+    return DLADMM_ERR_INVALID;
+  }
   if (p->objective && p->last_only) {
     set_error("objective with last_only needs a tensor-core precision and B %% 4 == 0 (the FFMA path reads the iterates back)");
     return DLADMM_ERR_INVALID;
@@ -374,7 +383,7 @@ int dladmm_forward(const dladmm_problem* p, void* stream) {
     case DLADMM_FAMILY_B: rc = forward_simt<DLADMM_FAMILY_B>(p, w, st); break;
     default: rc = forward_simt<DLADMM_FAMILY_C>(p, w, st); break;
   }
-  if (rc == DLADMM_OK && p->objective) rc = run_objective(p, p->objective_alpha, p->objective, st);   // Vsave is unused on this path
+  if (rc == DLADMM_OK && p->objective) rc = run_objective(p, p->objective_alpha, p->objective_kind, p->objective, st);   // Vsave is unused on this path
   return rc;
 }
 
@@ -382,9 +391,9 @@ int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* s
   int rc = validate(p, 1);
   if (rc) return rc;
   if (!g) { set_error("cotangents is NULL"); return DLADMM_ERR_INVALID; }
-  if (g->loss_kind != 0 && g->loss_kind != 1) { set_error("unknown loss_kind %d", g->loss_kind); return DLADMM_ERR_INVALID; }
-  if (g->loss_kind == 1 && (!g->loss_layer_weight || !g->loss_scale)) {
-    set_error("loss_kind 1 needs loss_layer_weight (host) and loss_scale (device)");
+  if (g->loss_kind < 0 || g->loss_kind > 2) { set_error("unknown loss_kind %d", g->loss_kind); return DLADMM_ERR_INVALID; }
+  if (g->loss_kind != 0 && (!g->loss_layer_weight || !g->loss_scale)) {
+    set_error("a fused loss needs loss_layer_weight (host) and loss_scale (device)");
     return DLADMM_ERR_INVALID;
   }
   if (p->B == 0) return DLADMM_OK;
@@ -410,17 +419,17 @@ int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* str
   DL_REQUIRE(p->Z && p->E && p->T && p->K > 0, "Z, E, T must be non-NULL");
   int rc;
   if ((rc = check_device())) return rc;
-  return run_objective(p, alpha, out, (cudaStream_t)stream);
+  return run_objective(p, alpha, p->objective_kind, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"
 
-static int run_objective(const dladmm_problem* p, float alpha, float* out, cudaStream_t st) {
+static int run_objective(const dladmm_problem* p, float alpha, int kind, float* out, cudaStream_t st) {
   DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * p->K, st));
   if (p->B == 0) return DLADMM_OK;
   i64 zs = (i64)p->d * p->B, ms = (i64)p->m * p->B;
   int bx = (int)std::min<i64>((zs + 255) / 256, 592);
-  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st); objective_kernel<<<dim3(bx, p->K), 256, 0, st>>>(p->Z, p->E, p->T, zs, ms, alpha, out); }
+  { LaunchScope ls(DLADMM_KIND_OBJECTIVE, st); objective_kernel<<<dim3(bx, p->K), 256, 0, st>>>(p->Z, p->E, p->T, zs, ms, alpha, kind, out); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }

@@ -130,6 +130,7 @@ struct M1Args {
   float* dR; float* cE; float* cL;   // outputs (m,B)
   i64 B;
   float lw; const float* lscale;     // fused L1-L1 loss: cotangent lw*scale*sign(E_j - T_{j+1}) on E_j, minus that on T_{j+1}
+  int lkind;                         // 2: LASSO residual term 0.5*(E_j - T_{j+1})^2 -> cotangent lw*scale*(E_j - T_{j+1})
 };
 
 template <int FAM>
@@ -150,7 +151,7 @@ __device__ __forceinline__ void m1_quad(const M1Args& a, int row, i64 col, float
   if (a.lscale) {
     const float sc = a.lw * __ldg(a.lscale);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float s = sc * sgn(ek.v[j] - tn.v[j]); dE[j] += s; dT[j] -= s; }
+    for (int j = 0; j < 4; ++j) { const float r = ek.v[j] - tn.v[j]; const float s = sc * (a.lkind == 2 ? r : sgn(r)); dE[j] += s; dT[j] -= s; }
   }
   float vbL[4]; bp_at4(a.bL, row, col, vbL);
   float dR[4], nE[4], nL[4];

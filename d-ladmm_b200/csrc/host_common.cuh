@@ -153,8 +153,8 @@ static inline M1Args make_m1(const dladmm_problem* p, const dladmm_cotangents* g
   a.th2 = make_bp(l.theta2);
   a.dR = w.dR; a.cE = w.cE; a.cL = w.cL;
   a.B = p->B;
-  a.lw = 0.f; a.lscale = nullptr;
-  if (g->loss_kind == 1 && g->loss_scale && g->loss_layer_weight) { a.lw = g->loss_layer_weight[j]; a.lscale = g->loss_scale; }
+  a.lw = 0.f; a.lscale = nullptr; a.lkind = g->loss_kind;
+  if (g->loss_kind != 0 && g->loss_scale && g->loss_layer_weight) { a.lw = g->loss_layer_weight[j]; a.lscale = g->loss_scale; }
   return a;
 }
 

@@ -25,13 +25,16 @@ static __global__ void __launch_bounds__(256) sg_norm_kernel(int m, i64 B, float
 // A(Znn-Zn) = Tnn - Tn: one thread per column, coalesced over the batch, no d x d operator.
 static __global__ void __launch_bounds__(256) sg_norm_elz_kernel(int m, int d, i64 B, float inv_bss1, const float* __restrict__ Tnn,
                                                                  const float* __restrict__ Tn, const float* __restrict__ Znn,
-                                                                 const float* __restrict__ Zn, float* __restrict__ out) {
+                                                                 const float* __restrict__ Zn, const float* __restrict__ Esub,
+                                                                 const float* __restrict__ Eadd, float* __restrict__ out) {
   const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
   if (b >= B) return;
   float s1 = 0.f, s3 = 0.f, s2 = 0.f;
   for (int i = 0; i < m; ++i) {
     const i64 off = (i64)i * B + b;
-    const float t = Tnn[off], dt = t - Tn[off];
+    float t = Tnn[off];
+    if (Esub) t = (t - Esub[off]) + Eadd[off];                     // Tnn given as A Znn + E' - X: swap E' for En
+    const float dt = t - Tn[off];
     s1 += t * t;
     s3 += dt * dt;
   }
@@ -58,8 +61,9 @@ static __global__ void __launch_bounds__(256) sg_keep_update_kernel(i64 B, const
       float upd = s;                                               // RT
       if (method == 1) upd = param * s + (1.f - param) * m0;        // EMA
       else if (method == 2) upd = (1.f - param) * m0;               // GS
-      mu[b] = upd;
+      if (method != 4) mu[b] = upd;
     }
+    if (method == 4) mu[b] = 1e10f;                                 // "None" (BlankUpdater): no threshold after the first test
   }
   fb = warp_sum(fb);
   __shared__ float sm[8];
@@ -109,12 +113,13 @@ int dladmm_sg_norm(int32_t m, int64_t B, float beta, float c, const float* Tn, c
 }
 
 int dladmm_sg_norm_elz(int32_t m, int32_t d, int64_t B, float inv_beta_ss1, const float* Tnn, const float* Tn, const float* Znn,
-                       const float* Zn, float* out, void* stream) {
+                       const float* Zn, const float* E_sub, const float* E_add, float* out, void* stream) {
   DL_REQUIRE(m > 0 && d > 0 && B >= 0 && Tnn && Tn && Znn && Zn && out, "sg_norm_elz: bad arguments");
+  DL_REQUIRE((E_sub == nullptr) == (E_add == nullptr), "sg_norm_elz: E_sub and E_add come together");
   if (B == 0) return DLADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
-    sg_norm_elz_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, d, B, inv_beta_ss1, Tnn, Tn, Znn, Zn, out); }
+    sg_norm_elz_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, d, B, inv_beta_ss1, Tnn, Tn, Znn, Zn, E_sub, E_add, out); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }
@@ -124,7 +129,7 @@ static int run_select(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, 
 int dladmm_sg_select_update(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, float* mu,
                             float one_minus_delta, int32_t method, float param, float* keep, float* fallbacks, void* stream) {
   DL_REQUIRE(n_arrays >= 0 && n_arrays <= 6 && (n_arrays == 0 || pairs) && snorm && mu && keep, "sg_select_update: bad arguments");
-  DL_REQUIRE(method >= 0 && method <= 3, "sg_select_update: unknown mu updater %d", method);
+  DL_REQUIRE(method >= 0 && method <= 4, "sg_select_update: unknown mu updater %d", method);
   if (B == 0) return DLADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);

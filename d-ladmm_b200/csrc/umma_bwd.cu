@@ -96,7 +96,7 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       epi.maskZ = s.mZ(k);
       epi.th1 = make_bp(l.theta1);
       epi.dx1 = sw.cZ; epi.ro = ro; epi.B = B;
-      const bool lossz = g->loss_kind == 1;
+      const bool lossz = g->loss_kind != 0;
       epi.Zk = s.Zout(k); epi.lz = lossz ? g->loss_alpha * g->loss_layer_weight[k] : 0.f; epi.lscale = lossz ? g->loss_scale : nullptr;
       if ((rc = launch_umma<umma::UEpiBG1<PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DZ, sw.dR, m, w.Atb, w.Ats, w.d256, w.mp, d, B, epi, st, grid)))
         return rc;
@@ -127,7 +127,8 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       epi.th2 = make_bp(lj.theta2);
       epi.dR = sw.dR; epi.cE = sw.cE; epi.cL = sw.cL;
       epi.ro = ro; epi.B = B;
-      epi.lw = g->loss_kind == 1 ? g->loss_layer_weight[j] : 0.f; epi.lscale = g->loss_kind == 1 ? g->loss_scale : nullptr;
+      epi.lw = g->loss_kind != 0 ? g->loss_layer_weight[j] : 0.f; epi.lscale = g->loss_kind != 0 ? g->loss_scale : nullptr;
+      epi.lkind = g->loss_kind;
       if ((rc = launch_umma<umma::UEpiBG2<FAM, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, d, w.Wtb + wi * w.m256 * w.dp, w.Wts + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
         return rc;
     }

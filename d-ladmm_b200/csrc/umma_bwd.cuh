@@ -118,6 +118,7 @@ struct UEpiBG2 {
   float* __restrict__ dR; float* cE; float* cL;
   RedOut ro; i64 B;
   float lw; const float* __restrict__ lscale;       // fused L1-L1 loss cotangents on E_{k-1} / T_k
+  int lkind;                                        // 2: LASSO residual term (cotangent proportional to E_{k-1} - T_k itself)
   uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const {
     p[0] = ss1.p ? Lp : nullptr;                     // L_{k-1} only feeds V_k for d(ss1) (tied variant)
@@ -184,7 +185,7 @@ struct UEpiBG2 {
       if (gE) dE += ok ? __ldg(gE + off) : 0.f;
       if (gT) dT += ok ? __ldg(gT + off) : 0.f;
       const float tn = tk, ek = in(st, slot, 4, i, col), lpp = in(st, slot, 5, i, col);
-      if (lscale) { const float sl = st.lsc * sgn(ek - tn); dE += sl; dT -= sl; }
+      if (lscale) { const float r = ek - tn; const float sl = st.lsc * (lkind == 2 ? r : sgn(r)); dE += sl; dT -= sl; }
       const float vbL = st.bL.at(row, b);
       red_contrib<PS>(bL, ro, SL_BL, st.red[0], row, b, group, ok, dL * tn, st.lane);
       const float dTt = dT + vbL * dL;

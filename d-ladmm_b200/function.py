@@ -71,7 +71,7 @@ def _build_layers(spec, params, grads):
 
 
 def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, for_backward, T_init=None, Vsave=None,
-             objective=None, objective_alpha=0.0):
+             objective=None, objective_alpha=0.0, objective_kind=0, start_half=False, stop_half=False, metrics=None):
     lib = _lib.load()
     p = _lib.Problem()
     p.abi_version = _lib.ABI_VERSION
@@ -89,6 +89,9 @@ def _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only
     p.Vsave = Vsave.data_ptr() if Vsave is not None else None
     p.objective = objective.data_ptr() if objective is not None else None
     p.objective_alpha = float(objective_alpha)
+    p.objective_kind = int(objective_kind)
+    p.start_half, p.stop_half = (1 if start_half else 0), (1 if stop_half else 0)
+    p.metrics = C.addressof(metrics) if metrics is not None else None
     nbytes = lib.dladmm_workspace_bytes(C.byref(p), 1 if for_backward else 0)
     ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=X.device)
     p.workspace = ws.data_ptr()
@@ -131,7 +134,32 @@ def padded_batch(spec, B):
     return (B + 3) // 4 * 4
 
 
-def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_init=None, objective_alpha=None, extras=None):
+def _metrics_desc(metrics, m, d, B_user, Bp, K, dev):
+    """dict(want=[names of _lib.METRICS], Z_label=, E_label=, X_clean=, dual_alpha=) -> (dladmm_metrics, out (K, MET_COUNT), keepalive)"""
+    mt = _lib.Metrics()
+    keep = []
+    for name in metrics.get("want", ()):
+        if name not in _lib.METRICS:
+            raise ValueError("unknown metric %r (known: %s)" % (name, ", ".join(_lib.METRICS)))
+        mt.want |= 1 << _lib.METRICS.index(name)
+    mt.dual_alpha = float(metrics.get("dual_alpha", 0.0))
+    for field, rows in (("Z_label", d), ("E_label", m), ("X_clean", m)):
+        t = metrics.get(field)
+        if t is None:
+            continue
+        _require_cuda_f32(field, t)
+        if tuple(t.shape) != (rows, B_user):
+            raise RuntimeError("%s must be (%d, %d), got %s" % (field, rows, B_user, tuple(t.shape)))
+        t = _pad_cols(t, Bp)
+        keep.append(t)
+        setattr(mt, field, t.data_ptr())
+    out = torch.zeros((K, _lib.MET_COUNT), dtype=torch.float32, device=dev)
+    mt.out = out.data_ptr()
+    return mt, out, keep
+
+
+def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_init=None, objective_alpha=None, extras=None,
+                objective_kind=0, start_half=False, stop_half=False, metrics=None):
     """Launch the K-layer forward.  Returns stacked (Z, E, L, T, maskZ, maskE).  `T_init` (m,B): T_0 supplied by the
     caller instead of A Z0 + E0 - X (single-layer steps from an arbitrary state).  `objective_alpha`: also compute the
     per-layer L1-L1 objective inside the product epilogues; `extras` (a dict) receives "objective" (K floats) and, in
@@ -166,13 +194,17 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
     Vsave = torch.empty((K, m, B), dtype=torch.float32, device=dev) if keep_v else None
     obj = torch.empty(K, dtype=torch.float32, device=dev) if objective_alpha is not None else None
     layers = _build_layers(spec, params, None)
+    mt = mt_out = mt_keep = None
+    if metrics is not None:
+        mt, mt_out, mt_keep = _metrics_desc(metrics, m, d, B_user, Bp, K, dev)
     with torch.cuda.device(dev):
         p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, last_only, False, T_init, Vsave, obj,
-                         objective_alpha or 0.0)
+                         objective_alpha or 0.0, objective_kind, start_half, stop_half, mt)
         _lib.check(lib.dladmm_forward(C.byref(p), torch.cuda.current_stream(dev).cuda_stream))
         ws.record_stream(torch.cuda.current_stream(dev))
     if extras is not None:
         extras["Vsave"], extras["objective"] = Vsave, obj
+        extras["metrics"] = mt_out
         extras["padded"] = (X, Z0, E0, L0, Z, E, L, T)
     if Bp != B_user:
         Z, E, L, T = Z[..., :B_user], E[..., :B_user], L[..., :B_user], T[..., :B_user]
@@ -274,19 +306,21 @@ def _layer_weight_tensor(weights, device):
 
 
 class UnrolledLADMML1L1(torch.autograd.Function):
-    """forward(spec, alpha, weights, A, X, Z0, E0, L0, *params) -> (loss, Z, E, L, T) with
+    """forward(spec, kind, alpha, weights, A, X, Z0, E0, L0, *params) -> (loss, Z, E, L, T) with
 
-        loss = (1/B) * sum_k weights[k] * sum_b ( alpha*||Z_k[:,b]||_1 + ||x[:,b] - A Z_k[:,b]||_1 )
+        loss = (1/B) * sum_k weights[k] * sum_b ( alpha*||Z_k[:,b]||_1 + r(x[:,b] - A Z_k[:,b]) )
 
-    the reference's training objective (main_syn_l1l1_scalar.py:289-299).  The loss cotangents are generated
+    kind 1: r = ||.||_1, the reference's L1-L1 training objective (main_syn_l1l1_scalar.py:289-299);
+    kind 2: r = 0.5*||.||_2^2, the LASSO training objective (main_syn_lasso_scalar.py:276-281).  The loss cotangents are generated
     inside the backward kernels (dladmm_cotangents.loss_kind = 1): no per-layer A@Z products, no (K,d,B)/(K,m,B)
     gradient stacks, no elementwise autograd graph.  The returned iterates are not differentiable."""
 
     @staticmethod
-    def forward(ctx, spec, alpha, weights, A, X, Z0, E0, L0, *params):
+    def forward(ctx, spec, kind, alpha, weights, A, X, Z0, E0, L0, *params):
         extras = {}
         Z, E, L, T, maskZ, maskE = run_forward(spec, A, X, Z0, E0, L0, list(params), want_masks=True,
-                                               objective_alpha=float(alpha), extras=extras)
+                                               objective_alpha=float(alpha), extras=extras, objective_kind=int(kind))
+        ctx.kind = int(kind)
         B = X.shape[1]
         obj = extras["objective"]
         w = _layer_weight_tensor(weights, X.device)
@@ -310,11 +344,11 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             maskE = saved[11]
             off = 12
         params = [t.contiguous() for t in saved[off:]]
-        needs = ctx.needs_input_grad[8:]
+        needs = ctx.needs_input_grad[9:]
         grads, flat = _flat_zero_grads(params, needs)
         scale = (gloss.detach().to(torch.float32) / float(max(ctx.B, 1))).reshape(1).contiguous()
         cot = _lib.Cotangents()
-        cot.loss_kind = 1
+        cot.loss_kind = ctx.kind
         cot.loss_alpha = ctx.alpha
         warr = (C.c_float * spec.K)(*ctx.weights)
         cot.loss_layer_weight = C.cast(warr, C.POINTER(C.c_float))
@@ -327,4 +361,5 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             ws.record_stream(torch.cuda.current_stream(dev))
             scale.record_stream(torch.cuda.current_stream(dev))
             _sync_gradients(spec, flat)
-        return (None,) * 8 + tuple(grads)
+        return (None,) * 9 + tuple(grads)
+

@@ -1,57 +1,52 @@
-"""mu_k updaters of the safeguarded evaluation -- mirror of the reference's mu_updater.py:18-116.
+"""mu_k updaters of the safeguarded evaluation (the reference's `mu_updater_dict[name](mu, param).step(norm, accepted)`
+surface, mu_updater.py:18-116).
 
-Each updater holds a per-column vector mu (B,) and is stepped with the norm of S(u^k) of the learned iterate and the
-0/1 acceptance vector.  `RMUpdater` in the reference returns a (values, indices) tuple and allocates with a float
-size (mu_updater.py:75-94, unusable as written); here it returns the running maximum over the last `parameter` norms.
+One table-driven class: per column, mu <- rule(norm, mu) where the column's learned iterate was accepted, unchanged
+elsewhere.  `METHOD_ID` are the ids `dladmm_sg_select_update` (csrc/safeguard.cu) takes: the safeguarded forwards fold the
+update into the selection kernel and only fall back to these host-side objects for "RM".  The reference's `RMUpdater`
+returns a (values, indices) tuple and allocates with a float size (unusable as written); here it is the running maximum
+of the last `parameter` norms.  "None" is the reference's BlankUpdater: the threshold becomes 1e10 after the first test.
 """
 import torch
 
+_RULES = {
+    "EMA": lambda s, mu, p: p * s + (1 - p) * mu,      # exponential moving average
+    "GS": lambda s, mu, p: (1 - p) * mu,               # geometric series
+    "RT": lambda s, mu, p: s,                          # recent term
+}
+METHOD_ID = {"EMA": 1, "GS": 2, "RT": 3, "None": 4}   # dladmm_sg_select_update `method`
 
-class EMAUpdater(object):
+
+class _RuleUpdater(object):
+    rule = None
+
     def __init__(self, mu, parameter):
         self.mu, self.parameter = mu, parameter
 
     def step(self, Sx_L2O_norm, bool_term):
-        update = self.parameter * Sx_L2O_norm + (1 - self.parameter) * self.mu
-        self.mu = ((1.0 - bool_term) * self.mu + bool_term * update).detach()
+        upd = _RULES[self.rule](Sx_L2O_norm, self.mu, self.parameter)
+        self.mu = torch.where(bool_term != 0, upd, self.mu).detach()
         return self.mu
 
 
-class GSUpdater(object):
-    def __init__(self, mu, parameter):
-        self.mu, self.parameter = mu, parameter
-
-    def step(self, Sx_L2O_norm, bool_term):
-        update = (1 - self.parameter) * self.mu
-        self.mu = ((1.0 - bool_term) * self.mu + bool_term * update).detach()
-        return self.mu
-
-
-class RTUpdater(object):
-    def __init__(self, mu, parameter):
-        self.mu, self.parameter = mu, parameter
-
-    def step(self, Sx_L2O_norm, bool_term):
-        self.mu = ((1.0 - bool_term) * self.mu + bool_term * Sx_L2O_norm).detach()
-        return self.mu
+def _rule(name):
+    return type(name + "Updater", (_RuleUpdater,), {"rule": name})
 
 
 class RMUpdater(object):
     def __init__(self, mu, parameter):
-        self.parameter = max(1, int(parameter))
-        self.recent = mu.new_zeros((mu.shape[0], self.parameter))
+        self.window = max(1, int(parameter))
+        self.recent = mu.new_zeros((mu.shape[0], self.window))
         self.pointer = 0
         self.step(mu)
 
     def step(self, Sx_L2O_norm, bool_term=None):
         self.recent[:, self.pointer] = Sx_L2O_norm
-        self.pointer = (self.pointer + 1) % self.parameter
+        self.pointer = (self.pointer + 1) % self.window
         return self.recent.max(dim=1).values
 
 
 class BlankUpdater(object):
-    """No safeguard threshold: mu_k = 1e10 (mu_updater.py:97-108)."""
-
     def __init__(self, mu, parameter):
         self.like = mu
 
@@ -59,4 +54,5 @@ class BlankUpdater(object):
         return torch.full_like(self.like, 1e10)
 
 
+EMAUpdater, GSUpdater, RTUpdater = _rule("EMA"), _rule("GS"), _rule("RT")
 mu_updater_dict = {"EMA": EMAUpdater, "GS": GSUpdater, "RT": RTUpdater, "RM": RMUpdater, "None": BlankUpdater}

@@ -24,8 +24,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .function import LayerSpec, UnrolledLADMM, UnrolledLADMML1L1, run_forward
-from .mu_updater import mu_updater_dict
+from .function import LayerSpec, UnrolledLADMM, UnrolledLADMML1L1, run_forward, padded_batch, _pad_cols
+from .mu_updater import mu_updater_dict, METHOD_ID
 
 _FAMILY = {"lena": _lib.FAMILY_A, "ltheta": _lib.FAMILY_A, "scalar": _lib.FAMILY_B, "full": _lib.FAMILY_B,
            "tied": _lib.FAMILY_B, "lasso": _lib.FAMILY_C, "newS": _lib.FAMILY_B, "tied_newS": _lib.FAMILY_B,
@@ -321,54 +321,173 @@ class DLADMMNet(nn.Module):
             return Zl, [self.E0] + El[:-1], [self.L0] + Ll[:-1]
         return (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)
 
-    def l1l1_loss(self, x, alpha, layer_weights=None):
+    def _fused_loss(self, kind, x, alpha, layer_weights, global_batch):
+        if not x.is_cuda:
+            raise RuntimeError("the fused training losses need a CUDA tensor: d-ladmm_b200 has no CPU path")
+        spec, params = self._spec_and_params()
+        w = [1.0] * self.layers if layer_weights is None else [float(v) for v in layer_weights]
+        if len(w) != self.layers:
+            raise ValueError("layer_weights must have one entry per layer")
+        B = x.shape[1]
+        if global_batch is None:
+            global_batch = B
+            if spec.grad_sync is not None:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    global_batch = B * dist.get_world_size(spec.grad_sync[0])
+        loss, Z, E, L, T = UnrolledLADMML1L1.apply(spec, kind, float(alpha), w, self.A, x, self.Z0, self.E0, self.L0, *params)
+        if global_batch != B:
+            loss = loss * (float(B) / float(global_batch))
+        return loss, self._as_lists(Z, E, L, T)
+
+    def l1l1_loss(self, x, alpha, layer_weights=None, global_batch=None):
         """Fused training objective of the reference drivers (main_syn_l1l1_scalar.py:289-299):
 
             loss = sum_k w_k * ( alpha * mean_b ||Z_k[:,b]||_1 + mean_b ||x[:,b] - A Z_k[:,b]||_1 )
 
         with w_k = layer_weights[k] (the scripts use 0.6**epoch for k < K-1 and 1 for the last layer).
         Returns (loss, outputs) where `outputs` is what forward(x) returns, detached.  loss.backward() runs
-        the library's backward with the loss cotangents generated inside the kernels."""
+        the library's backward with the loss cotangents generated inside the kernels.
+
+        Normalisation under data parallelism: the mean is over `global_batch` columns -- by default this rank's B, or
+        B x world size when `sync_gradients()` is on (equal column shards), so that the SUM-allreduced `.grad` is the
+        gradient of the global-mean loss and each rank's returned loss is its share of it (they add up over ranks)."""
+        return self._fused_loss(1, x, alpha, layer_weights, global_batch)
+
+    def lasso_loss(self, x, alpha, layer_weights=None, global_batch=None):
+        """Fused LASSO training objective (main_syn_lasso_scalar.py:276-281):
+
+            loss = sum_k w_k * ( alpha * mean_b ||Z_k[:,b]||_1 + 0.5 * mean_b ||x[:,b] - A Z_k[:,b]||_2^2 )
+
+        Same mechanics and normalisation as l1l1_loss (objective_kind / loss_kind = 2 of the C ABI)."""
+        return self._fused_loss(2, x, alpha, layer_weights, global_batch)
+
+    def forward_metrics(self, x, want, Z_label=None, E_label=None, X_clean=None, dual_alpha=0.0, last_only=False):
+        """Inference: forward(x) with the per-layer sums the reference's drivers compute script-side accumulated inside
+        the product epilogues (no second pass over the iterates, no extra A@Z_k products).  `want`: names out of
+        _lib.METRICS.  Returns (dict name -> (K,) tensor of sums over the batch, outputs):
+
+            l1_z sum|Z_k|; sqerr_z sum(Z_label-Z_k)^2; l1_res sum|x-A Z_k|; sq_res sum(x-A Z_k)^2; sqerr_e sum(E_label-E_k)^2;
+            sqerr_az sum(X_clean-A Z_k)^2; l1_e sum|E_k|; dot_lx sum L_k*x; dgap_l sum dual_gap(L_k,1);
+            dgap_atl sum dual_gap(A^T L_k, dual_alpha)  (one extra product per layer, only when asked for)
+
+        See nmse_db / psnr_db / dual_gap_loss below for the reference's formulas on top of these sums."""
         if not x.is_cuda:
-            raise RuntimeError("DLADMMNet.l1l1_loss needs a CUDA tensor: d-ladmm_b200 has no CPU path")
+            raise RuntimeError("DLADMMNet.forward_metrics needs a CUDA tensor: d-ladmm_b200 has no CPU path")
+        if self.variant in _NEWS and last_only:
+            raise RuntimeError("last_only is not offered for the newS variants")
         spec, params = self._spec_and_params()
-        w = [1.0] * self.layers if layer_weights is None else [float(v) for v in layer_weights]
-        if len(w) != self.layers:
-            raise ValueError("layer_weights must have one entry per layer")
-        loss, Z, E, L, T = UnrolledLADMML1L1.apply(spec, float(alpha), w, self.A, x, self.Z0, self.E0, self.L0, *params)
-        return loss, self._as_lists(Z, E, L, T)
+        K = self.layers
+        extras = {}
+        desc = dict(want=list(want), Z_label=Z_label, E_label=E_label, X_clean=X_clean, dual_alpha=dual_alpha)
+        with torch.no_grad():
+            Z, E, L, T, _, _ = run_forward(spec, self.A, x, self.Z0, self.E0, self.L0, [p.detach() for p in params],
+                                           want_masks=False, last_only=last_only, extras=extras, metrics=desc)
+        if last_only:
+            Zl, El, Ll, Tl = [Z[(K - 1) % 2]], [E[(K - 1) % 2]], [L[(K - 1) % 2]], [T[K % 2]]
+            outs = (Zl, El, Ll, Tl) if _RETURNS_T[self.variant] else (Zl, El, Ll)
+        else:
+            outs = self._as_lists(Z, E, L, T)
+        out = extras["metrics"]
+        return {name: out[:, _lib.METRICS.index(name)] for name in want}, outs
+
+    @staticmethod
+    def nmse_db(sums, Z_label, E_label):
+        """NMSE per layer in dB as test_syn_l1l1_scalar.py:537-541 forms it from the accumulated squared errors:
+        10 log10( sum(Z_label-Z_k)^2 / sum Z_label^2 + sum(E_label-E_k)^2 / sum E_label^2 )  (the 1/n_test factors cancel)."""
+        return 10.0 * torch.log10(sums["sqerr_z"] / Z_label.pow(2).sum() + sums["sqerr_e"] / E_label.pow(2).sum())
+
+    @staticmethod
+    def psnr_db(sums, numel):
+        """PSNR per layer as main_lena.py:138-143 / 262-267: mse = mean((255*gt - 255*A Z_k)^2) over `numel` elements,
+        psnr = -10 log10(mse) + 48.131."""
+        return -10.0 * torch.log10(sums["sqerr_az"] * (255.0 * 255.0 / float(numel))) + 48.131
+
+    def dual_gap_loss(self, sums, alpha, B):
+        """Per-layer training loss of main_lena.py:221-228 from the fused sums (values only; training on it goes through
+        the generic autograd path): alpha*mean|Z_k| + mean|E_k| + mean dual_gap(A^T L_k, alpha) + mean dual_gap(L_k, 1)
+        + mean(L_k * x)."""
+        nz, nm = float(self.d * B), float(self.m * B)
+        return (alpha * sums["l1_z"] / nz + sums["l1_e"] / nm + sums["dgap_atl"] / nz + sums["dgap_l"] / nm + sums["dot_lx"] / nm)
 
 
-    # ---- classical LADMM step, safeguard operator and safeguarded evaluation (family B) -------------------------------
+    # ---- classical LADMM step, safeguard operator and safeguarded evaluation ------------------------------------------
+    #   Z -> E -> L ordering (scalar / full / tied):  KM, S, forward_safeguarded   test_syn_l1l1_scalar.py:126-317
+    #   E -> L -> Z ordering (newS variants):        KM_ZEL, KM_ELZ, Snorm_ELZ, forward_safeguarded
+    #                                                                              test_syn_l1l1_newS_Acols.py:136-277
+    # Every step is a K = 1 or K = 2 call of the library from an arbitrary state (dladmm_problem.T_init / start_half /
+    # stop_half); norms, the per-column selection and the mu_k update are csrc/safeguard.cu.
     def two_norm(self, z, dim=0):
         """test_syn_l1l1_scalar.py:126-128"""
         return (z ** 2).sum(dim=dim).sqrt()
 
+    def _lip(self):
+        """||A^T A||_2 as a host float (the tensor `self.L` stays for scripts): no device sync per KM call."""
+        if getattr(self, "_lip_float", None) is None or self._lipschitz is None:
+            self._lip_float = float(self.L.item())
+        return self._lip_float
+
+    def _steps(self, spec, params, Zk, Ek, Lk, X, T_init=None, start_half=False, stop_half=False):
+        Z, E, L, T, _, _ = run_forward(spec, self.A, X, Zk, Ek, Lk, params, want_masks=False, T_init=T_init,
+                                       start_half=start_half, stop_half=stop_half)
+        return Z, E, L, T
+
+    def _t0(self, X, Z0=None, E0=None):
+        """T_0 = A Z0 + E0 - X through the library (a K = 0 call: the first fused product alone)."""
+        spec0 = LayerSpec(_FAMILY[self.variant], self.m, self.d, 0, _lib.PRECISIONS[self.precision], [], [])
+        z = self.Z0 if Z0 is None else Z0
+        e = self.E0 if E0 is None else E0
+        return self._steps(spec0, [], z, e, e, X)[3][0]
+
     def _one_layer(self, spec1, params, Zk, Ek, Lk, Tk, X):
-        Z, E, L, T, _, _ = run_forward(spec1, self.A, X, Zk, Ek, Lk, [p.detach() for p in params], want_masks=False, T_init=Tk)
+        Z, E, L, T = self._steps(spec1, params, Zk, Ek, Lk, X, T_init=Tk)
         return Z[0], E[0], L[0], T[1]
 
+    def _scalar(self, v):
+        return torch.full((1, 1), float(v), dtype=torch.float32, device=self.A.device)
+
     def _km_spec(self, beta, ss1, ss2, alpha):
-        key = (float(beta), float(ss1), float(ss2), float(alpha))
+        """Classical step of the Z -> E -> L ordering as ONE family-B layer: W = A^T with ss1 in the tied slot, all betas =
+        beta, thresholds ss1*alpha and ss2 (test_syn_l1l1_scalar.py:131-160)."""
+        key = ("zel_b", float(beta), float(ss1), float(ss2), float(alpha))
         cache = self.__dict__.setdefault("_km_cache", {})
         if key not in cache:
-            dev = self.A.device
-            s = lambda v: torch.full((1, 1), float(v), dtype=torch.float32, device=dev)
+            s = self._scalar
             params = [self.A.t().contiguous(), s(beta), s(ss1), s(ss2), s(float(ss1) * float(alpha)), s(ss2)]
             slots = {"beta1": 1, "beta2": 1, "beta3": 1, "ss1": 2, "ss2": 3, "theta1": 4, "theta2": 5}
             spec = LayerSpec(_lib.FAMILY_B, self.m, self.d, 1, _lib.PRECISIONS[self.precision], [slots], [0])
-            cache.clear()
+            if len(cache) > 8:
+                cache.clear()
             cache[key] = (spec, params)
         return cache[key]
 
+    def _km_spec_elz(self, beta, ss1, alpha, K):
+        """Classical step with ss2 = 1/beta (KM_ZEL / KM_ELZ, test_syn_l1l1_newS_Acols.py:136-171): K identical family-A
+        layers  Z = act(Z - ss1 A^T (L + beta T), ss1 alpha),  E = act(X - A Z - L/beta, 1/beta),  L += beta T."""
+        key = ("elz_a", float(beta), float(ss1), float(alpha), int(K))
+        cache = self.__dict__.setdefault("_km_cache", {})
+        if key not in cache:
+            s = self._scalar
+            params = [self.A.t().contiguous(), s(beta), s(1.0 / beta), s(ss1), s(float(ss1) * float(alpha)), s(1.0 / beta)]
+            slots = {"beta1": 1, "beta2": 2, "ss1": 3, "theta1": 4, "theta2": 5}
+            spec = LayerSpec(_lib.FAMILY_A, self.m, self.d, int(K), _lib.PRECISIONS[self.precision], [slots] * int(K), [0] * int(K))
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = (spec, params)
+        return cache[key]
+
+    def _need(self, newS, what):
+        ok = _FAMILY[self.variant] == _lib.FAMILY_B and ((self.variant in _NEWS) == newS)
+        if not ok:
+            raise NotImplementedError("%s exists for the %s variants only (as in the reference's evaluation scripts)" %
+                                      (what, "newS (E -> L -> Z)" if newS else "scalar / full / tied (Z -> E -> L)"))
+
     def KM(self, Zk, Ek, Lk, Tk, X, **kwargs):
-        """One classical LADMM iteration (test_syn_l1l1_scalar.py:131-160): the learned family-B layer with W = A^T scaled
-        by ss1, all betas = beta, thresholds ss1*alpha and ss2.  Returns (Varn, Zn, En, Tn, Ln)."""
-        if _FAMILY[self.variant] != _lib.FAMILY_B or self.variant in _NEWS:
-            raise NotImplementedError("KM/S/safeguard are built for the family-B variants (scalar, full, tied)")
+        """One classical LADMM iteration (test_syn_l1l1_scalar.py:131-160).  Returns (Varn, Zn, En, Tn, Ln)."""
+        self._need(False, "KM")
         beta = float(kwargs.get("beta", 1.0))
         ss1 = kwargs.get("ss1", None)
-        ss1 = 0.999 / self.L.item() if ss1 is None else float(ss1)
+        ss1 = 0.999 / self._lip() if ss1 is None else float(ss1)
         ss2 = float(kwargs.get("ss2", 0.3))
         alpha = float(kwargs.get("alpha", 0.01))
         spec1, params = self._km_spec(beta, ss1, ss2, alpha)
@@ -384,8 +503,10 @@ class DLADMMNet(nn.Module):
         return torch.cat([beta * Tn, c * (En - 2 * Ek + Ep)])
 
     def _s_norm(self, Zk, Ek, Lk, Tk, X, Ep, alpha):
+        self._need(False, "S")
         beta, ss2 = 1.0, 0.3
-        _, _, En, Tn, _ = self.KM(Zk, Ek, Lk, Tk, X, beta=beta, ss2=ss2, alpha=alpha)
+        spec1, params = self._km_spec(beta, 0.999 / self._lip(), ss2, alpha)
+        _, En, _, Tn = self._one_layer(spec1, params, Zk, Ek, Lk, Tk, X)
         c1 = beta * ss2
         out = torch.empty(X.shape[1], dtype=torch.float32, device=X.device)
         stream = torch.cuda.current_stream(X.device).cuda_stream
@@ -393,60 +514,183 @@ class DLADMMNet(nn.Module):
                                               Ek.contiguous().data_ptr(), Ep.contiguous().data_ptr(), out.data_ptr(), stream))
         return out
 
+    # E -> L -> Z ordering ------------------------------------------------------------------------------------------
+    def KM_ZEL(self, Zk, Ek, Lk, Tk, X, **kwargs):
+        """test_syn_l1l1_newS_Acols.py:136-152: classical step in Z -> E -> L order with ss2 = 1/beta.
+        Returns (Varn, Zn, En, Tn, Ln)."""
+        self._need(True, "KM_ZEL")
+        beta = float(kwargs.get("beta", 1.0))
+        ss1 = float(kwargs.get("ss1", 0.999 / self._lip()))
+        spec1, params = self._km_spec_elz(beta, ss1, float(kwargs.get("alpha", 0.01)), 1)
+        Zn, En, Ln, Tn = self._one_layer(spec1, params, Zk, Ek, Lk, Tk, X)
+        return Lk + beta * Tk, Zn, En, Tn, Ln
+
+    def _km_elz(self, Ek, Lk, Zn, X, beta, ss1, alpha, with_next_estep=False):
+        """E- and L-step from the given Z, then the next Z-step: one K = 2 call that starts with an E/T/L half layer
+        (start_half) and, unless the safeguard norm needs A Znn, stops after the Z half of the second (stop_half)."""
+        spec2, params = self._km_spec_elz(beta, ss1, alpha, 2)
+        return self._steps(spec2, params, Zn, Ek, Lk, X, start_half=True, stop_half=not with_next_estep)
+
+    def KM_ELZ(self, Ek, Lk, Zn, X, **kwargs):
+        """test_syn_l1l1_newS_Acols.py:155-171.  Returns (En, Tn, Ln, Varnn, Znn)."""
+        self._need(True, "KM_ELZ")
+        beta = float(kwargs.get("beta", 1.0))
+        ss1 = float(kwargs.get("ss1", 0.999 / self._lip()))
+        Z, E, L, T = self._km_elz(Ek, Lk, Zn, X, beta, ss1, float(kwargs.get("alpha", 0.01)))
+        return E[0], T[1], L[0], L[0] + beta * T[1], Z[1]
+
+    def Snorm_ELZ(self, Ek, Lk, Zn, X, **kwargs):
+        """test_syn_l1l1_newS_Acols.py:174-192: sqrt(||A Znn + En - X||^2 + (Znn - Zn)^T P2 (Znn - Zn)) per column, with
+        P2 = I/(beta ss1) - A^T A.  Computed without the d x d operator: the quadratic form is
+        ||Znn - Zn||^2/(beta ss1) - ||A (Znn - Zn)||^2 and A (Znn - Zn) = Tnn - Tn comes out of the fused products."""
+        self._need(True, "Snorm_ELZ")
+        beta, ss1 = 1.0, 0.999 / self._lip()
+        Zn = Zn.contiguous()
+        Z, E, L, T = self._km_elz(Ek, Lk, Zn, X, beta, ss1, float(kwargs.get("alpha", 0.01)), with_next_estep=True)
+        B = X.shape[1]
+        out = torch.empty(B, dtype=torch.float32, device=X.device)
+        if Z.shape[-1] != B or not Z.is_contiguous():      # (narrowed views of a padded call: the kernels take pitch B)
+            Z, E, T = Z.contiguous(), E.contiguous(), T.contiguous()
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        # T[2] = A Znn + E' - X with E' = E[1] (the E-step after Znn); swap E' for En = E[0]
+        _lib.check(_lib.load().dladmm_sg_norm_elz(self.m, self.d, B, 1.0 / (beta * ss1), T[2].data_ptr(), T[1].data_ptr(),
+                                                  Z[1].data_ptr(), Zn.data_ptr(), E[1].data_ptr(), E[0].data_ptr(),
+                                                  out.data_ptr(), stream))
+        return out
+
+    def _select(self, pairs_in, s_norm, mu_state, delta, keep_row):
+        """Per-column choice between the learned and the classical candidate + the mu_k update, on the device.
+        mu_state = [mu tensor (B,), method name, param, host updater or None]."""
+        lib = _lib.load()
+        B = s_norm.shape[0]
+        outs = [torch.empty_like(a) for a, _ in pairs_in]
+        pairs = (_lib.SgPair * len(pairs_in))()
+        for i, ((a, b_), o) in enumerate(zip(pairs_in, outs)):
+            pairs[i].a, pairs[i].b, pairs[i].out, pairs[i].rows = a.data_ptr(), b_.data_ptr(), o.data_ptr(), a.shape[0]
+        stream = torch.cuda.current_stream(s_norm.device).cuda_stream
+        mu, method, param, host_updater = mu_state
+        if host_updater is None:
+            _lib.check(lib.dladmm_sg_select_update(len(pairs_in), pairs, B, s_norm.data_ptr(), mu.data_ptr(), float(1.0 - delta),
+                                                   METHOD_ID[method], float(param), keep_row.data_ptr(), None, stream))
+        else:                       # "RM": a window of recent norms, kept by the host-side updater object
+            _lib.check(lib.dladmm_sg_select(len(pairs_in), pairs, B, s_norm.data_ptr(), mu.data_ptr(), float(1.0 - delta),
+                                            keep_row.data_ptr(), stream))
+            mu_state[0] = host_updater.step(s_norm, keep_row).contiguous()
+        return outs
+
+    def _mu_state(self, mu0, method, param):
+        if method not in mu_updater_dict:
+            raise ValueError("unknown mu_k updater %r" % (method,))
+        host = None if method in METHOD_ID else mu_updater_dict[method](mu0, param)
+        mu = mu0.clone() if host is None else mu0          # the fused kernel updates mu in place
+        return [mu.contiguous(), method, param, host]
+
     def forward_safeguarded(self, x, use_learned, use_safeguard, continued=False, K=None, num_iter=200, delta=-99.0,
                             mu_k_method="None", mu_k_param=0.0, alpha=0.01):
-        """The evaluation forward of test_syn_l1l1_scalar.py:179-317: per layer the classical KM step, the learned step,
-        the safeguard test ||S(u_L2O)|| < (1-delta)*mu_k per column, the per-column selection and the mu_k update.
-        Returns (Z, E, L, T) lists, plus sg_count (columns that fell back to KM, per layer) when both flags are set."""
-        if _FAMILY[self.variant] != _lib.FAMILY_B or self.variant in _NEWS:
-            raise NotImplementedError("forward_safeguarded is built for the family-B variants (scalar, full, tied); the newS "
-                                      "ordering has its own safeguard (KM_ELZ / Snorm_ELZ), not built")
+        """The evaluation forward of the reference's test scripts: per layer the classical step, the learned step, the
+        safeguard test ||S(u_L2O)|| < (1-delta)*mu_k per column, the per-column selection and the mu_k update.
+
+        scalar / full / tied (test_syn_l1l1_scalar.py:179-317): returns (Z, E, L, T) lists;
+        newS variants (test_syn_l1l1_newS_Acols.py:195-277):    returns (Z, E, L) with the initial variables first;
+        plus sg_count (columns that fell back to the classical step, per layer) when both flags are set."""
+        if _FAMILY[self.variant] != _lib.FAMILY_B:
+            raise NotImplementedError("forward_safeguarded exists for the family-B variants (the reference only has it there)")
         layers = self.layers
         if K is None:
             K = layers if (not continued and (use_learned or use_safeguard)) else num_iter
-        X = x.contiguous()
-        B = X.shape[1]
-        lib = _lib.load()
+        if use_safeguard and not use_learned:
+            raise AssertionError("use_safeguard needs use_learned (test_syn_l1l1_scalar.py:240)")
         spec, params = self._spec_and_params()
+        params = [p.detach() for p in params]
+        # run at the padded pitch throughout (zero columns stay zero and are dropped at the end): the norm / selection
+        # kernels address (rows x B) arrays with pitch B
+        B_user = x.shape[1]
+        Bp = padded_batch(spec, B_user)
+        pad = lambda t: _pad_cols(t, Bp)
+        X, Z0, E0, L0 = pad(x), pad(self.Z0), pad(self.E0), pad(self.L0)
         with torch.no_grad():
-            T = [self.A.mm(self.Z0) + self.E0 - X]
-            Z, E, L = [], [], []
-            return_cnt = use_learned and use_safeguard
-            if return_cnt:
-                mu_k = self._s_norm(self.Z0, self.E0, self.L0, T[-1], X, self.E0, alpha)
-                updater = mu_updater_dict[mu_k_method](mu_k, mu_k_param)
-                sg_count = [0.0] * layers
-            for k in range(K):
-                if continued and k == layers:
-                    use_learned = use_safeguard = False
-                Zp, Ep_, Lp = (self.Z0, self.E0, self.L0) if k == 0 else (Z[-1], E[-1], L[-1])
-                _, Zn_KM, En_KM, Tn_KM, Ln_KM = self.KM(Zp, Ep_, Lp, T[-1], X, alpha=alpha)
+            if self.variant in _NEWS:
+                out = self._safeguarded_newS(spec, params, X, Z0, E0, L0, use_learned, use_safeguard, continued, K, delta,
+                                             mu_k_method, mu_k_param, alpha)
+            else:
+                out = self._safeguarded_zel(spec, params, X, Z0, E0, L0, use_learned, use_safeguard, continued, K, delta,
+                                            mu_k_method, mu_k_param, alpha)
+        lists, keep_all = out
+        if Bp != B_user:
+            lists = [[t[:, :B_user] for t in lst] for lst in lists]
+        if keep_all is not None:
+            cnt = (float(B_user) - keep_all[:, :B_user].sum(dim=1)).tolist()       # the one host read of the evaluation
+            sg_count = [0.0] * layers
+            for k in range(min(layers, len(cnt))):
+                sg_count[k] = cnt[k]
+            return tuple(lists) + (sg_count,)
+        return tuple(lists)
+
+    def _safeguarded_zel(self, spec, params, X, Z0, E0, L0, use_learned, use_safeguard, continued, K, delta, method, param, alpha):
+        layers, B, dev = self.layers, X.shape[1], X.device
+        km_spec, km_params = self._km_spec(1.0, 0.999 / self._lip(), 0.3, alpha)
+        T = [self._t0(X, Z0, E0)]
+        Z, E, L = [], [], []
+        both = use_learned and use_safeguard
+        keep_all = torch.ones((min(K, layers), B), dtype=torch.float32, device=dev) if both else None
+        if both:
+            mu_state = self._mu_state(self._s_norm(Z0, E0, L0, T[-1], X, E0, alpha), method, param)
+        for k in range(K):
+            if continued and k == layers:
+                use_learned = use_safeguard = False
+            Zp, Ep_, Lp = (Z0, E0, L0) if k == 0 else (Z[-1], E[-1], L[-1])
+            Zn_KM, En_KM, Ln_KM, Tn_KM = self._one_layer(km_spec, km_params, Zp, Ep_, Lp, T[-1], X)
+            if use_learned:
+                spec1 = LayerSpec(spec.family, self.m, self.d, 1, spec.precision, [spec.slots[k]], [spec.weights[k]], spec.fixed)
+                Zn, En, Ln, Tn = self._one_layer(spec1, params, Zp, Ep_, Lp, T[-1], X)
+            if use_safeguard:
+                s_norm = self._s_norm(Zn, En, Ln, Tn, X, Ep_, alpha)
+                outs = self._select([(Zn, Zn_KM), (En, En_KM), (Tn, Tn_KM), (Ln, Ln_KM)], s_norm, mu_state, delta, keep_all[k])
+                Z.append(outs[0]); E.append(outs[1]); T.append(outs[2]); L.append(outs[3])
+            elif use_learned:
+                Z.append(Zn); E.append(En); T.append(Tn); L.append(Ln)
+            else:
+                Z.append(Zn_KM); E.append(En_KM); T.append(Tn_KM); L.append(Ln_KM)
+        return [Z, E, L, T], keep_all
+
+    def _safeguarded_newS(self, spec, params, X, Z0, E0, L0, use_learned, use_safeguard, continued, K, delta, method, param, alpha):
+        layers, B, dev = self.layers, X.shape[1], X.device
+        beta, ss1 = 1.0, 0.999 / self._lip()
+        Z, E, L = [], [], []
+        both = use_learned and use_safeguard
+        keep_all = torch.ones((min(K, layers), B), dtype=torch.float32, device=dev) if both else None
+        if both:
+            mu_state = self._mu_state(self.Snorm_ELZ(E0, L0, Z0, X, alpha=alpha), method, param)
+        for k in range(K):
+            if continued and k == layers:
+                use_learned = use_safeguard = False
+            if k == 0:
+                # both candidates are a Z-step from (Z0, E0, L0) with T_0 = A Z0 + E0 - X (computed by the call itself)
+                km1, kmp = self._km_spec_elz(beta, ss1, alpha, 1)
+                En_KM, Ln_KM = E0, L0
+                Zn_KM = self._steps(km1, kmp, Z0, E0, L0, X, stop_half=True)[0][0]
                 if use_learned:
-                    spec1 = LayerSpec(spec.family, self.m, self.d, 1, spec.precision, [spec.slots[k]], [spec.weights[k]], spec.fixed)
-                    Zn, En, Ln, Tn = self._one_layer(spec1, params, Zp, Ep_, Lp, T[-1], X)
-                if use_safeguard:
-                    assert use_learned
-                    s_norm = self._s_norm(Zn, En, Ln, Tn, X, Ep_, alpha)
-                    keep = torch.empty(B, dtype=torch.float32, device=X.device)
-                    outs = [torch.empty_like(t) for t in (Zn, En, Tn, Ln)]
-                    pairs = (_lib.SgPair * 4)()
-                    for i, (a, b_, o) in enumerate(zip((Zn, En, Tn, Ln), (Zn_KM, En_KM, Tn_KM, Ln_KM), outs)):
-                        pairs[i].a, pairs[i].b, pairs[i].out, pairs[i].rows = a.data_ptr(), b_.data_ptr(), o.data_ptr(), a.shape[0]
-                    mu_vec = mu_k if isinstance(mu_k, torch.Tensor) else torch.full((B,), float(mu_k), device=X.device)
-                    _lib.check(lib.dladmm_sg_select(4, pairs, B, s_norm.data_ptr(), mu_vec.contiguous().data_ptr(),
-                                                    float(1.0 - delta), keep.data_ptr(),
-                                                    torch.cuda.current_stream(X.device).cuda_stream))
-                    mu_k = updater.step(s_norm, keep)
-                    Z.append(outs[0]); E.append(outs[1]); T.append(outs[2]); L.append(outs[3])
-                    if k < layers:
-                        sg_count[k] = float(B - keep.sum().item())
-                elif use_learned:
-                    Z.append(Zn); E.append(En); T.append(Tn); L.append(Ln)
-                else:
-                    Z.append(Zn_KM); E.append(En_KM); T.append(Tn_KM); L.append(Ln_KM)
-        if return_cnt:
-            return Z, E, L, T, sg_count
-        return Z, E, L, T
+                    spec1 = LayerSpec(spec.family, self.m, self.d, 1, spec.precision, [spec.slots[0]], [spec.weights[0]], spec.fixed)
+                    En_L, Ln_L = E0, L0
+                    Zn_L = self._steps(spec1, params, Z0, E0, L0, X, stop_half=True)[0][0]
+            else:
+                Zk, Ek, Lk, _ = self._km_elz(E[-1], L[-1], Z[-1], X, beta, ss1, alpha)
+                En_KM, Ln_KM, Zn_KM = Ek[0], Lk[0], Zk[1]
+                if use_learned:
+                    # E- and L-step with layer k-1's parameters, Z-step with layer k's (:234-242)
+                    spec2 = LayerSpec(spec.family, self.m, self.d, 2, spec.precision, [spec.slots[k - 1], spec.slots[k]],
+                                      [spec.weights[k - 1], spec.weights[k]], spec.fixed)
+                    Zl, El, Ll, _ = self._steps(spec2, params, Z[-1], E[-1], L[-1], X, start_half=True, stop_half=True)
+                    En_L, Ln_L, Zn_L = El[0], Ll[0], Zl[1]
+            if use_safeguard:
+                s_norm = self.Snorm_ELZ(En_L, Ln_L, Zn_L, X, alpha=alpha)
+                outs = self._select([(En_L, En_KM), (Ln_L, Ln_KM), (Zn_L, Zn_KM)], s_norm, mu_state, delta, keep_all[k])
+                E.append(outs[0]); L.append(outs[1]); Z.append(outs[2])
+            elif use_learned:
+                E.append(En_L); L.append(Ln_L); Z.append(Zn_L)
+            else:
+                E.append(En_KM); L.append(Ln_KM); Z.append(Zn_KM)
+        return [[Z0] + Z, [E0] + E, [L0] + L], keep_all
 
 
 class DLADMMNetScalar(DLADMMNet):

@@ -245,13 +245,17 @@ DLADMM_API int dladmm_sg_select(int32_t n_arrays, const dladmm_sg_pair* pairs, i
 
 /* Safeguard of the E -> L -> Z ordering (Snorm_ELZ, test_syn_l1l1_newS_Acols.py:174-192) without the d x d matrix
  * P2 = I/(beta ss1) - A^T A:  out[b] = sqrt( ||Tnn[:,b]||^2 + inv_beta_ss1 * ||Znn[:,b] - Zn[:,b]||^2 - ||Tnn[:,b] - Tn[:,b]||^2 )
- * with Tn = A Zn + En - X and Tnn = A Znn + En - X (so Tnn - Tn = A (Znn - Zn)).  Tn, Tnn are (m,B); Zn, Znn (d,B). */
+ * with Tn = A Zn + En - X and Tnn = A Znn + En - X (so Tnn - Tn = A (Znn - Zn)).  Tn, Tnn are (m,B); Zn, Znn (d,B).
+ * E_sub / E_add (both or neither, (m,B)): the caller holds A Znn + E' - X (the T output of a following E-step) instead of
+ * Tnn; then Tnn is taken as (Tnn_given - E_sub) + E_add with E_sub = E', E_add = En. */
 DLADMM_API int dladmm_sg_norm_elz(int32_t m, int32_t d, int64_t B, float inv_beta_ss1, const float* Tnn, const float* Tn,
-                                  const float* Znn, const float* Zn, float* out, void* stream);
+                                  const float* Znn, const float* Zn, const float* E_sub, const float* E_add, float* out,
+                                  void* stream);
 
 /* mu_k updaters of mu_updater.py:18-72 fused with the selection: as dladmm_sg_select, then per column
  *   method 1 (EMA): upd = param*snorm + (1-param)*mu;  2 (GS): upd = (1-param)*mu;  3 (RT): upd = snorm;
- *   mu[b] = keep[b] ? upd : mu[b]   (in place; method 0 leaves mu alone), and *fallbacks (one device float, accumulated)
+ *   mu[b] = keep[b] ? upd : mu[b]   (in place; method 0 leaves mu alone; method 4, the reference's "None" updater
+ *   mu_updater.py:97-108, sets mu[b] = 1e10 for every column), and *fallbacks (one device float, accumulated)
  *   += number of columns with keep == 0.  One launch for keep + mu + count, one for the copies. */
 DLADMM_API int dladmm_sg_select_update(int32_t n_arrays, const dladmm_sg_pair* pairs, int64_t B, const float* snorm, float* mu,
                                        float one_minus_delta, int32_t method, float param, float* keep, float* fallbacks,

@@ -1,8 +1,9 @@
 """Load the reference's own ``DLADMMNet`` classes from /root/reference (build container only).
 
-TEST INFRASTRUCTURE -- not product code.  Used by ``oracle/make_golden.py`` and by the CPU
-tests that pin ``oracle/dladmm_oracle.py`` to the reference.  ``/root/reference`` does not
-exist on the GPU box, so nothing marked ``gpu`` may import this module.
+TEST INFRASTRUCTURE -- not product code.  Used by ``oracle/make_golden.py``, by the CPU
+tests that pin ``oracle/dladmm_oracle.py`` to the reference, and by ``bench.py``'s reference legs.
+``/root/reference`` does not exist on the GPU box: there the loader finds the byte copies that
+``oracle/fetch_ref.py`` staged under ``oracle/_ref/`` (git-ignored), if any.
 
 The reference scripts hard-code ``.cuda()`` in ``DLADMMNet.__init__`` (e.g.
 main_syn_l1l1_scalar.py:40-44) and most of them run training at import time, so the class is
@@ -20,7 +21,19 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("DLADMM_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """$DLADMM_REFERENCE_ROOT, else /root/reference (build container), else oracle/_ref (the files oracle/fetch_ref.py staged,
+    which travel to the GPU box)."""
+    env = os.environ.get("DLADMM_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if not os.path.isfile("/root/reference/main_syn_l1l1_scalar.py") and os.path.isfile(os.path.join(staged, "main_syn_l1l1_scalar.py")):
+        return staged
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 # variant name -> reference script that declares the class (SURVEY.md section 2)
 VARIANT_FILES = {

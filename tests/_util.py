@@ -118,3 +118,37 @@ class SgGolden(object):
     def kwargs(self):
         return dict(continued=self.continued, num_iter=self.num_iter, delta=self.delta, mu_k_method=self.method,
                     mu_k_param=self.param, alpha=self.alpha)
+
+
+class ElzGolden(object):
+    """A fixture written by oracle/make_golden_safeguard_newS.py (reference test_syn_l1l1_newS_Acols.py outputs):
+    Z/E/L hold K+1 entries (initial variables first), there is no T list."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        t = lambda k: torch.from_numpy(z[k].copy())
+        self.A, self.X = t("A"), t("X")
+        self.m, self.d = self.A.shape
+        self.B = self.X.shape[1]
+        self.lip, self.layers, self.alpha = float(z["lip"]), int(z["layers"]), float(z["alpha"])
+        self.use_learned, self.use_safeguard = bool(z["use_learned"]), bool(z["use_safeguard"])
+        self.continued, self.num_iter = bool(z["continued"]), int(z["num_iter"])
+        self.delta, self.method, self.param = float(z["delta"]), str(z["method"]), float(z["param"])
+        self.Z, self.E, self.L = t("Z"), t("E"), t("L")
+        self.sg_count = z["sg_count"].tolist()
+        self.keys = [str(k) for k in z["keys"]]
+        self.sd = {k: t("sd/" + k) for k in self.keys}
+        self.Z0, self.E0, self.L0 = torch.zeros(self.d, self.B), torch.zeros(self.m, self.B), torch.zeros(self.m, self.B)
+        if "s_norm" in z.files:
+            s, thr = t("s_norm"), t("thr")
+            self.margin = ((s - thr).abs() / thr.abs().clamp_min(1e-9)).min(dim=0).values
+        else:
+            self.margin = torch.full((self.B,), float("inf"))
+
+    def robust_columns(self, tol):
+        return self.margin > tol
+
+    def kwargs(self):
+        return dict(continued=self.continued, num_iter=self.num_iter, delta=self.delta, mu_k_method=self.method,
+                    mu_k_param=self.param, alpha=self.alpha)

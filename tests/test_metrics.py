@@ -1,0 +1,156 @@
+"""SURVEY.md section 8(f)-3, GPU: the per-layer loss / metric sums accumulated inside the product epilogues
+(dladmm_problem.metrics, objective_kind) and the fused LASSO training loss (dladmm_cotangents.loss_kind = 2), against
+the script-side formulas of the reference evaluated in fp64 on the returned iterates:
+main_syn_l1l1_scalar.py:289-299, main_syn_lasso_scalar.py:276-281, test_syn_l1l1_scalar.py:486-546 (NMSE),
+main_lena.py:138-147, 221-228, 262-267 (PSNR, dual gap).  Plus the stated tolerance of the bf16 operand mode."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dladmm_oracle as orc
+import dladmm_b200 as dl
+from dladmm_b200 import _lib
+from _util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(variant, m, d, B, K, seed, precision="tf32x3"):
+    torch.manual_seed(seed)
+    data = dl.gen_syn_data(B, m=m, d=d, seed=100 + seed)
+    Z0 = torch.rand(d, B, device="cuda") / d
+    E0 = torch.zeros(m, B, device="cuda"); L0 = torch.zeros(m, B, device="cuda")
+    model = dl.VARIANT_CLASSES[variant](m, 1, d, B, data.A, Z0, E0, L0, K, precision=precision)
+    return model, data
+
+
+def _dual_gap(x, a):       # main_lena.py:145-147
+    return F.softplus(x - a) + F.softplus(-x - a)
+
+
+@pytest.mark.parametrize("variant,precision,B", [("scalar", "tf32x3", 640), ("full", "tf32", 260), ("lena", "tf32x3", 20 * 13),
+                                                 ("lasso", "tf32x3", 384), ("scalar", "bf16", 512)])
+def test_fused_metrics_match_script_side_formulas(variant, precision, B):
+    m, d, K = (64, 128, 5) if variant != "lena" else (64, 96, 4)
+    if variant == "lena":
+        torch.manual_seed(1)
+        data = dl.gen_syn_data(B, m=m, d=d, seed=9)
+        z = lambda r: torch.zeros(r, 20, device="cuda")
+        model = dl.DLADMMNetLena(m, 1, d, 20, data.A, z(d), z(m), z(m), K, precision=precision)
+        rep = B // 20
+        model.Z0, model.E0, model.L0 = (t.repeat(1, rep) for t in (model.Z0, model.E0, model.L0))
+    else:
+        model, data = _case(variant, m, d, B, K, 3, precision)
+    x = data.X
+    Xc = data.X - data.E                      # the noiseless observation A Z* (PSNR ground truth role)
+    names = list(_lib.METRICS)
+    sums, outs = model.forward_metrics(x, names, Z_label=data.Z, E_label=data.E, X_clean=Xc, dual_alpha=0.45)
+    Z, E, L = outs[:3]
+    plain = model(x)
+    assert all(torch.equal(a, b) for a, b in zip(Z, plain[0])) and all(torch.equal(a, b) for a, b in zip(L, plain[2]))
+    A = data.A.double()
+    x64 = x.double()
+    tol = 3e-2 if precision == "bf16" else (3e-3 if precision == "tf32" else 2e-4)
+    for k in range(K):
+        z, e, l = Z[k].double(), E[k].double(), L[k].double()
+        az = A @ z
+        want = {"l1_z": z.abs().sum(), "sqerr_z": (data.Z.double() - z).pow(2).sum(), "l1_res": (x64 - az).abs().sum(),
+                "sq_res": (x64 - az).pow(2).sum(), "sqerr_e": (data.E.double() - e).pow(2).sum(),
+                "sqerr_az": (Xc.double() - az).pow(2).sum(), "l1_e": e.abs().sum(), "dot_lx": (l * x64).sum(),
+                "dgap_l": _dual_gap(l, 1.0).sum(), "dgap_atl": _dual_gap(A.t() @ l, 0.45).sum()}
+        for n in names:
+            got, exp = sums[n][k].item(), want[n].item()
+            scale = max(abs(exp), 1e-3 * float(m * B))
+            assert abs(got - exp) < tol * scale, (variant, precision, n, k, got, exp)
+    # the reference's derived quantities
+    nm = model.nmse_db(sums, data.Z, data.E)
+    mz = torch.stack([(data.Z - Z[k]).pow(2).sum() for k in range(K)]) / B
+    me = torch.stack([(data.E - E[k]).pow(2).sum() for k in range(K)]) / B
+    nm_ref = 10 * torch.log10(mz / (data.Z.pow(2).sum() / B) + me / (data.E.pow(2).sum() / B))      # test_syn_l1l1_scalar.py:537-541
+    assert torch.allclose(nm, nm_ref, atol={"bf16": 0.05, "tf32": 0.02}.get(precision, 2e-3))
+    ps = model.psnr_db(sums, Xc.numel())
+    ps_ref = torch.stack([-10 * torch.log10(F.mse_loss(255 * Xc, 255 * (data.A @ Z[k]))) + 48.131 for k in range(K)])
+    assert torch.allclose(ps, ps_ref, atol={"bf16": 0.1, "tf32": 0.03}.get(precision, 5e-3))
+    dg = model.dual_gap_loss(sums, 0.45, B)
+    dg_ref = torch.stack([0.45 * Z[k].abs().mean() + E[k].abs().mean() + _dual_gap(data.A.t() @ L[k], 0.45).mean()
+                          + _dual_gap(L[k], 1).mean() + (L[k] * x).mean() for k in range(K)])          # main_lena.py:221-228
+    assert torch.allclose(dg, dg_ref, rtol=5e-2 if precision == "bf16" else 2e-3, atol=1e-4)
+
+
+def test_metrics_with_last_only_and_subset():
+    model, data = _case("scalar", 64, 128, 1024, 6, 4)
+    sums, outs = model.forward_metrics(data.X, ["l1_res", "sqerr_z"], Z_label=data.Z, last_only=True)
+    full, _ = model.forward_metrics(data.X, ["l1_res", "sqerr_z"], Z_label=data.Z)
+    assert torch.equal(sums["l1_res"], full["l1_res"]) and torch.equal(sums["sqerr_z"], full["sqerr_z"])
+    assert len(outs[0]) == 1
+    with pytest.raises(RuntimeError, match="Z_label"):
+        model.forward_metrics(data.X, ["sqerr_z"])
+    with pytest.raises(ValueError):
+        model.forward_metrics(data.X, ["nope"])
+    fp = dl.DLADMMNetScalar(64, 1, 128, 1024, data.A, model.Z0, model.E0, model.L0, 6, precision="fp32")
+    with pytest.raises(RuntimeError, match="tensor-core"):
+        fp.forward_metrics(data.X, ["l1_res"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("variant", ["lasso", "scalar"])
+def test_fused_lasso_loss_and_gradients_against_fp64_autograd(variant, precision):
+    """model.lasso_loss: value from the forward epilogues (objective_kind 2) and parameter gradients from the backward with
+    loss_kind 2, against fp64 autograd of the oracle on the script's loss (main_syn_lasso_scalar.py:276-281)."""
+    m, d, B, K = 48, 96, 516, 4
+    model, data = _case(variant, m, d, B, K, 8, precision)
+    w = [0.6 ** (K - 1 - k) for k in range(K)]
+    alpha = 0.02
+    loss, outs = model.lasso_loss(data.X, alpha, w)
+    loss.backward()
+    d64 = lambda t: t.detach().double().cpu()
+    sd = {k: d64(v) for k, v in model.state_dict().items()}
+    A, X = d64(data.A), d64(data.X)
+
+    def loss_fn(Z, E, L, T):
+        return sum(w[k] * (alpha * Z[k].abs().sum(dim=0).mean() + 0.5 * (X - A.mm(Z[k])).pow(2).sum(dim=0).mean()) for k in range(K))
+
+    lref, gref = orc.autograd_grads(variant, sd, A, X, d64(model.Z0), d64(model.E0), d64(model.L0), K, loss_fn)
+    assert abs(loss.item() - float(lref)) < 5e-5 * abs(float(lref))
+    G = max(float(v.norm()) for n, v in gref.items() if not n.startswith("fc"))
+    for n, p in model.named_parameters():
+        floor = 1e-2 * G if not n.startswith("fc") else 1e-5
+        assert rel_l2(p.grad.cpu(), gref[n], floor=floor) < 5e-3, (variant, precision, n)
+
+
+def test_loss_normalisation_with_global_batch():
+    model, data = _case("scalar", 32, 64, 128, 3, 2)
+    l1, _ = model.l1l1_loss(data.X, 0.01)
+    l2, _ = model.l1l1_loss(data.X, 0.01, global_batch=512)
+    assert abs(l2.item() * 4 - l1.item()) < 1e-5 * abs(l1.item())
+    l1.backward()
+    g1 = [p.grad.clone() for p in model.parameters()]
+    for p in model.parameters():
+        p.grad = None
+    l2.backward()
+    for a, p in zip(g1, model.parameters()):
+        assert torch.allclose(p.grad * 4, a, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("variant", ["scalar", "full", "lasso", "ltheta"])
+def test_bf16_mode_stated_tolerance(variant):
+    """DLADMM_PREC_BF16: tcgen05 kind::f16 on bf16 operands (iterates stay fp32).  Stated tolerance: per-layer relative L2
+    error of the iterates <= 3e-2 against the fp64 oracle at K = 6 (each product carries ~4e-3 relative error; tf32x3 on the
+    same case is <= 2e-5), and the same result as the tf32 mode to that tolerance."""
+    m, d, B, K = 250, 500, 1028, 6
+    model, data = _case(variant, m, d, B, K, 5, "bf16")
+    with torch.no_grad():
+        out = model(data.X)
+    d64 = lambda t: t.detach().double().cpu()
+    sd = {k: d64(v) for k, v in model.state_dict().items()}
+    ref = orc.forward(variant, sd, d64(data.A), d64(data.X), d64(model.Z0), d64(model.E0), d64(model.L0), K)
+    worst = 0.0
+    for i in range(3):
+        for k in range(K):
+            worst = max(worst, rel_l2(out[i][k].cpu(), ref[i][k], floor=1e-2 * B ** 0.5))
+    assert worst < 3e-2, worst
+    assert worst > 1e-5            # (it really is the bf16 arithmetic)
+    # training through the bf16 forward: the backward runs single-pass tf32 on the saved fp32 iterates
+    loss, _ = model.l1l1_loss(data.X, 0.01) if variant in ("scalar", "full") else (sum(z.abs().sum() for z in model(data.X)[0]) / B, None)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())

@@ -90,7 +90,7 @@ def test_newS_forward_and_gradients_match_reference_on_gpu(name, precision):
 @pytest.mark.gpu
 def test_newS_objective_and_loss_follow_the_variant_conventions():
     """forward_objective / l1l1_loss on a newS module: the objective depends on Z_k only (identical lists), the returned
-    E / L lists use the variant's own shifted convention, and the family-B safeguard entry points refuse the variant."""
+    E / L lists use the variant's own shifted convention, and the Z -> E -> L safeguard entry points refuse the variant."""
     g = NewSGolden("newS_small")
     model = g.build("cuda")
     x = g.X.cuda()
@@ -104,5 +104,5 @@ def test_newS_objective_and_loss_follow_the_variant_conventions():
     assert rel_l2(obj, exp) < 1e-4
     loss, outs = model.l1l1_loss(x, 0.01)
     assert len(outs) == 3 and abs(loss.item() - exp.sum().item() / x.shape[1]) < 1e-4 * abs(loss.item())
-    with pytest.raises(NotImplementedError):
-        model.forward_safeguarded(x, True, True)
+    with pytest.raises(NotImplementedError):        # the Z -> E -> L entry points refuse the E -> L -> Z variants (and vice versa)
+        model.KM(model.Z0, model.E0, model.L0, model.E0, x)

@@ -16,8 +16,8 @@ def make(B, off):
 def grads(model, data, total_B, sync, post):
     model.zero_grad(set_to_none=True)
     model.sync_gradients(sync)
-    loss, _ = model.l1l1_loss(data.X, 0.01)
-    (loss * data.X.shape[1] / total_B).backward()          # normalise by the GLOBAL batch
+    loss, _ = model.l1l1_loss(data.X, 0.01, global_batch=total_B)     # mean over the GLOBAL batch (the default when sync is on)
+    loss.backward()
     if post:
         dl.allreduce_gradients(list(model.parameters()))
     return [p.grad.clone() for p in model.parameters()]
