@@ -60,10 +60,14 @@ def test_forward_backward_against_fp64_oracle_at_config_size(variant, K, B):
     sd = {k: d64(v) for k, v in model.state_dict().items()}
     A, X = d64(data.A), d64(data.X)
     ref = orc.forward(variant, sd, A, X, d64(Z0), d64(E0), d64(L0), K)
+    # Stated tolerance of tf32x3 at config depth (profiles/r02_precision_table.md): one product is exact to ~2e-6 (K=250) /
+    # ~4e-6 (K=500) -- the tensor core's fp32 accumulator rounds toward zero on every MMA, a BIAS, linear in K -- and because
+    # the bias is coherent from layer to layer the iterate error grows with depth: <= 1e-5 in the first layers, ~1e-4 at
+    # k = 14..19 (the reference's own fp32 arithmetic stays at 6e-7).  A wrong kernel is off by O(1).
     for name, got, exp in (("Z", outs[0], ref[0]), ("E", outs[1], ref[1]), ("L", outs[2], ref[2])):
         for k in range(K):
             err = rel_l2(got[k].cpu(), exp[k], floor=1e-2 * (B ** 0.5))
-            assert err < 2e-5, (variant, name, k, err)
+            assert err < (2e-5 if k < 3 else 3e-4), (variant, name, k, err)
 
     def loss_fn(Z, E, L, T, Xc):
         if lasso:
@@ -71,7 +75,7 @@ def test_forward_backward_against_fp64_oracle_at_config_size(variant, K, B):
         return sum(w[k] * (alpha * Z[k].abs().sum() + (Xc - A.mm(Z[k])).abs().sum()) for k in range(K)) / B
 
     lref, gref = _oracle_grads_chunked(variant, sd, A, X, d64(Z0), d64(E0), d64(L0), K, loss_fn)
-    assert abs(loss.item() - lref) < 2e-5 * abs(lref), (loss.item(), lref)
+    assert abs(loss.item() - lref) < 1e-4 * abs(lref), (loss.item(), lref)
     # scalar gradients can be sums that cancel to a small fraction of their terms: judge them against the largest
     # gradient of their kind too.  Prox masks / sign(residual) within rounding of a threshold flip between fp32 and
     # fp64 (a handful of 2.5 M elements), which moves a gradient by ~1e-3 relative; a wrong kernel is off by O(1).
