@@ -41,6 +41,12 @@ F_GEMM_PER_COL = 2.0 * M * D                      # one (d x m)(m x 1) or (m x d
 # (profiles/r01_ncu_full_summary_v7.md; a training-mode launch: it also writes the 1-byte prox masks, 16.4 MB for `gemm_elt`
 # and 32.8 MB for `gemm_z`, which the inference launch timed here does not), keyed by (precision, kernel kind)
 TRAFFIC_NCU = {("tf32x3", "gemm_elt"): 332.131072e6 + 228.349184e6, ("tf32x3", "gemm_z"): 197.948416e6 + 119.981056e6}
+try:      # round 2: the persistent kernel's capture (profiles/r02_ncu_persistent.json, written by tools/ncu_summary.py)
+    with open(os.path.join(ROOT, "profiles", "r02_ncu_persistent.json")) as _fh:
+        _j = json.load(_fh)
+    TRAFFIC_NCU[("tf32x3", "fwd_persistent")] = _j["dram__bytes_read.sum"] + _j["dram__bytes_write.sum"]
+except Exception:
+    pass
 
 
 def _peaks():
@@ -633,8 +639,9 @@ def run_ours(args):
         kinds = {k: v for k, v in prof.items() if v[1] > 0}
         dom = max(kinds, key=lambda k: kinds[k][0])
         dom_ms, dom_n = kinds[dom]
-        gemm_kinds = ("gemm_t0", "gemm_z", "gemm_elt")
-        flops_per_launch = F_GEMM_PER_COL * B
+        gemm_kinds = ("gemm_t0", "gemm_z", "gemm_elt", "fwd_persistent")
+        # the all-layer persistent kernel runs every product of the forward in one launch
+        flops_per_launch = F_FWD * B if dom == "fwd_persistent" else F_GEMM_PER_COL * B
         mma_passes = {"fp32": 1, "tf32": 1, "tf32x3": 3, "bf16": 1}[precision]
         # algorithmic HBM bytes per launch of each fused product kernel: the activation
         # operand + the epilogue inputs read + the outputs written (weights are L2-resident, 3xTF32 splits never
@@ -644,6 +651,9 @@ def run_ours(args):
             "gemm_z": 4.0 * B * (M + D + D),                 # V | Z_{k-1} | Z_k
             "gemm_elt": 4.0 * B * (D + 3 * M + 4 * M),       # Z_k | X, E_{k-1}, L_{k-1} | E_k, T_{k+1}, L_k, V
         }
+        # one launch of the persistent kernel = T_0 + K x (W V kernel + A Z kernel) worth of algorithmic traffic
+        bytes_per_launch["fwd_persistent"] = (bytes_per_launch["gemm_t0"] +
+                                              K_LAYERS * (bytes_per_launch["gemm_z"] + bytes_per_launch["gemm_elt"]))
         avg_ms = dom_ms / dom_n
         tensor_peak = peaks["tf32_tflops"] / mma_passes
         tensor_ach = flops_per_launch / (avg_ms * 1e-3) / 1e12 if dom in gemm_kinds else None

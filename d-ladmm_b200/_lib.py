@@ -70,7 +70,7 @@ class SgPair(C.Structure):
 
 EXPORTS = ["dladmm_sg_norm", "dladmm_sg_select", "dladmm_sg_norm_elz", "dladmm_sg_select_update", "dladmm_workspace_bytes", "dladmm_forward", "dladmm_backward", "dladmm_gen_workspace_bytes",
            "dladmm_gen_syn", "dladmm_objective", "dladmm_query", "dladmm_last_error", "dladmm_launch_count",
-           "dladmm_profile_start", "dladmm_profile_stop"]
+           "dladmm_profile_start", "dladmm_profile_stop", "dladmm_debug_trace"]
 
 KIND_NAMES = ["prep", "gemm_t0", "gemm_z", "gemm_elt", "bwd_elem", "bwd_gemm_dz", "bwd_gemm_dw", "bwd_gemm_dv",
               "bwd_reduce", "gen", "objective", "metric_gemm", "safeguard", "fwd_persistent"]
@@ -120,6 +120,8 @@ def load():
     lib.dladmm_profile_start.argtypes = []
     lib.dladmm_profile_stop.restype = C.c_int
     lib.dladmm_profile_stop.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.dladmm_debug_trace.restype = C.c_int64
+    lib.dladmm_debug_trace.argtypes = [C.POINTER(C.c_int64), C.c_int64]
     lib.dladmm_last_error.restype = C.c_char_p
     lib.dladmm_last_error.argtypes = []
     _lib = lib

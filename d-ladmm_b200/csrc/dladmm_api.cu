@@ -326,6 +326,8 @@ int dladmm_profile_stop(double* ms_by_kind, int64_t* launches_by_kind) {
   return rc;
 }
 
+int64_t dladmm_debug_trace(int64_t* host_out, int64_t capacity) { return pf_trace_read((long long*)host_out, (long long)capacity); }
+
 int dladmm_query(int device, dladmm_caps* caps) {
   if (!caps) { set_error("caps is NULL"); return DLADMM_ERR_INVALID; }
   memset(caps, 0, sizeof(*caps));

@@ -162,6 +162,7 @@ static inline M1Args make_m1(const dladmm_problem* p, const dladmm_cotangents* g
 bool umma_eligible(const dladmm_problem* p);
 size_t umma_workspace_bytes(const dladmm_problem* p, int for_backward);
 int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st);
+int pf_trace_read(long long* host_out, long long capacity);
 int umma_backward(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& sw, void* ws_base, cudaStream_t st);
 
 }  // namespace dladmm

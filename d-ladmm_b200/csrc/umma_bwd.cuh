@@ -15,20 +15,68 @@ namespace umma {
 //   !PS: one entry per (32-column group, feature row)                     -> part[(slot * ngroups + group) * prow + row]
 struct RedOut { float* part; int nentries; int ngroups; int prow; };
 
-template <bool PS>
-__device__ __forceinline__ void red_contrib(const BP& q, const RedOut& ro, int slot, float& acc, int row, i64 col, i64 group,
-                                            bool ok, float val, int lane) {
-  if (PS) {                                         // every parameter is a (1,1) scalar: register accumulation only
-    acc += ok ? val : 0.f;                          // (entries of parameters without a gradient are never read back)
-    return;
+// Sums over the 32 lanes of N values per lane in N-1 + log2(32/N) shuffles (a warp_sum per value would take 5 N): at
+// every stage a lane keeps one half of its values and hands the other half to its partner.  Returns, in lane l, the total
+// of value index  l >> (5 - log2 N)  (N = 32: lane l owns value l; N = 8: four lanes share each value).  N a power of two.
+template <int N>
+__device__ __forceinline__ float warp_multi_sum(float (&x)[N], int lane) {
+  int s = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = up ? x[j] : x[j + n / 2];
+      const float keep = up ? x[j + n / 2] : x[j];
+      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
   }
-  if (q.g == nullptr) return;                       // warp-uniform
-  if (q.period) {                                   // per-slot parameter (main_lena.py:35-36): direct accumulation
-    if (ok) atomicAdd(q.g + (i64)row * q.rs + col % q.period, val);
-    return;
+  float v = x[0];
+#pragma unroll
+  for (; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+// One parameter-gradient contribution of element (row i of the chunk, this lane's column).
+//   PS  : register accumulation (st.red[IDX]), reduced once per kernel (red_finish).
+//   !PS : stashed in st.rv[i * NRED + IDX]; red_flush reduces the chunk's CHUNK x NRED values over the warp's 32 columns with
+//         one multi-value butterfly and writes one partial per (slot, 32-column group, row).
+template <bool PS, int IDX, int NRED, class State>
+__device__ __forceinline__ void red_put(State& st, const BP& q, int i, int row, i64 col, bool ok, float val) {
+  if constexpr (PS) {                               // every parameter is a (1,1) scalar
+    st.red[IDX] += ok ? val : 0.f;                  // (entries of parameters without a gradient are never read back)
+  } else {
+    if (q.g == nullptr) return;                     // warp-uniform
+    if (q.period) {                                 // per-slot parameter (main_lena.py:35-36): direct accumulation
+      if (ok) atomicAdd(q.g + (i64)row * q.rs + col % q.period, val);
+      return;
+    }
+    st.rv[i * NRED + IDX] = ok ? val : 0.f;
   }
-  const float s = warp_sum(ok ? val : 0.f);
-  if (lane == 0) ro.part[((i64)slot * ro.ngroups + group) * ro.prow + row] = s;
+}
+template <int NRED>
+__device__ __forceinline__ uint32_t red_mask(const BP* const (&qs)[NRED]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int r = 0; r < NRED; ++r) m |= (qs[r]->g != nullptr && qs[r]->p != nullptr && qs[r]->period == 0) ? (1u << r) : 0u;
+  return m;
+}
+template <bool PS, int NRED, int CHUNK, int NPOW, class State>
+__device__ __forceinline__ void red_flush(State& st, const RedOut& ro, const int (&slots)[NRED], uint32_t gmask, int row0, int n_feat,
+                                          i64 group, int lane) {
+  if constexpr (!PS) {
+    if (gmask == 0) return;                         // warp-uniform: no per-row gradient is wanted
+    const float v = warp_multi_sum<NPOW>(st.rv, lane);
+    constexpr int SH = 5 - ilog2(NPOW);
+    const int idx = lane >> SH;
+    if ((lane & ((1 << SH) - 1)) != 0 || idx >= CHUNK * NRED) return;
+    const int i = idx / NRED, r = idx % NRED, row = row0 + i;
+    int slot = slots[0];
+#pragma unroll
+    for (int k = 1; k < NRED; ++k) slot = r == k ? slots[k] : slot;
+    if (row < n_feat && ((gmask >> r) & 1u)) ro.part[((i64)slot * ro.ngroups + group) * ro.prow + row] = v;
+  }
 }
 
 template <bool PS, int NRED>
@@ -50,7 +98,7 @@ struct UEpiBG1 {
   static constexpr int WARPS = 16;                 // measured: 1.97 -> 1.67 ms per 15 layers against 8 warps
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 3;                    // gZ_k, carried dZ, Z_k (fused loss) -- each optional
-  struct State { float red[1]; int lane; float lsc; int o_gz, o_cz, o_zk, o_mk; };
+  struct State { float red[1]; float rv[PS ? 1 : CHUNK]; uint32_t gmask; int lane; float lsc; int o_gz, o_cz, o_zk, o_mk; };
   struct Pre { unsigned mk[CHUNK]; };
   const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
   BP th1; float* dx1; RedOut ro; i64 B;
@@ -58,8 +106,10 @@ struct UEpiBG1 {
   uint32_t in_mask;
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = gZ; p[1] = cZin; p[2] = lscale ? Zk : nullptr; }
   const uint8_t* host_mask() const { return maskZ; }
+  static constexpr int NROWP = 0;
   __device__ __forceinline__ void begin(State& st) const {
     st.red[0] = 0.f; st.lane = threadIdx.x & 31;
+    { const BP* const qs[1] = {&th1}; st.gmask = red_mask<1>(qs); }
     st.lsc = lscale ? lz * __ldg(lscale) : 0.f;
     st.o_gz = slot_rank(in_mask, 0) * SUBF(CHUNK); st.o_cz = slot_rank(in_mask, 1) * SUBF(CHUNK); st.o_zk = slot_rank(in_mask, 2) * SUBF(CHUNK);
     st.o_mk = (in_mask & EIN_MASK_BIT) ? __popc(in_mask & ~EIN_MASK_BIT) * SUBF(CHUNK) * 4 : -1;   // byte offset of the staged mask
@@ -79,6 +129,10 @@ struct UEpiBG1 {
   template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64 group) const {
+    if constexpr (!PS) {
+#pragma unroll
+      for (int i = 0; i < CHUNK; ++i) st.rv[i] = 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
@@ -92,9 +146,10 @@ struct UEpiBG1 {
       const unsigned mk = st.o_mk >= 0 ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
       const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
-      red_contrib<PS>(th1, ro, SL_TH1, st.red[0], row, b, group, ok, dz * (mn - mp), st.lane);
+      red_put<PS, 0, 1>(st, th1, i, row, b, ok, dz * (mn - mp));
       if (ok) dx1[off] = o;
     }
+    { const int slots[1] = {SL_TH1}; red_flush<PS, 1, CHUNK, CHUNK>(st, ro, slots, st.gmask, row0, n_feat, group, st.lane); }
   }
 };
 
@@ -106,7 +161,7 @@ struct UEpiBG2 {
   static constexpr int CHUNK = 4;     // up to 7 staged arrays + mask per element: keep one ring slot small (depth >= EPI_PARTS)
   static constexpr int NIN = 7;    // L_{k-1} (tied), T_k, cL | cE, E_{k-1}, L_{k-2}, E_{k-2}(B)   (the last four only below the top layer)
                                    // upstream cotangents gL, gE, gT (generic autograd path only) are read straight from global memory
-  struct State { float red[6]; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };
+  struct State { float red[6]; float rv[PS ? 1 : 32]; uint32_t gmask; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };
   struct Pre { unsigned mk[CHUNK]; };
   // layer k
   const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
@@ -127,6 +182,15 @@ struct UEpiBG2 {
     p[6] = (has_prev && FAM == DLADMM_FAMILY_B) ? Ep : nullptr;
   }
   const uint8_t* host_mask() const { return (has_prev && FAM != DLADMM_FAMILY_C) ? maskE : nullptr; }
+  static constexpr int NROWP = PS ? 0 : 5;
+  __device__ __forceinline__ void row_params(BP (&q)[5]) const { q[0] = b1; q[1] = bL; q[2] = b2; q[3] = ss2; q[4] = ss2_2; }
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const {
+    if (have & 1u) st.b1.tab = tab;
+    if (have & 2u) st.bL.tab = tab + n;
+    if (have & 4u) st.b2.tab = tab + 2 * n;
+    if (have & 8u) st.ss2.tab = tab + 3 * n;
+    if (have & 16u) st.ss2_2.tab = tab + 4 * n;
+  }
   __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
     for (int r = 0; r < 6; ++r) st.red[r] = 0.f;
@@ -134,6 +198,11 @@ struct UEpiBG2 {
     st.s1 = ss1.p ? __ldg(ss1.p) : 1.f;
     st.lane = threadIdx.x & 31;
     st.lsc = lscale ? lw * __ldg(lscale) : 0.f;
+    {   // order of st.red / st.rv entries: bL, th2, ss2 (C: ss2_1), b2 (C: ss2_2), b1, ss1
+      const BP* const qs[6] = {&bL, &th2, &ss2, FAM == DLADMM_FAMILY_C ? &ss2_2 : &b2, &b1, &ss1};
+      st.gmask = red_mask<6>(qs);
+      if (!has_prev) st.gmask &= 0x30u;             // top layer of the chain: only b1 / ss1 get a contribution here
+    }
 #pragma unroll
     for (int i = 0; i < NIN; ++i) st.o[i] = slot_rank(in_mask, i) * SUBF(CHUNK);
     st.o_mk = (in_mask & EIN_MASK_BIT) ? __popc(in_mask & ~EIN_MASK_BIT) * SUBF(CHUNK) * 4 : -1;
@@ -164,6 +233,17 @@ struct UEpiBG2 {
   template <bool FAST>
   __device__ __forceinline__ void rows(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                        const float (&v)[CHUNK], int n_feat, i64 group) const {
+    if constexpr (!PS) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) st.rv[i] = 0.f;
+    }
+    rows_body<FAST>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+    const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
+    red_flush<PS, 6, CHUNK, 32>(st, ro, slots, st.gmask, row0, n_feat, group, st.lane);
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void rows_body(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
+                                            const float (&v)[CHUNK], int n_feat, i64 group) const {
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
@@ -174,8 +254,8 @@ struct UEpiBG2 {
       const float lp = in(st, slot, 0, i, col), tk = in(st, slot, 1, i, col);
       const float var = lp + vb1 * tk;                // V_k recomputed
       const float dV = -st.s1 * v[i];
-      red_contrib<PS>(b1, ro, SL_B1, st.red[4], row, b, group, ok, dV * tk, st.lane);
-      red_contrib<PS>(ss1, ro, SL_SS1, st.red[5], row, b, group, ok, -var * v[i], st.lane);
+      red_put<PS, 4, 6>(st, b1, i, row, b, ok, dV * tk);
+      red_put<PS, 5, 6>(st, ss1, i, row, b, ok, -var * v[i]);
       float dL = in(st, slot, 2, i, col) + dV;
       float dT = vb1 * dV;
       if (!FAST && !has_prev) continue;             // warp-uniform
@@ -187,7 +267,7 @@ struct UEpiBG2 {
       const float tn = tk, ek = in(st, slot, 4, i, col), lpp = in(st, slot, 5, i, col);
       if (lscale) { const float r = ek - tn; const float sl = st.lsc * (lkind == 2 ? r : sgn(r)); dE += sl; dT -= sl; }
       const float vbL = st.bL.at(row, b);
-      red_contrib<PS>(bL, ro, SL_BL, st.red[0], row, b, group, ok, dL * tn, st.lane);
+      red_put<PS, 0, 6>(st, bL, i, row, b, ok, dL * tn);
       const float dTt = dT + vbL * dL;
       const float dEt = dE + dTt;
       float dRv, nE, nL;
@@ -199,23 +279,23 @@ struct UEpiBG2 {
         const float q = lpp + vb2 * that;
         const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
         const float du = dEt * (mp + mn);
-        red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
+        red_put<PS, 1, 6>(st, th2, i, row, b, ok, dEt * (mn - mp));
         const float dQ = -vs2 * du;
-        red_contrib<PS>(ss2, ro, SL_SS2, st.red[2], row, b, group, ok, -du * q, st.lane);
+        red_put<PS, 2, 6>(st, ss2, i, row, b, ok, -du * q);
         const float dThat = vb2 * dQ;
-        red_contrib<PS>(b2, ro, SL_B2, st.red[3], row, b, group, ok, dQ * that, st.lane);
+        red_put<PS, 3, 6>(st, b2, i, row, b, ok, dQ * that);
         dRv = dTt + dThat; nE = du + dThat; nL = dL + dQ;
       } else if (FAM == DLADMM_FAMILY_A) {
         const float vb2 = st.b2.at(row, b);
         const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
         const float du = dEt * (mp + mn);
-        red_contrib<PS>(th2, ro, SL_TH2, st.red[1], row, b, group, ok, dEt * (mn - mp), st.lane);
-        red_contrib<PS>(b2, ro, SL_B2, st.red[3], row, b, group, ok, -du * lpp, st.lane);
+        red_put<PS, 1, 6>(st, th2, i, row, b, ok, dEt * (mn - mp));
+        red_put<PS, 3, 6>(st, b2, i, row, b, ok, -du * lpp);
         dRv = dTt - du; nE = 0.f; nL = dL - vb2 * du;
       } else {
         const float v1 = st.ss2.at(row, b), v2 = st.ss2_2.at(row, b);
-        red_contrib<PS>(ss2, ro, SL_SS2, st.red[2], row, b, group, ok, dEt * (ek - tn), st.lane);
-        red_contrib<PS>(ss2_2, ro, SL_B2, st.red[3], row, b, group, ok, -dEt * lpp, st.lane);
+        red_put<PS, 2, 6>(st, ss2, i, row, b, ok, dEt * (ek - tn));
+        red_put<PS, 3, 6>(st, ss2_2, i, row, b, ok, -dEt * lpp);
         dRv = dTt - v1 * dEt; nE = 0.f; nL = dL - v2 * dEt;
       }
       if (ok) {

@@ -26,21 +26,24 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 // a broadcast parameter resolved once per kernel: scalars live in a register, per-row / per-slot ones are read
 // through the read-only path (warp-uniform address when there is no column period)
 // PSCALAR = every parameter of the call is a (1,1) scalar (scalar / tied / lasso variants): no loads, less code.
+// Per-row parameters ((rows,1): the full / ltheta variants) are copied once per kernel into a small shared-memory table by the
+// epilogue warps (`tab`, see umma_gemm.cuh): with ~220 KB of the SM's 228 KB configured as shared memory the L1 is a few KB
+// and a __ldg per row and parameter missed it most of the time (measured: the A Z kernel of `full` 0.32 ms vs 0.12 ms scalar).
 template <bool PSCALAR>
 struct PV {
-  const float* p; int rs; int period; float s;
+  const float* p; int rs; int period; float s; const float* tab;
   __device__ __forceinline__ void init(const BP& q) {
-    p = q.p; rs = q.rs; period = q.period;
+    p = q.p; rs = q.rs; period = q.period; tab = nullptr;
     s = (q.p && q.rs == 0 && q.period == 0) ? __ldg(q.p) : 0.f;
   }
   __device__ __forceinline__ float at(int row, i64 col) const {
     if (PSCALAR) return s;
+    if (tab) return tab[row];                       // warp-uniform address: one broadcast read
     i64 off = (i64)row * rs;
     if (period) off += col % period;
     return __ldg(p + off);
   }
 };
-
 __host__ __device__ constexpr int SUBF(int chunk) { return chunk * TILE_B; }   // floats of one staged array of one chunk
 
 struct NoPre {};
@@ -58,6 +61,9 @@ struct UEpiT0 {
   __nv_bfloat16* __restrict__ Vh; i64 ldh;         // bf16 mode: the W V operand as bf16 (pitch ldh)
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = E0; p[1] = X; p[2] = L0; }
   const uint8_t* host_mask() const { return nullptr; }
+  static constexpr int NROWP = PSCALAR ? 0 : 1;
+  __device__ __forceinline__ void row_params(BP (&q)[1]) const { q[0] = b1; }
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const { if (have & 1u) st.b1.tab = tab; }
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
@@ -97,6 +103,9 @@ struct UEpiZ {
   __nv_bfloat16* __restrict__ Zh; i64 ldh;         // bf16 mode: Z_k as bf16, the operand of the A Z product
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; p[1] = sq_part ? Zlabel : nullptr; }
   const uint8_t* host_mask() const { return nullptr; }
+  static constexpr int NROWP = PSCALAR ? 0 : 1;
+  __device__ __forceinline__ void row_params(BP (&q)[1]) const { q[0] = th1; }
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const { if (have & 1u) st.th1.tab = tab; }
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; st.obj = 0.f; st.sq = 0.f; }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     if (obj_part) {
@@ -158,6 +167,16 @@ struct UEpiELT {
     if (MET) { p[3] = Elabel; p[4] = Xclean; }
   }
   const uint8_t* host_mask() const { return nullptr; }
+  static constexpr int NROWP = PSCALAR ? 0 : 6;
+  __device__ __forceinline__ void row_params(BP (&q)[6]) const { q[0] = b2; q[1] = ss2; q[2] = ss2_2; q[3] = th2; q[4] = bL; q[5] = b1n; }
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const {
+    if (have & 1u) st.b2.tab = tab;
+    if (have & 2u) st.ss2.tab = tab + n;
+    if (have & 4u) st.ss2_2.tab = tab + 2 * n;
+    if (have & 8u) st.th2.tab = tab + 3 * n;
+    if (have & 16u) st.bL.tab = tab + 4 * n;
+    if (have & 32u) st.b1n.tab = tab + 5 * n;
+  }
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);
     st.obj = 0.f;
@@ -239,6 +258,7 @@ struct UEpiDgap {
   float a; float* part; uint32_t in_mask;
   void host_inputs(const float* (&)[MAX_EIN]) const {}
   const uint8_t* host_mask() const { return nullptr; }
+  static constexpr int NROWP = 0;
   __device__ __forceinline__ void begin(State& st) const { st.s = 0.f; }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const float s = warp_sum(st.s);

@@ -109,6 +109,25 @@ __device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* small, i
   for (int i = 0; i < N; ++i)
     dst[tid + i * NTHREADS] = make_float4(tf32_small(v[i].x), tf32_small(v[i].y), tf32_small(v[i].z), tf32_small(v[i].w));
 }
+// Single-pass TF32: the tensor core TRUNCATES fp32 operands to tf32 -- a bias toward zero that is coherent from layer to layer
+// (measured: 7.7e-4 per product, but 2.2e-2 on the iterates after 15 layers; bf16 operands rounded to nearest: 2.4e-3 per
+// product, 5.6e-3 after 15 layers).  The splitter warps therefore round the activation tile to the nearest tf32 in place.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+template <int BYTES, int NTHREADS>
+__device__ __forceinline__ void round_tile(uint8_t* raw, int tid) {
+  constexpr int N = BYTES / 16 / NTHREADS;
+  static_assert(N * 16 * NTHREADS == BYTES, "tile bytes must be a multiple of 16 * threads");
+  float4* p = reinterpret_cast<float4*>(raw);
+  float4 v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = p[tid + i * NTHREADS];
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[tid + i * NTHREADS] = make_float4(tf32_rn(v[i].x), tf32_rn(v[i].y), tf32_rn(v[i].z), tf32_rn(v[i].w));
+}
 // Programmatic dependent launch: a kernel launched with programmatic stream serialization may become resident while its
 // predecessor drains; everything that reads or writes global memory sits behind grid_dep_wait().
 __device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -297,7 +316,8 @@ struct SmemPlan {
   static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
   static constexpr int STAGES = 3;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int ROWTAB = 8192;                                  // per-row parameter table of the epilogue (umma_epilogues.cuh)
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + ROWTAB + 1024;   // + alignment slack
 };
 constexpr int MAX_RING_DEPTH = 36;
 
@@ -316,6 +336,21 @@ struct RingPos {
     while (s >= depth) { s -= depth; ph ^= 1u; }
   }
 };
+
+// tabulate the (rows,1) parameters among q[0..NP) -- called by all epilogue threads (etid of nthr); returns the bit mask of the
+// tabulated ones; the caller synchronises the epilogue warps before the table is read
+template <int NP>
+__device__ __forceinline__ uint32_t fill_rowtab(const BP (&q)[NP], float* tab, int n_feat, int n_pad, int etid, int nthr) {
+  uint32_t have = 0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    if (q[i].p == nullptr || q[i].period != 0 || q[i].rs != 1) continue;      // absent, per batch slot, or a scalar
+    have |= 1u << i;
+    for (int r = etid; r < n_pad; r += nthr) tab[i * n_pad + r] = r < n_feat ? __ldg(q[i].p + r) : 0.f;
+  }
+  return have;
+}
+
 
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(roles_threads(Epi::WARPS), 1)
@@ -348,6 +383,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* efull = bars + 3 * STAGES + 4;                   // [MAX_RING_DEPTH]
   uint64_t* eempty = bars + 3 * STAGES + 4 + MAX_RING_DEPTH;  // [MAX_RING_DEPTH]
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4 + 2 * MAX_RING_DEPTH);
+  float* rowtab = (float*)(ring + RING_BYTES + Plan::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 ntiles = gs.n_tiles;
@@ -451,17 +487,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t db_small = desc_at(b_hi, b_lo + (Plan::B_BYTES >> 4) + ks * (32 >> 4));
               umma_tf32(d_tmem, da_big, db_small, idesc, first);
               umma_tf32(d_tmem, da_big, db_big, idesc, 1u);
-            } else {
+            } else if (NPASS == 2) {
               umma_op<BF>(d_tmem, da_big, db_big, idesc, first);
             }
           }
         }
         __syncwarp();
-        if (NPASS == 3) {
-          mbar_wait(&ready[s], ph);                    // small part of the activation tile written by the splitters
+        if (NPASS == 3 || NPASS == 1) {
+          mbar_wait(&ready[s], ph);                    // small part written (3 passes) / tile rounded to tf32 (1 pass) by the splitters
           tc_fence_after();
         }
         if (elect_one()) {
+          if (NPASS == 1) {
+#pragma unroll
+            for (int ks = 0; ks < KC / MMA_K; ++ks)
+              umma_tf32(d_tmem, desc_at(a_hi, a_lo + ks * (A_KSTEP >> 4)), desc_at(b_hi, b_lo + ks * (32 >> 4)), idesc,
+                        (kc == 0 && ks == 0) ? 0u : 1u);
+          }
           if (NPASS == 3) {
 #pragma unroll
             for (int ks = 0; ks < KC / MMA_K; ++ks) {
@@ -517,7 +559,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= SPLIT_WARP0) {
     // ===== operand splitters (3-pass mode): small = x - trunc_tf32(x) of the activation tile, in shared memory =====
-    if (NPASS == 3) {
+    if (NPASS == 3 || NPASS == 1) {
       const int tid = threadIdx.x - SPLIT_WARP0 * 32;
       int s = 0; uint32_t ph = 0; int trs = 0; (void)trs;
       for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -525,7 +567,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full[s], ph);                       // TMA bytes landed; the stage was free (producer waited on empty)
           if (tid == 0) UMMA_TR(gs, trs, 2);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          split_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, tid);
+          if (NPASS == 3) split_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, tid);
+          else round_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, tid);
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
           __syncwarp();
           if (tid == 0) UMMA_TR(gs, trs, 3);
@@ -542,6 +585,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
+    if constexpr (Epi::NROWP > 0) {
+      // per-row parameters of this launch -> shared memory, once (the epilogue warps only: named barrier 1)
+      const int n_pad = gs.n_ntiles * TILE_N;
+      if (Epi::NROWP * n_pad * 4 <= Plan::ROWTAB) {     // uniform over the grid
+        BP q[Epi::NROWP];
+        epi.row_params(q);
+        const uint32_t have = fill_rowtab<Epi::NROWP>(q, rowtab, gs.n_feat, n_pad, threadIdx.x - EPI_WARP0 * 32, EPI_WARPS * 32);
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+        epi.bind_rows(state, rowtab, n_pad, have);
+      }
+    }
     RingPos rp; rp.init(half, depth);                  // this part's chunks are every EPI_PARTS-th slot of the staging ring
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(gs, tile);
@@ -667,6 +721,25 @@ inline int make_tmap_2d(CUtensorMap* out, const float* base, i64 rows, i64 cols,
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld pitch=%lld box=%dx%d", (int)r, rows, cols, pitch, box_cols,
               box_rows);
+    return DLADMM_ERR_CUDA;
+  }
+  return DLADMM_OK;
+}
+
+// 3D fp32: `slabs` row-major (rows x cols) matrices `slab_stride` elements apart; box = (box_cols x box_rows x 1)
+inline int make_tmap_3d(CUtensorMap* out, const float* base, i64 slabs, i64 rows, i64 cols, i64 pitch, i64 slab_stride, int box_cols,
+                        int box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DLADMM_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)slab_stride * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3D) failed (%d) slabs=%lld rows=%lld cols=%lld pitch=%lld stride=%lld box=%dx%d", (int)r, slabs, rows,
+              cols, pitch, slab_stride, box_cols, box_rows);
     return DLADMM_ERR_CUDA;
   }
   return DLADMM_OK;

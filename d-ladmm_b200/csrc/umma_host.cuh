@@ -3,6 +3,7 @@
 #include "host_common.cuh"
 #include "umma_gemm.cuh"
 #include "umma_epilogues.cuh"
+#include "umma_persist.cuh"
 
 namespace dladmm {
 
@@ -36,6 +37,9 @@ struct UWorkspace {
   __nv_bfloat16 *Vh, *Zh;   // bf16 mode: the operands of the two products, (m x ldh) and 2 x (d x ldh) (Z_k alternates)
   __nv_bfloat16 *Lh;        // bf16 mode + dual-gap metric: L_k as the operand of A^T L_k
   i64 ldh;             // pitch of the bf16 operand copies (B rounded up to 8: TMA needs a 16-byte multiple)
+  unsigned* pf_flags;  // persistent forward: [2K+1][batch tiles] readiness counters
+  float* pf_obj;       // persistent forward: [units][8] partial sums of the fused objective
+  size_t pf_flag_bytes;
   size_t bytes;
   int m256, d256, mp, dp, nW;
 };
@@ -71,6 +75,14 @@ static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   w.Vh = (__nv_bfloat16*)take(bf ? (size_t)(p->m * w.ldh + 1) / 2 : 0);
   w.Zh = (__nv_bfloat16*)take(bf ? (size_t)(2 * p->d * w.ldh + 1) / 2 : 0);
   w.Lh = (__nv_bfloat16*)take(bf && atl ? (size_t)(p->m * w.ldh + 1) / 2 : 0);
+  {
+    const i64 nbt = (p->B + umma::TILE_B - 1) / umma::TILE_B;
+    const i64 nt_z = (p->d + umma::TILE_N - 1) / umma::TILE_N, nt_e = (p->m + umma::TILE_N - 1) / umma::TILE_N;
+    const i64 units = nbt * (nt_e + (i64)p->K * (nt_z + nt_e));
+    w.pf_flag_bytes = (size_t)(2 * p->K + 1) * nbt * sizeof(unsigned);
+    w.pf_flags = (unsigned*)take((size_t)(2 * p->K + 1) * nbt);
+    w.pf_obj = take(p->objective ? (size_t)units * 8 : 0);
+  }
   w.bytes = off;
   return w;
 }
@@ -133,7 +145,7 @@ static __global__ void __launch_bounds__(256) prep_split_kernel(SplitJobs jobs, 
     } else if (NPASS == 2) {
       reinterpret_cast<__nv_bfloat16*>(jb.big)[(i64)r * Cpad + c] = __float2bfloat16_rn(v);
     } else {
-      jb.big[(i64)r * Cpad + c] = v;
+      jb.big[(i64)r * Cpad + c] = umma::tf32_rna(v);         // single pass: nearest tf32 (the tensor core would truncate)
     }
   }
 }
@@ -163,7 +175,7 @@ static __global__ void __launch_bounds__(256) prep_split_t_kernel(SplitJobs jobs
     } else if (NPASS == 2) {
       reinterpret_cast<__nv_bfloat16*>(jb.big)[(i64)r * Cpad + c] = __float2bfloat16_rn(v);
     } else {
-      jb.big[(i64)r * Cpad + c] = v;
+      jb.big[(i64)r * Cpad + c] = umma::tf32_rna(v);         // single pass: nearest tf32 (the tensor core would truncate)
     }
   }
 }

@@ -291,6 +291,11 @@ DLADMM_API int64_t dladmm_launch_count(void);
 DLADMM_API int dladmm_profile_start(void);
 DLADMM_API int dladmm_profile_stop(double* ms_by_kind, int64_t* launches_by_kind);
 
+/* Debugging aid: with DLADMM_PF_TRACE=1 in the environment the all-layer persistent forward kernel stamps clock64 per unit for
+ * its first 4 CTAs ([4][512][8] values, layout in csrc/umma_persist.cuh); this copies the stamps of the last forward to the host
+ * (synchronises the device).  Returns the number of values, or -1 when tracing is off / capacity too small. */
+DLADMM_API int64_t dladmm_debug_trace(int64_t* host_out, int64_t capacity);
+
 DLADMM_API const char* dladmm_last_error(void);
 
 #ifdef __cplusplus

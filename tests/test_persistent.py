@@ -1,0 +1,100 @@
+"""GPU: the all-layer persistent forward kernel (csrc/umma_persist.cuh: one launch, cross-CTA readiness counters per
+(stage, batch tile)) against the per-layer launches (DLADMM_NO_PERSISTENT=1) -- same tiles, same MMA order, same epilogue
+arithmetic, so every iterate and prox mask must be BIT-IDENTICAL -- for every family, scalar and per-row parameters, ragged
+batches, inference (last_only ping-pong slabs) and training mode (masks + kept V_k), and through a backward."""
+import os
+
+import pytest
+import torch
+
+import dladmm_b200 as dl
+from dladmm_b200 import _lib
+from dladmm_b200.function import run_forward
+
+pytestmark = pytest.mark.gpu
+
+
+class per_layer(object):
+    def __enter__(self):
+        os.environ["DLADMM_NO_PERSISTENT"] = "1"
+
+    def __exit__(self, *a):
+        os.environ.pop("DLADMM_NO_PERSISTENT", None)
+
+
+def _model(variant, m, d, B, K, precision, seed=3):
+    torch.manual_seed(seed)
+    data = dl.gen_syn_data(B, m=m, d=d, seed=40 + seed, dense_noise_sigma=(1.0 / m ** 0.5 if variant == "lasso" else None))
+    bs = 20 if variant == "lena" else B
+    Z0 = torch.rand(d, bs, device="cuda") / d
+    E0 = torch.zeros(m, bs, device="cuda"); L0 = torch.zeros(m, bs, device="cuda")
+    model = dl.VARIANT_CLASSES[variant](m, 1, d, bs, data.A, Z0, E0, L0, K, precision=precision)
+    if variant == "lena":
+        rep = B // 20
+        model.Z0, model.E0, model.L0 = (t.repeat(1, rep).contiguous() for t in (model.Z0, model.E0, model.L0))
+    with torch.no_grad():                       # move every parameter off its constant default so that rows / layers differ
+        for n, p in model.named_parameters():
+            if not n.startswith("fc"):
+                p.mul_(1.0 + 0.2 * torch.rand_like(p))
+    return model, data
+
+
+CASES = [("scalar", 250, 500, 20000, 5, "tf32x3"), ("scalar", 250, 500, 132, 4, "tf32"), ("full", 250, 500, 1028, 4, "tf32x3"),
+         ("tied", 96, 200, 4100, 6, "tf32x3"), ("lasso", 250, 500, 2048, 3, "tf32x3"), ("ltheta", 64, 100, 512, 3, "tf32x3"),
+         ("lena", 256, 512, 20 * 60, 3, "tf32x3"), ("scalar", 40, 72, 24, 2, "tf32x3"), ("full", 1000, 2000, 256, 2, "tf32x3")]
+
+
+@pytest.mark.parametrize("variant,m,d,B,K,precision", CASES)
+def test_persistent_forward_is_bit_identical_to_per_layer_launches(variant, m, d, B, K, precision):
+    model, data = _model(variant, m, d, B, K, precision)
+    spec, params = model._spec_and_params()
+    params = [p.detach() for p in params]
+    for kw in (dict(want_masks=False), dict(want_masks=False, last_only=True), dict(want_masks=True, extras={})):
+        for objective in (None, 0.01):
+            if objective is not None and "extras" not in kw:
+                kw = dict(kw, extras={})
+            n0 = _lib.launch_count()
+            a = run_forward(spec, model.A, data.X, model.Z0, model.E0, model.L0, params, objective_alpha=objective, **kw)
+            n_pers = _lib.launch_count() - n0
+            ea = dict(kw.get("extras") or {})
+            with per_layer():
+                n0 = _lib.launch_count()
+                b = run_forward(spec, model.A, data.X, model.Z0, model.E0, model.L0, params, objective_alpha=objective, **kw)
+                n_layer = _lib.launch_count() - n0
+            eb = dict(kw.get("extras") or {})
+            assert n_pers < n_layer and n_layer >= 2 * K + 1, (n_pers, n_layer)      # (the persistent schedule really ran)
+            for name, x, y in zip(("Z", "E", "L", "T", "maskZ", "maskE"), a, b):
+                assert (x is None) == (y is None)
+                if x is not None:
+                    assert torch.equal(x, y), (variant, name, kw.keys(), (x.float() - y.float()).abs().max().item())
+            if objective is not None:
+                assert torch.allclose(ea["objective"], eb["objective"], rtol=2e-5), (ea["objective"], eb["objective"])
+            if kw.get("want_masks"):
+                assert torch.equal(ea["Vsave"], eb["Vsave"])
+
+
+def test_training_step_through_the_persistent_forward():
+    model, data = _model("scalar", 250, 500, 4096, 5, "tf32x3")
+    loss, _ = model.l1l1_loss(data.X, 0.01)
+    loss.backward()
+    g1 = [p.grad.clone() for p in model.parameters()]
+    l1 = loss.item()
+    model.zero_grad(set_to_none=True)
+    with per_layer():
+        loss, _ = model.l1l1_loss(data.X, 0.01)
+        loss.backward()
+    assert abs(loss.item() - l1) < 1e-5 * abs(l1)
+    for a, p in zip(g1, model.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_many_calls_back_to_back_reuse_the_counters():
+    """The readiness counters live in the per-call workspace and are zeroed on the stream: 20 forwards in a row, different
+    batch sizes interleaved, all equal to the per-layer result."""
+    model, data = _model("scalar", 250, 500, 8192, 6, "tf32x3")
+    with per_layer(), torch.no_grad():
+        ref = model(data.X)
+    with torch.no_grad():
+        for i in range(20):
+            out = model(data.X)
+            assert all(torch.equal(a, b) for a, b in zip(out[0] + out[3], ref[0] + ref[3])), i
