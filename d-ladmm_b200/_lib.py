@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libdladmm.so")
+# (DLADMM_LIB_PATH: an alternative build of the same library, for A/B measurements of compile-time switches)
+LIB_PATH = os.environ.get("DLADMM_LIB_PATH") or os.path.join(HERE, "csrc", "libdladmm.so")
 
 ABI_VERSION = 5
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2

@@ -34,7 +34,7 @@ static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const 
   return DLADMM_OK;
 }
 
-template <int FAM, int NPASS, bool PS>
+template <int FAM, int NPASS, int PS>
 static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& sw, const UBwdWorkspace& w,
                          cudaStream_t st) {
   Slabs s(p);
@@ -84,11 +84,12 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
   // (15 reduction launches of ~20 us each were 3 % of a training step)
   const size_t layer_entries = (size_t)SL_COUNT * ro.nentries;
   std::vector<ScalarJob> sjobs;
-  if (PS) DL_CUDA(cudaMemsetAsync(w.part, 0, sizeof(float) * layer_entries * K, st));
+  constexpr bool SC = PS == umma::PM_SCALAR;      // all parameters scalar: per-warp entries, one reduction launch at the end
+  if (SC) DL_CUDA(cudaMemsetAsync(w.part, 0, sizeof(float) * layer_entries * K, st));
   for (int k = K - 1; k >= 0; --k) {
     const dladmm_layer& l = p->layers[k];
     const size_t wi = (size_t)weight_index(p, k);
-    if (PS) ro.part = w.part + layer_entries * k;
+    if (SC) ro.part = w.part + layer_entries * k;
     {
       umma::UEpiBG1<PS> epi;
       epi.gZ = g->gZ ? g->gZ + s.zs * k : nullptr;
@@ -137,7 +138,7 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
     add_job(jobs, SL_B1, l.beta1, m);
     add_job(jobs, SL_SS1, l.ss1, m);
     if (k > 0) add_m1_jobs(p, jobs, p->layers[k - 1]);
-    if (PS) {
+    if (SC) {
       for (int i = 0; i < jobs.n; ++i) sjobs.push_back(ScalarJob{ro.part + (size_t)jobs.j[i].slot * ro.nentries, jobs.j[i].grad});
       continue;
     }
@@ -166,10 +167,12 @@ int umma_backward(const dladmm_problem* p, const dladmm_cotangents* g, const Wor
   char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
   UBwdWorkspace w = ucarve_bwd(p, base);
   const bool x3 = p->precision == DLADMM_PREC_TF32X3;
-  const bool ps = all_params_scalar(p);
-#define DL_BWD(F)                                                                                                   \
-  (x3 ? (ps ? backward_umma<F, 3, true>(p, g, sw, w, st) : backward_umma<F, 3, false>(p, g, sw, w, st))              \
-      : (ps ? backward_umma<F, 1, true>(p, g, sw, w, st) : backward_umma<F, 1, false>(p, g, sw, w, st)))
+  const int pm = param_mode(p);
+#define DL_BPM(F, NP)                                                                                                  \
+  (pm == umma::PM_SCALAR ? backward_umma<F, NP, umma::PM_SCALAR>(p, g, sw, w, st)                                      \
+                         : pm == umma::PM_ROWS ? backward_umma<F, NP, umma::PM_ROWS>(p, g, sw, w, st)                  \
+                                               : backward_umma<F, NP, umma::PM_GENERAL>(p, g, sw, w, st))
+#define DL_BWD(F) (x3 ? DL_BPM(F, 3) : DL_BPM(F, 1))
   switch (p->family) {
     case DLADMM_FAMILY_A: return DL_BWD(DLADMM_FAMILY_A);
     case DLADMM_FAMILY_B: return DL_BWD(DLADMM_FAMILY_B);

@@ -93,8 +93,9 @@ __device__ __forceinline__ void red_finish(const RedOut& ro, const int (&slots)[
 __device__ __forceinline__ int slot_rank(uint32_t mask, int i) { return (mask >> i) & 1u ? __popc(mask & ((1u << i) - 1u)) : -1; }
 
 // dZ_k = gZ_k + carried + A^T dR ; dx1 = dZ_k * (m+ + m-) ; dtheta1 ; dx1 is the operand of the next two products
-template <bool PS>
+template <int PM>
 struct UEpiBG1 {
+  static constexpr bool PS = PM == PM_SCALAR;
   static constexpr int WARPS = 16;                 // measured: 1.97 -> 1.67 ms per 15 layers against 8 warps
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 3;                    // gZ_k, carried dZ, Z_k (fused loss) -- each optional
@@ -155,13 +156,14 @@ struct UEpiBG1 {
 
 // dV = -s1 * W^T dx1 ; dbeta1, dss1 ; carried dL, dT ; then the elementwise cotangent flow of layer k-1 (m1):
 // writes dR for the next A^T dR product, carried dE and dL.
-template <int FAM, bool PS>
+template <int FAM, int PM>
 struct UEpiBG2 {
+  static constexpr bool PS = PM == PM_SCALAR;
   static constexpr int WARPS = 8;                  // 7 staged arrays: two parts keep 2 ring slots each in flight (16 warps: 1 each, slower)
   static constexpr int CHUNK = 4;     // up to 7 staged arrays + mask per element: keep one ring slot small (depth >= EPI_PARTS)
   static constexpr int NIN = 7;    // L_{k-1} (tied), T_k, cL | cE, E_{k-1}, L_{k-2}, E_{k-2}(B)   (the last four only below the top layer)
                                    // upstream cotangents gL, gE, gT (generic autograd path only) are read straight from global memory
-  struct State { float red[6]; float rv[PS ? 1 : 32]; uint32_t gmask; PV<PS> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };
+  struct State { float red[6]; float rv[PS ? 1 : 32]; uint32_t gmask; PV<PM> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };
   struct Pre { unsigned mk[CHUNK]; };
   // layer k
   const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
@@ -182,14 +184,10 @@ struct UEpiBG2 {
     p[6] = (has_prev && FAM == DLADMM_FAMILY_B) ? Ep : nullptr;
   }
   const uint8_t* host_mask() const { return (has_prev && FAM != DLADMM_FAMILY_C) ? maskE : nullptr; }
-  static constexpr int NROWP = PS ? 0 : 5;
+  static constexpr int NROWP = PM == PM_ROWS ? 5 : 0;
   __device__ __forceinline__ void row_params(BP (&q)[5]) const { q[0] = b1; q[1] = bL; q[2] = b2; q[3] = ss2; q[4] = ss2_2; }
-  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const {
-    if (have & 1u) st.b1.tab = tab;
-    if (have & 2u) st.bL.tab = tab + n;
-    if (have & 4u) st.b2.tab = tab + 2 * n;
-    if (have & 8u) st.ss2.tab = tab + 3 * n;
-    if (have & 16u) st.ss2_2.tab = tab + 4 * n;
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n) const {
+    st.b1.tab = tab; st.bL.tab = tab + n; st.b2.tab = tab + 2 * n; st.ss2.tab = tab + 3 * n; st.ss2_2.tab = tab + 4 * n;
   }
   __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll

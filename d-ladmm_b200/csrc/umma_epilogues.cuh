@@ -23,13 +23,16 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// a broadcast parameter resolved once per kernel: scalars live in a register, per-row / per-slot ones are read
-// through the read-only path (warp-uniform address when there is no column period)
-// PSCALAR = every parameter of the call is a (1,1) scalar (scalar / tied / lasso variants): no loads, less code.
-// Per-row parameters ((rows,1): the full / ltheta variants) are copied once per kernel into a small shared-memory table by the
-// epilogue warps (`tab`, see umma_gemm.cuh): with ~220 KB of the SM's 228 KB configured as shared memory the L1 is a few KB
-// and a __ldg per row and parameter missed it most of the time (measured: the A Z kernel of `full` 0.32 ms vs 0.12 ms scalar).
-template <bool PSCALAR>
+// How a kernel instantiation reads the per-layer broadcast parameters (template argument PM of the epilogue functors):
+//   PM_SCALAR  every parameter of the call is a (1,1) scalar (scalar / tied / lasso variants): one register each, no loads;
+//   PM_ROWS    scalars and (rows,1) vectors only (full / ltheta): the epilogue warps copy the 256 rows of the current tile of every
+//              parameter into a shared-memory table (fill_rowtab, umma_gemm.cuh) and at() is ONE unconditional broadcast read.
+//              With ~220 KB of the SM configured as shared memory the L1 is a few KB: a __ldg per row and parameter missed it, and
+//              the "table or __ldg" choice at run time cost a convergence barrier per access (measured: A Z epilogue of `full`
+//              61 us per tile against 20 us scalar);
+//   PM_GENERAL anything else, i.e. per-batch-slot (rows, bs) parameters (main_lena.py:35-36): __ldg with the column period.
+enum { PM_GENERAL = 0, PM_SCALAR = 1, PM_ROWS = 2 };
+template <int PM>
 struct PV {
   const float* p; int rs; int period; float s; const float* tab;
   __device__ __forceinline__ void init(const BP& q) {
@@ -37,8 +40,8 @@ struct PV {
     s = (q.p && q.rs == 0 && q.period == 0) ? __ldg(q.p) : 0.f;
   }
   __device__ __forceinline__ float at(int row, i64 col) const {
-    if (PSCALAR) return s;
-    if (tab) return tab[row];                       // warp-uniform address: one broadcast read
+    if (PM == PM_SCALAR) return s;
+    if (PM == PM_ROWS) return tab[row];             // tab is pre-offset by the tile's first row; warp-uniform address
     i64 off = (i64)row * rs;
     if (period) off += col % period;
     return __ldg(p + off);
@@ -49,7 +52,7 @@ __host__ __device__ constexpr int SUBF(int chunk) { return chunk * TILE_B; }   /
 struct NoPre {};
 
 // T_0 = A Z0 + E0 - X, and V_0 = L0 + beta1_0 * T_0 for the first Z-step
-template <bool PSCALAR>
+template <int PSCALAR>
 struct UEpiT0 {
   static constexpr int WARPS = 8;
   static constexpr int CHUNK = 8;
@@ -61,9 +64,9 @@ struct UEpiT0 {
   __nv_bfloat16* __restrict__ Vh; i64 ldh;         // bf16 mode: the W V operand as bf16 (pitch ldh)
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = E0; p[1] = X; p[2] = L0; }
   const uint8_t* host_mask() const { return nullptr; }
-  static constexpr int NROWP = PSCALAR ? 0 : 1;
+  static constexpr int NROWP = PSCALAR == PM_ROWS ? 1 : 0;
   __device__ __forceinline__ void row_params(BP (&q)[1]) const { q[0] = b1; }
-  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const { if (have & 1u) st.b1.tab = tab; }
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n) const { st.b1.tab = tab; }
   __device__ __forceinline__ void begin(State& st) const { st.b1.init(b1); }
   __device__ __forceinline__ void end(State&, int, int) const {}
   __device__ __forceinline__ void prefetch(Pre&, int, i64, bool, int) const {}
@@ -89,7 +92,7 @@ struct UEpiT0 {
 };
 
 // Z_k = act(Z_{k-1} - [ss1*] acc, theta1)
-template <bool PSCALAR>
+template <int PSCALAR>
 struct UEpiZ {
   static constexpr int WARPS = 8;
   static constexpr int CHUNK = 16;
@@ -103,9 +106,9 @@ struct UEpiZ {
   __nv_bfloat16* __restrict__ Zh; i64 ldh;         // bf16 mode: Z_k as bf16, the operand of the A Z product
   void host_inputs(const float* (&p)[MAX_EIN]) const { p[0] = Zp; p[1] = sq_part ? Zlabel : nullptr; }
   const uint8_t* host_mask() const { return nullptr; }
-  static constexpr int NROWP = PSCALAR ? 0 : 1;
+  static constexpr int NROWP = PSCALAR == PM_ROWS ? 1 : 0;
   __device__ __forceinline__ void row_params(BP (&q)[1]) const { q[0] = th1; }
-  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const { if (have & 1u) st.th1.tab = tab; }
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n) const { st.th1.tab = tab; }
   __device__ __forceinline__ void begin(State& st) const { st.th1.init(th1); st.s1 = ss1.p ? __ldg(ss1.p) : 1.f; st.obj = 0.f; st.sq = 0.f; }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     if (obj_part) {
@@ -145,7 +148,7 @@ struct UEpiZ {
 constexpr int ELT_NMET = 7;                        // L1_RES, SQ_RES, SQERR_E, SQERR_AZ, L1_E, DOT_LX, DGAP_L
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(__expf(x)); }   // F.softplus, threshold 20
 
-template <int FAM, bool PSCALAR, bool MET = false>
+template <int FAM, int PSCALAR, bool MET = false>
 struct UEpiELT {
   static constexpr int WARPS = 8;
   static constexpr int CHUNK = 8;
@@ -167,15 +170,10 @@ struct UEpiELT {
     if (MET) { p[3] = Elabel; p[4] = Xclean; }
   }
   const uint8_t* host_mask() const { return nullptr; }
-  static constexpr int NROWP = PSCALAR ? 0 : 6;
+  static constexpr int NROWP = PSCALAR == PM_ROWS ? 6 : 0;
   __device__ __forceinline__ void row_params(BP (&q)[6]) const { q[0] = b2; q[1] = ss2; q[2] = ss2_2; q[3] = th2; q[4] = bL; q[5] = b1n; }
-  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n, uint32_t have) const {
-    if (have & 1u) st.b2.tab = tab;
-    if (have & 2u) st.ss2.tab = tab + n;
-    if (have & 4u) st.ss2_2.tab = tab + 2 * n;
-    if (have & 8u) st.th2.tab = tab + 3 * n;
-    if (have & 16u) st.bL.tab = tab + 4 * n;
-    if (have & 32u) st.b1n.tab = tab + 5 * n;
+  __device__ __forceinline__ void bind_rows(State& st, const float* tab, int n) const {
+    st.b2.tab = tab; st.ss2.tab = tab + n; st.ss2_2.tab = tab + 2 * n; st.th2.tab = tab + 3 * n; st.bL.tab = tab + 4 * n; st.b1n.tab = tab + 5 * n;
   }
   __device__ __forceinline__ void begin(State& st) const {
     st.b2.init(b2); st.ss2.init(ss2); st.ss2_2.init(ss2_2); st.th2.init(th2); st.bL.init(bL); st.b1n.init(b1n);

@@ -36,7 +36,7 @@ static __global__ void __launch_bounds__(256) metrics_reduce_kernel(const float*
 // where metric i of layer k keeps its per-warp partial sums
 static inline float* met_slot(const UWorkspace& w, int k, int i) { return w.metp + ((size_t)k * DLADMM_MET_COUNT + i) * OBJ_ENTRIES; }
 
-template <int FAM, int NPASS, bool PS, bool MET>
+template <int FAM, int NPASS, int PS, bool MET>
 static int launch_elt(const dladmm_problem* p, const UWorkspace& w, const Slabs& s, int k, const void* Zk, float* Vnext,
                       __nv_bfloat16* Vnext_h, cudaStream_t st) {
   const dladmm_layer& l = p->layers[k];
@@ -59,7 +59,7 @@ static int launch_elt(const dladmm_problem* p, const UWorkspace& w, const Slabs&
   return launch_umma<umma::UEpiELT<FAM, PS, MET>, NPASS>(DLADMM_KIND_GEMM_ELT, Zk, p->d, w.Ab, w.As, w.m256, w.dp, p->m, p->B, epi, st, 0, w.ldh);
 }
 
-template <int FAM, int NPASS, bool PS>
+template <int FAM, int NPASS, int PS>
 static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
   Slabs s(p);
   const int m = p->m, d = p->d, K = p->K;
@@ -202,6 +202,13 @@ static bool persistent_eligible(const dladmm_problem* p) {
   if (!persistent_allowed()) return false;
   if (p->precision != DLADMM_PREC_TF32X3 && p->precision != DLADMM_PREC_TF32) return false;
   if (p->K < 1 || p->K > umma::PF_MAX_LAYERS) return false;
+  // Tensor-bound shapes gain nothing from the merged schedule (their per-layer launches already run ~90 % of the tensor peak and
+  // the one-launch version measured 5 % slower at m 1000, d 2000: 50.3 vs 47.7 ms per 32 768-column forward on the same box);
+  // DLADMM_PERSISTENT=1 forces it for any shape
+  {
+    const char* e = getenv("DLADMM_PERSISTENT");
+    if (!(e && e[0] == '1') && (i64)p->m * p->d > (i64)512 * 1024) return false;
+  }
   if (p->start_half || p->stop_half || p->T_init) return false;
   if (p->metrics && p->metrics->want) return false;
   {   // the kernel numbers its units with 32 bits
@@ -214,7 +221,7 @@ static bool persistent_eligible(const dladmm_problem* p) {
 
 static umma::BPc to_bpc(const dladmm_bparam& q) { umma::BPc b; b.p = q.ptr; b.rs = q.row_stride; b.period = q.col_period; return b; }
 
-template <int FAM, int NPASS, bool PS>
+template <int FAM, int NPASS, int PS>
 static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
   constexpr int KC = KChunk<NPASS>::value;
   using Plan = umma::SmemPlan<NPASS, KC>;
@@ -324,11 +331,12 @@ int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {
   char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
   UWorkspace w = ucarve(p, base);
   const bool x3 = p->precision == DLADMM_PREC_TF32X3, bf = p->precision == DLADMM_PREC_BF16;
-  const bool ps = all_params_scalar(p);
+  const int pm = param_mode(p);
+#define DL_PM(FN, F, NP)                                                                                  \
+  (pm == umma::PM_SCALAR ? FN<F, NP, umma::PM_SCALAR>(p, w, st)                                           \
+                         : pm == umma::PM_ROWS ? FN<F, NP, umma::PM_ROWS>(p, w, st) : FN<F, NP, umma::PM_GENERAL>(p, w, st))
   if (persistent_eligible(p)) {
-#define DL_PF(F)                                                                                                  \
-  (x3 ? (ps ? forward_persistent<F, 3, true>(p, w, st) : forward_persistent<F, 3, false>(p, w, st))                \
-      : (ps ? forward_persistent<F, 1, true>(p, w, st) : forward_persistent<F, 1, false>(p, w, st)))
+#define DL_PF(F) (x3 ? DL_PM(forward_persistent, F, 3) : DL_PM(forward_persistent, F, 1))
     switch (p->family) {
       case DLADMM_FAMILY_A: return DL_PF(DLADMM_FAMILY_A);
       case DLADMM_FAMILY_B: return DL_PF(DLADMM_FAMILY_B);
@@ -336,10 +344,7 @@ int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {
     }
 #undef DL_PF
   }
-#define DL_FWD(F)                                                                                       \
-  (x3 ? (ps ? forward_umma<F, 3, true>(p, w, st) : forward_umma<F, 3, false>(p, w, st))                  \
-      : bf ? (ps ? forward_umma<F, 2, true>(p, w, st) : forward_umma<F, 2, false>(p, w, st))             \
-      : (ps ? forward_umma<F, 1, true>(p, w, st) : forward_umma<F, 1, false>(p, w, st)))
+#define DL_FWD(F) (x3 ? DL_PM(forward_umma, F, 3) : bf ? DL_PM(forward_umma, F, 2) : DL_PM(forward_umma, F, 1))
   switch (p->family) {
     case DLADMM_FAMILY_A: return DL_FWD(DLADMM_FAMILY_A);
     case DLADMM_FAMILY_B: return DL_FWD(DLADMM_FAMILY_B);

@@ -62,17 +62,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or a time limit passes; the explicit limit (ns) keeps a
+// waiting role from coming back to re-issue the instruction every few hundred cycles (the kernels run under the power cap:
+// issue slots spent on polling are clocks taken from the tensor pipe)
+#ifndef DLADMM_MBAR_SUSPEND_NS
+#define DLADMM_MBAR_SUSPEND_NS 100000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
+#if DLADMM_MBAR_SUSPEND_NS > 0
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)DLADMM_MBAR_SUSPEND_NS)
         : "memory");
   } while (!done);
 }
@@ -337,20 +347,20 @@ struct RingPos {
   }
 };
 
-// tabulate the (rows,1) parameters among q[0..NP) -- called by all epilogue threads (etid of nthr); returns the bit mask of the
-// tabulated ones; the caller synchronises the epilogue warps before the table is read
+// PM_ROWS: tabulate rows [j0, j0 + TILE_N) of the parameters q[0..NP) (scalars are broadcast, absent ones left alone: they are
+// never read) -- called by all epilogue threads (etid of nthr); the caller synchronises the epilogue warps around it.
+// Table layout: parameter i at tab + i * TILE_N, indexed by row - j0.
 template <int NP>
-__device__ __forceinline__ uint32_t fill_rowtab(const BP (&q)[NP], float* tab, int n_feat, int n_pad, int etid, int nthr) {
-  uint32_t have = 0;
+__device__ __forceinline__ void fill_rowtab(const BP (&q)[NP], float* tab, int j0, int n_feat, int etid, int nthr) {
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    if (q[i].p == nullptr || q[i].period != 0 || q[i].rs != 1) continue;      // absent, per batch slot, or a scalar
-    have |= 1u << i;
-    for (int r = etid; r < n_pad; r += nthr) tab[i * n_pad + r] = r < n_feat ? __ldg(q[i].p + r) : 0.f;
+    if (q[i].p == nullptr) continue;
+    for (int r = etid; r < TILE_N; r += nthr) {
+      const int row = j0 + r;
+      tab[i * TILE_N + r] = row < n_feat ? __ldg(q[i].p + (i64)row * q[i].rs) : 0.f;
+    }
   }
-  return have;
 }
-
 
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(roles_threads(Epi::WARPS), 1)
@@ -585,17 +595,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0; uint32_t aph = 0;
     typename Epi::State state;
     epi.begin(state);
-    if constexpr (Epi::NROWP > 0) {
-      // per-row parameters of this launch -> shared memory, once (the epilogue warps only: named barrier 1)
-      const int n_pad = gs.n_ntiles * TILE_N;
-      if (Epi::NROWP * n_pad * 4 <= Plan::ROWTAB) {     // uniform over the grid
-        BP q[Epi::NROWP];
-        epi.row_params(q);
-        const uint32_t have = fill_rowtab<Epi::NROWP>(q, rowtab, gs.n_feat, n_pad, threadIdx.x - EPI_WARP0 * 32, EPI_WARPS * 32);
-        asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-        epi.bind_rows(state, rowtab, n_pad, have);
-      }
-    }
+    int tab_j0 = -1;                                   // PM_ROWS: the feature tile the parameter table currently holds
     RingPos rp; rp.init(half, depth);                  // this part's chunks are every EPI_PARTS-th slot of the staging ring
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(gs, tile);
@@ -605,6 +605,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rpw = ti.nrows / EPI_PARTS;            // feature rows per (tile, part); half as many in a half tile
       const int nch = rpw / CHK;
       const int jw = ti.j0 + half * rpw;               // first feature row of this warp
+      if constexpr (Epi::NROWP > 0) {
+        // per-row parameters of this tile's 256 feature rows -> shared memory (the epilogue warps only: named barrier 1);
+        // once per launch when the product has a single feature tile
+        static_assert(Epi::NROWP * TILE_N * 4 <= Plan::ROWTAB, "row-parameter table");
+        if (ti.j0 != tab_j0) {                          // uniform over the epilogue warps
+          asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");      // the previous tile's readers are done
+          BP q[Epi::NROWP];
+          epi.row_params(q);
+          fill_rowtab<Epi::NROWP>(q, rowtab, ti.j0, gs.n_feat, threadIdx.x - EPI_WARP0 * 32, EPI_WARPS * 32);
+          asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+          epi.bind_rows(state, rowtab - ti.j0, TILE_N);
+          tab_j0 = ti.j0;
+        }
+      }
       typename Epi::Pre pre;
       epi.prefetch(pre, jw, b, valid, gs.n_feat);
       mbar_wait(&tfull[acc], aph);

@@ -378,6 +378,8 @@ static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, c
   return DLADMM_OK;
 }
 
+// umma::PM_SCALAR / PM_ROWS / PM_GENERAL of a problem (see umma_epilogues.cuh)
+static int param_mode(const dladmm_problem* p);
 static bool all_params_scalar(const dladmm_problem* p) {
   bool ps = true;
   for (int k = 0; k < p->K; ++k) {
@@ -386,6 +388,17 @@ static bool all_params_scalar(const dladmm_problem* p) {
     for (int i = 0; i < 8; ++i) ps = ps && (all[i]->ptr == nullptr || (all[i]->row_stride == 0 && all[i]->col_period == 0));
   }
   return ps;
+}
+
+static int param_mode(const dladmm_problem* p) {
+  if (all_params_scalar(p)) return umma::PM_SCALAR;
+  for (int k = 0; k < p->K; ++k) {
+    const dladmm_layer& l = p->layers[k];
+    const dladmm_bparam* all[8] = {&l.beta1, &l.beta2, &l.beta3, &l.ss1, &l.ss2, &l.ss2_2, &l.theta1, &l.theta2};
+    for (int i = 0; i < 8; ++i)
+      if (all[i]->ptr && (all[i]->col_period != 0 || (all[i]->row_stride != 0 && all[i]->row_stride != 1))) return umma::PM_GENERAL;
+  }
+  return umma::PM_ROWS;
 }
 
 }  // namespace dladmm

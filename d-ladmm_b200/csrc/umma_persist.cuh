@@ -209,7 +209,7 @@ __device__ __forceinline__ void pf_run_epilogue(const Epi& epi, typename Epi::St
   }
 }
 
-template <int FAM, bool PS, int NPASS, int KC>
+template <int FAM, int PS, int NPASS, int KC>
 __global__ void __launch_bounds__(roles_threads(8) + 32, 1)
 umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid_constant__ PfParams p) {
   using Plan = SmemPlan<NPASS, KC>;
@@ -526,6 +526,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
     const int etid = threadIdx.x - EPI_WARP0 * 32;
     int acc = 0; uint32_t aph = 0; int ui = 0;
     int ps = 0; uint32_t pph = 0;
+    int tab_key = -1;
     RingPos rp; rp.init(half, PF_DEPTH);
     const int rpw = TILE_N / EPI_PARTS;
     for (uint32_t v = walk.first; v < walk.total; v += walk.stride) {
@@ -538,6 +539,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
       const int slab = p.last_only ? (k & 1) : k;
       const uint32_t t0 = tmem_base + acc * TILE_N + half * rpw + ((uint32_t)(q * 32) << 16);
       float* objp = p.obj_part ? p.obj_part + un.u * EPI_WARPS : nullptr;
+      const int key = (un.stage << 8) | (un.j0 >> 8);   // PM_ROWS: which (stage, feature tile) the parameter table holds
       if (un.type == PF_T0) {
         UEpiT0<PS> epi;
         epi.E0 = p.E0; epi.X = p.X; epi.L0 = p.L0; epi.T0 = p.T;
@@ -545,15 +547,15 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         epi.V = p.K > 0 ? p.V : nullptr; epi.B = p.B; epi.in_mask = 7u; epi.Vh = nullptr; epi.ldh = 0;
         typename UEpiT0<PS>::State state;
         epi.begin(state);
-        if constexpr (!PS) {
-          const int n_pad = p.nt_e * TILE_N;
-          asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");      // the previous unit's readers are done with the table
-          if (n_pad * 4 <= Plan::ROWTAB) {
+        if constexpr (PS == PM_ROWS) {
+          if (tab_key != key) {                           // (uniform over the epilogue warps)
+            asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");    // the previous unit's readers are done with the table
             BP qv[1]; epi.row_params(qv);
-            const uint32_t have = fill_rowtab<1>(qv, rowtab, p.m, n_pad, etid, EPI_WARPS * 32);
+            fill_rowtab<1>(qv, rowtab, un.j0, p.m, etid, EPI_WARPS * 32);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-            epi.bind_rows(state, rowtab, n_pad, have);
+            tab_key = key;
           }
+          epi.bind_rows(state, rowtab - un.j0, TILE_N);
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
@@ -566,15 +568,15 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         epi.obj_part = objp; epi.Zlabel = nullptr; epi.sq_part = nullptr; epi.Zh = nullptr; epi.ldh = 0;
         typename UEpiZ<PS>::State state;
         epi.begin(state);
-        if constexpr (!PS) {
-          const int n_pad = p.nt_z * TILE_N;
-          asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-          if (n_pad * 4 <= Plan::ROWTAB) {
+        if constexpr (PS == PM_ROWS) {
+          if (tab_key != key) {                           // (uniform over the epilogue warps)
+            asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");    // the previous unit's readers are done with the table
             BP qv[1]; epi.row_params(qv);
-            const uint32_t have = fill_rowtab<1>(qv, rowtab, p.d, n_pad, etid, EPI_WARPS * 32);
+            fill_rowtab<1>(qv, rowtab, un.j0, p.d, etid, EPI_WARPS * 32);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-            epi.bind_rows(state, rowtab, n_pad, have);
+            tab_key = key;
           }
+          epi.bind_rows(state, rowtab - un.j0, TILE_N);
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
@@ -595,15 +597,15 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         epi.Vh = nullptr; epi.ldh = 0; epi.B = p.B; epi.in_mask = FAM == DLADMM_FAMILY_B ? 7u : 3u;
         typename UEpiELT<FAM, PS, false>::State state;
         epi.begin(state);
-        if constexpr (!PS) {
-          const int n_pad = p.nt_e * TILE_N;
-          asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-          if (6 * n_pad * 4 <= Plan::ROWTAB) {
+        if constexpr (PS == PM_ROWS) {
+          if (tab_key != key) {                           // (uniform over the epilogue warps)
+            asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");    // the previous unit's readers are done with the table
             BP qv[6]; epi.row_params(qv);
-            const uint32_t have = fill_rowtab<6>(qv, rowtab, p.m, n_pad, etid, EPI_WARPS * 32);
+            fill_rowtab<6>(qv, rowtab, un.j0, p.m, etid, EPI_WARPS * 32);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-            epi.bind_rows(state, rowtab, n_pad, have);
+            tab_key = key;
           }
+          epi.bind_rows(state, rowtab - un.j0, TILE_N);
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();

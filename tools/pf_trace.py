@@ -10,12 +10,13 @@ import numpy as np, torch, dladmm_b200 as dl
 from dladmm_b200 import _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 prec = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
-m, d, K = 250, 500, 15
+variant = sys.argv[3] if len(sys.argv) > 3 else "scalar"
+m, d, K = (int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else (250, 500, 15)
 data = dl.gen_syn_data(B, m=m, d=d, seed=1)
 Z0 = torch.rand(d, B, device="cuda") / d
 z = lambda r: torch.zeros(r, B, device="cuda")
 torch.manual_seed(1126)
-model = dl.DLADMMNetScalar(m, 1, d, B, data.A, Z0, z(m), z(m), K, precision=prec)
+model = dl.VARIANT_CLASSES[variant](m, 1, d, B, data.A, Z0, z(m), z(m), K, precision=prec)
 with torch.no_grad():
     for _ in range(3):
         model(data.X)
