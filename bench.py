@@ -332,8 +332,10 @@ def run_ours(args):
     from dladmm_b200 import _lib
 
     rank, world, local = _dist_env()
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
+    # keep NCCL's banner off stdout (rank 0 prints exactly one JSON line): it is printed at NCCL_DEBUG=VERSION and above
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local)

@@ -14,6 +14,14 @@ from dladmm_b200.function import run_forward
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _force_persistent():
+    """The library only takes the one-launch schedule for HBM-bound shapes (m*d <= 512K); force it for every case here."""
+    os.environ["DLADMM_PERSISTENT"] = "1"
+    yield
+    os.environ.pop("DLADMM_PERSISTENT", None)
+
+
 class per_layer(object):
     def __enter__(self):
         os.environ["DLADMM_NO_PERSISTENT"] = "1"
