@@ -80,7 +80,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -389,7 +389,19 @@ def run_ours(args):
     t_wall1 = time.time()
     launches = _lib.launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
+    if rank == 0 and ms_total < 400.0:
+        # the timed region (steps x ~3 ms) is shorter than a few nvidia-smi samples: keep the SAME step running, untimed, for
+        # ~0.4 s more so that the clock / throttle record is taken under this load (the timing above is not affected)
+        t_probe = time.time()
+        while time.time() - t_probe < 0.4:
+            for _ in range(10):
+                step_resident()
+            torch.cuda.synchronize(dev)
+        t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "the %d timed steps plus ~0.4 s of the same step, untimed" % args.steps
+    barrier()
 
     # ---- per-kernel pass (CUDA events around every launch, same steps) --------------------------------
     _lib.profile_start()
@@ -506,21 +518,21 @@ def run_ours(args):
     # ---- end to end with the FINAL iterate brought back to the host (what an inference caller wants) -------------------
     e2e_z = None
     if not args.quick:
-        z_host = [torch.empty((D, B), dtype=torch.float32).pin_memory() for _ in range(2)]
-
         def run_e2e_z(nsteps):
+            # upload of batch i+1 (HostFeed) and download of result i-1 (HostDrain) both overlap the forward of batch i
             feed = dl.HostFeed((X_host for _ in range(nsteps)), dev)
-            done = [None, None]
-            for i, x_dev in enumerate(feed):
+            drain = dl.HostDrain(dev)
+            acc = 0.0
+            for x_dev in feed:
                 with torch.no_grad():
                     Zl = model(x_dev, last_only=True)[0]
-                if done[i & 1] is not None:
-                    done[i & 1].synchronize()                 # the pinned buffer of step i-2 has been read
-                z_host[i & 1].copy_(Zl[0], non_blocking=True)
-                ev = torch.cuda.Event(); ev.record(); done[i & 1] = ev
-            for ev in done:
-                if ev is not None:
-                    ev.synchronize()
+                hz = drain.push(Zl[0])
+                if hz is not None:
+                    acc += float(hz[0, 0])            # the host reads the result
+                    drain.recycle(hz)
+            for hz in drain.flush():
+                acc += float(hz[0, 0])
+                drain.recycle(hz)
             return feed.bytes_copied
         run_e2e_z(2)
         barrier()
@@ -531,7 +543,6 @@ def run_ours(args):
         barrier()
         e2e_z = {"ms_per_step": e0.elapsed_time(e1) / args.steps, "h2d_bytes_per_step": int(hb // args.steps),
                  "d2h_bytes_per_step": int(4 * D * B)}
-        del z_host
 
     # ---- optional: the large-scale shape (BASELINE configs[4] "C5": A 1000x2000, K=40), tensor-bound regime ---------
     c5 = None
@@ -734,7 +745,8 @@ def run_ours(args):
                                                       "iterates returned) and with last_only=True in the headline precision")
         if e2e_z:
             line["e2e_final_z"] = dict(e2e_z, ms_per_step=extra["e2e_z"], value=world * B / (extra["e2e_z"] * 1e-3), unit=UNIT,
-                                       api="HostFeed -> DLADMMNet.forward(x, last_only=True) -> final Z copied to pinned host memory every step")
+                                       api="HostFeed -> DLADMMNet.forward(x, last_only=True) -> HostDrain: the final Z of every step copied to pinned host memory "
+                                           "(copy of step i-1 overlaps the forward of step i) and read on the host")
         if c5:
             f5 = 2.0 * 1000 * 2000 * (2 * 40 + 1)                  # algorithmic flops per instance (324 MFLOP)
             B5 = c5["columns_per_gpu"]

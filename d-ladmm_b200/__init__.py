@@ -13,12 +13,12 @@ from .gen_syn import gen_syn_data, SynData, replace_A_columns, load_mat, save_ma
 from .objective import l1l1_objective
 from .mu_updater import mu_updater_dict
 from .sharding import column_shard, allreduce_gradients, ShardedTrainer
-from .host_feed import HostFeed
+from .host_feed import HostFeed, HostDrain
 
 __all__ = ["DLADMMNet", "DLADMMNetScalar", "DLADMMNetFull", "DLADMMNetTied", "DLADMMNetLasso", "DLADMMNetLena",
            "DLADMMNetLtheta", "DLADMMNetNewS", "DLADMMNetTiedNewS", "DLADMMNetPtiedNewS", "VARIANT_CLASSES", "UnrolledLADMM", "LayerSpec", "run_forward", "gen_syn_data",
            "SynData", "l1l1_objective", "column_shard", "allreduce_gradients", "ShardedTrainer",
-           "default_precision", "library_path", "query_device", "mu_updater_dict", "HostFeed", "replace_A_columns", "load_mat", "save_mat"]
+           "default_precision", "library_path", "query_device", "mu_updater_dict", "HostFeed", "HostDrain", "replace_A_columns", "load_mat", "save_mat"]
 
 
 def library_path():

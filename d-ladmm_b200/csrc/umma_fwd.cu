@@ -251,9 +251,8 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   pp->obj_part = p->objective ? w.pf_obj : nullptr;
   pp->flags = w.pf_flags;
   pp->spin_limit = 4000000000ll;                    // ~2 s of SM clocks
-  // (measured: the L2 prefetch of the next unit's epilogue inputs costs 8-12 % -- the lines are evicted before use and read twice --
-  //  so it is off unless DLADMM_PF_PREFETCH=1; see profiles/r02_persistent_experiments.md)
-  { const char* e = getenv("DLADMM_PF_PREFETCH"); pp->prefetch = (e && e[0] == '1') ? 1 : 0; }
+  // DLADMM_PF_PREFETCH=D: L2 prefetch distance of the staging producer in chunks (0 = off)
+  { const char* e = getenv("DLADMM_PF_PREFETCH"); pp->prefetch = e ? atoi(e) : 0; }
   pp->trace = pf_trace_buffer();
   { const char* e = getenv("DLADMM_PF_XRESIDENT"); pp->x_resident = (e && e[0] == '0') ? 0 : ((i64)m * B * 4 <= (i64)96 << 20); }
   // two CTA sets half a layer period apart once every SM has several tiles of each half (see PfParams::nstreams)
@@ -301,7 +300,7 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   static bool attr_set[MAX_DEVICES] = {false};
   const int dev = current_device_index();
   if (!attr_set[dev]) {
-    DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL));
+    DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (umma::pf_smem_total<NPASS, KC>())));
     attr_set[dev] = true;
   }
   const int grid = pp->nstreams == 2 ? device_sm_count() : (int)std::min<i64>(std::max(pp->units_z, pp->units_e), device_sm_count());
@@ -309,7 +308,7 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
     LaunchScope ls(DLADMM_KIND_FWD_PERSISTENT, st);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::roles_threads(8) + 32); cfg.dynamicSmemBytes = Plan::TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::roles_threads(8) + 32); cfg.dynamicSmemBytes = (umma::pf_smem_total<NPASS, KC>()); cfg.stream = st;
     // the CTAs wait on one another's counters: a cooperative launch makes the driver guarantee (or refuse) that the whole grid is
     // resident at once, whatever else shares the device
     cudaLaunchAttribute attr[1];

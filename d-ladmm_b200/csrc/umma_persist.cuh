@@ -65,7 +65,7 @@ struct PfParams {
   float* obj_part;                     // [total_units][8 epilogue warps] partial sums of the fused objective, or NULL
   unsigned* flags;                     // [2K+1][n_btiles] readiness counters, zeroed by the host before the launch
   long long spin_limit;                // clock64 ticks a producer may wait for a counter before it traps
-  int prefetch;                        // 1: the staging producer L2-prefetches the epilogue inputs of its CTA's NEXT unit
+  int prefetch;                        // D > 0: the staging producer requests every chunk's boxes into L2 D chunks ahead
   int x_resident;                      // 1: loads of X carry an L2 evict_last policy
   long long* trace;                    // debugging (DLADMM_PF_TRACE=1): [PF_TRACE_CTAS][PF_TRACE_UNITS][8] clock64 stamps, or NULL
   PfLayer layer[PF_MAX_LAYERS];
@@ -180,8 +180,17 @@ __device__ __forceinline__ void pf_wait_ready(const PfParams& p, const PfUnit& u
   __syncwarp();
 }
 
+// shared-memory split of the persistent kernel: operand stages vs staging ring (compile-time switches for A/B builds)
+#ifndef PF_STAGES
+#define PF_STAGES 3
+#endif
+#ifndef PF_RING_BYTES
+#define PF_RING_BYTES RING_BYTES
+#endif
 constexpr int PF_SLOT_BYTES = 3 * 8 * TILE_B * 4;         // one staging-ring slot: three arrays x 8 rows (T_0, E/T/L) or one x 16 rows (Z)
-constexpr int PF_DEPTH = RING_BYTES / PF_SLOT_BYTES;      // 6
+constexpr int PF_DEPTH = PF_RING_BYTES / PF_SLOT_BYTES;   // 6
+template <int NPASS, int KC>
+constexpr int pf_smem_total() { return PF_STAGES * SmemPlan<NPASS, KC>::STAGE_BYTES + PF_RING_BYTES + SmemPlan<NPASS, KC>::BAR_BYTES + SmemPlan<NPASS, KC>::ROWTAB + 1024; }
 static_assert(PF_DEPTH % 2 == 0, "ring depth must be a multiple of the epilogue parts");
 
 // the epilogue of ONE unit for one epilogue warp (rows [jw, jw + rpw) of the tile)
@@ -213,7 +222,7 @@ template <int FAM, int PS, int NPASS, int KC>
 __global__ void __launch_bounds__(roles_threads(8) + 32, 1)
 umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid_constant__ PfParams p) {
   using Plan = SmemPlan<NPASS, KC>;
-  constexpr int STAGES = Plan::STAGES;
+  constexpr int STAGES = PF_STAGES;
   constexpr int EPI_WARPS = 8, EPI_PARTS = 2;
   constexpr int SPLIT_WARP0 = EPI_WARP0 + EPI_WARPS, EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS, PUB_WARP = EIN_WARP + 1;
   constexpr int PUB_SLOTS = 4;
@@ -224,7 +233,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem + STAGES * Plan::STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(ring + RING_BYTES);
+  uint64_t* bars = (uint64_t*)(ring + PF_RING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* ready = bars + 2 * STAGES;
@@ -237,7 +246,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
   uint64_t* rfull = pempty + PUB_SLOTS;                                  // [PUB_SLOTS] the scout saw a unit's inputs complete
   uint64_t* rempty = rfull + PUB_SLOTS;                                  // [PUB_SLOTS] ... and both TMA producers took note
   uint32_t* tmem_slot = (uint32_t*)(rempty + PUB_SLOTS);
-  float* rowtab = (float*)(ring + RING_BYTES + Plan::BAR_BYTES);
+  float* rowtab = (float*)(ring + PF_RING_BYTES + Plan::BAR_BYTES);
   static_assert((3 * STAGES + 4 + 2 * MAX_RING_DEPTH + 4 * PUB_SLOTS) * 8 + 8 <= Plan::BAR_BYTES, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -382,37 +391,39 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
       __syncwarp();
       if (++rs == PUB_SLOTS) { rs = 0; rph ^= 1; }
       // The staging ring holds 72 KB -- a fraction of a tile's epilogue inputs (384 KB for an E/T/L unit) -- so with a loaded DRAM
-      // latency of a few microseconds the ring alone keeps too few bytes in flight and the epilogue warps starve.  While this unit
-      // is staged, the inputs of the CTA's NEXT unit are pulled into L2 (no shared memory needed), if that unit's producers are
-      // already done (they almost always are: its stage-below ran a layer ago); the ring loads of the next unit then hit L2.
-      if (p.prefetch && v + walk.stride < walk.total) {
-        const PfUnit nx = walk.decode(p, v + walk.stride);
-        bool ok = true;
+      // latency of a few microseconds the ring alone keeps too few bytes in flight.  p.prefetch = D > 0: every chunk's boxes are
+      // also requested into L2 D chunks ahead (cp.async.bulk.prefetch.tensor needs no shared memory), across the unit boundary
+      // when the next unit's inputs are already complete; the ring loads then hit L2.  (Prefetching the WHOLE next unit was
+      // measured 8-12 % slower: 57 MB per round do not survive in a 126 MB L2 that also streams 14 GB per forward.)
+      PfUnit nx = un; bool nx_ok = false;
+      if (p.prefetch > 0 && v + walk.stride < walk.total) {
+        nx = walk.decode(p, v + walk.stride);
+        nx_ok = true;
         if (nx.stage > 0) {
           const int below = (nx.type == PF_Z) ? p.nt_e : p.nt_z;
-          ok = ld_acquire_u32(p.flags + (i64)(nx.stage - 1) * p.n_btiles + nx.bt) >= (unsigned)(8 * below);
+          nx_ok = ld_acquire_u32(p.flags + (i64)(nx.stage - 1) * p.n_btiles + nx.bt) >= (unsigned)(8 * below);
         }
-        if (ok) {
-          const int nb0 = (int)(nx.bt * TILE_B);
-          const int nchk = nx.type == PF_Z ? 16 : 8;
-          const int nfeat = nx.type == PF_Z ? p.d : p.m;
-          const int nslab = p.last_only ? ((nx.k - 1) & 1) : (nx.k - 1);
-          for (int r = lane * nchk; r < TILE_N; r += 32 * nchk) {      // one box of rows per lane and pass
-            const int row0 = nx.j0 + r;
-            if (row0 >= nfeat) break;
-            if (nx.type == PF_T0) {
-              tma_prefetch_2d(&maps.sE0, nb0, row0); tma_prefetch_2d(&maps.sX, nb0, row0); tma_prefetch_2d(&maps.sL0, nb0, row0);
-            } else if (nx.type == PF_Z) {
-              if (nx.k == 0) tma_prefetch_2d(&maps.sZ0, nb0, row0); else tma_prefetch_3d(&maps.sZ, nb0, row0, nslab);
-            } else {
-              tma_prefetch_2d(&maps.sX, nb0, row0);
-              if (nx.k == 0) tma_prefetch_2d(&maps.sL0, nb0, row0); else tma_prefetch_3d(&maps.sL, nb0, row0, nslab);
-              if (FAM == DLADMM_FAMILY_B) { if (nx.k == 0) tma_prefetch_2d(&maps.sE0, nb0, row0); else tma_prefetch_3d(&maps.sE, nb0, row0, nslab); }
-            }
+      }
+      auto prefetch_chunk = [&](const PfUnit& w, int c) {      // both parts of chunk c of unit w (called by one elected lane)
+        const int wb0 = (int)(w.bt * TILE_B);
+        const int wchk = w.type == PF_Z ? 16 : 8;
+        const int wfeat = w.type == PF_Z ? p.d : p.m;
+        const int wslab = p.last_only ? ((w.k - 1) & 1) : (w.k - 1);
+#pragma unroll
+        for (int h = 0; h < EPI_PARTS; ++h) {
+          const int row0 = w.j0 + h * (TILE_N / EPI_PARTS) + c * wchk;
+          if (row0 >= wfeat) continue;
+          if (w.type == PF_T0) {
+            tma_prefetch_2d(&maps.sE0, wb0, row0); tma_prefetch_2d(&maps.sX, wb0, row0); tma_prefetch_2d(&maps.sL0, wb0, row0);
+          } else if (w.type == PF_Z) {
+            if (w.k == 0) tma_prefetch_2d(&maps.sZ0, wb0, row0); else tma_prefetch_3d(&maps.sZ, wb0, row0, wslab);
+          } else {
+            tma_prefetch_2d(&maps.sX, wb0, row0);
+            if (w.k == 0) tma_prefetch_2d(&maps.sL0, wb0, row0); else tma_prefetch_3d(&maps.sL, wb0, row0, wslab);
+            if (FAM == DLADMM_FAMILY_B) { if (w.k == 0) tma_prefetch_2d(&maps.sE0, wb0, row0); else tma_prefetch_3d(&maps.sE, wb0, row0, wslab); }
           }
         }
-        __syncwarp();
-      }
+      };
       const int b0 = (int)(un.bt * TILE_B);
       const int chk = un.type == PF_Z ? 16 : 8;
       const int n_feat = un.type == PF_Z ? p.d : p.m;
@@ -421,6 +432,12 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
       const int pslab = p.last_only ? ((un.k - 1) & 1) : (un.k - 1);      // slab of the previous layer's iterate (k >= 1)
       const bool has_ep = FAM == DLADMM_FAMILY_B;
       for (int c = 0; c < nch; ++c) {
+        if (p.prefetch > 0 && elect_one()) {
+          const int cp = c + p.prefetch;
+          if (cp < nch) prefetch_chunk(un, cp);
+          else if (nx_ok && cp - nch < (TILE_N / EPI_PARTS) / (nx.type == PF_Z ? 16 : 8)) prefetch_chunk(nx, cp - nch);
+        }
+        __syncwarp();
         for (int h = 0; h < EPI_PARTS; ++h, rp.advance(1, PF_DEPTH)) {
           const int s = rp.s;
           mbar_wait(&eempty[s], rp.ph ^ 1);

@@ -80,3 +80,73 @@ class HostFeed(object):
         cur.wait_event(self._ready[j])
         self._current = j
         return self._bufs[j]
+
+
+class HostDrain(object):
+    """Device -> host counterpart of HostFeed: results of step i are copied to pinned host memory on a side stream while step
+    i+1 computes.
+
+        drain = HostDrain(device)
+        for x in HostFeed(batches, device):
+            Z = model(x, last_only=True)[0][0]
+            host_z = drain.push(Z)          # -> the pinned host tensor of the step `depth` pushes ago, complete, or None
+        for host_z in drain.flush(): ...    # the last `depth` results
+
+    `push` snapshots nothing: it enqueues the copy of `t` after the producer's work (an event on the current stream) and the
+    caller must not overwrite `t` before the copy ran -- the library's outputs are fresh tensors every call, so that holds
+    for them by construction (`record_stream` keeps the allocator from recycling the block early)."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HostDrain needs a CUDA device: d-ladmm_b200 has no CPU path")
+        self._depth = max(1, int(depth))
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._host = [None] * self._depth
+        self._done = [None] * self._depth
+        self._n = 0
+        self.bytes_copied = 0
+
+    def push(self, t):
+        j = self._n % self._depth
+        out = None
+        if self._done[j] is not None:           # the copy that used this pinned buffer `depth` pushes ago
+            self._done[j].synchronize()
+            out = self._host[j]
+            self._host[j] = None
+        buf = self._pool_take(t)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ev)
+            buf.copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        t.record_stream(self._copy_stream)
+        self._host[j], self._done[j] = buf, done
+        self._n += 1
+        self.bytes_copied += t.numel() * t.element_size()
+        return out
+
+    def _pool_take(self, t):
+        """A pinned host buffer of t's shape: recycled from `recycle()` when possible (pinning memory is slow)."""
+        pool = self.__dict__.setdefault("_pool", [])
+        for i, b in enumerate(pool):
+            if b.shape == t.shape and b.dtype == t.dtype:
+                return pool.pop(i)
+        return torch.empty(t.shape, dtype=t.dtype).pin_memory()
+
+    def recycle(self, host_tensor):
+        """Give a host tensor returned by push()/flush() back once it has been consumed."""
+        self.__dict__.setdefault("_pool", []).append(host_tensor)
+
+    def flush(self):
+        """Wait for the outstanding copies; returns their host tensors, oldest first."""
+        outs = []
+        for i in range(self._depth):
+            j = (self._n + i) % self._depth
+            if self._done[j] is not None:
+                self._done[j].synchronize()
+                outs.append(self._host[j])
+                self._host[j] = self._done[j] = None
+        return outs

@@ -106,3 +106,19 @@ def test_many_calls_back_to_back_reuse_the_counters():
         for i in range(20):
             out = model(data.X)
             assert all(torch.equal(a, b) for a, b in zip(out[0] + out[3], ref[0] + ref[3])), i
+
+
+def test_host_drain_returns_every_result_in_order():
+    dev = torch.device("cuda:0")
+    drain = dl.HostDrain(dev)
+    want, got = [], []
+    for i in range(7):
+        t = torch.full((33, 1000), float(i), device=dev) + torch.arange(1000, device=dev)
+        want.append(t.cpu())
+        h = drain.push(t)
+        del t
+        if h is not None:
+            got.append(h.clone()); drain.recycle(h)
+    got += [h.clone() for h in drain.flush()]
+    assert len(got) == 7 and all(torch.equal(a, b) for a, b in zip(got, want))
+    assert drain.bytes_copied == 7 * 33 * 1000 * 4
