@@ -7,7 +7,7 @@ to PyTorch eager or to the CPU.
 """
 from . import _lib
 from .net import (DLADMMNet, DLADMMNetFull, DLADMMNetLasso, DLADMMNetLena, DLADMMNetLtheta, DLADMMNetScalar,
-                  DLADMMNetTied, DLADMMNetNewS, DLADMMNetTiedNewS, DLADMMNetPtiedNewS, VARIANT_CLASSES, default_precision)
+                  DLADMMNetTied, DLADMMNetNewS, DLADMMNetTiedNewS, DLADMMNetPtiedNewS, VARIANT_CLASSES, default_precision, resolve_precision)
 from .function import UnrolledLADMM, LayerSpec, run_forward
 from .gen_syn import gen_syn_data, SynData, replace_A_columns, load_mat, save_mat
 from .objective import l1l1_objective
@@ -18,7 +18,7 @@ from .host_feed import HostFeed, HostDrain
 __all__ = ["DLADMMNet", "DLADMMNetScalar", "DLADMMNetFull", "DLADMMNetTied", "DLADMMNetLasso", "DLADMMNetLena",
            "DLADMMNetLtheta", "DLADMMNetNewS", "DLADMMNetTiedNewS", "DLADMMNetPtiedNewS", "VARIANT_CLASSES", "UnrolledLADMM", "LayerSpec", "run_forward", "gen_syn_data",
            "SynData", "l1l1_objective", "column_shard", "allreduce_gradients", "ShardedTrainer",
-           "default_precision", "library_path", "query_device", "mu_updater_dict", "HostFeed", "HostDrain", "replace_A_columns", "load_mat", "save_mat"]
+           "default_precision", "resolve_precision", "library_path", "query_device", "mu_updater_dict", "HostFeed", "HostDrain", "replace_A_columns", "load_mat", "save_mat"]
 
 
 def library_path():

@@ -9,8 +9,8 @@ LIB_PATH = os.environ.get("DLADMM_LIB_PATH") or os.path.join(HERE, "csrc", "libd
 
 ABI_VERSION = 5
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
-PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_BF16 = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "bf16": PREC_BF16}
+PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_BF16, PREC_TF32_BF16X2 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "bf16": PREC_BF16, "tf32_bf16x2": PREC_TF32_BF16X2}
 # dladmm_metric: index of each per-layer metric in the (K, MET_COUNT) output of a forward with `metrics`
 METRICS = ("l1_z", "sqerr_z", "l1_res", "sq_res", "sqerr_e", "sqerr_az", "l1_e", "dot_lx", "dgap_l", "dgap_atl")
 MET_COUNT = len(METRICS)

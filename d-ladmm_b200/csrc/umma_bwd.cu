@@ -6,7 +6,7 @@ namespace dladmm {
 
 template <int NPASS>
 static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const float* s1ptr, float* C, int ldc, cudaStream_t st) {
-  constexpr int KC = NPASS == 3 ? 16 : 32;
+  constexpr int KC = NPASS >= 3 ? 16 : 32;
   using Plan = umma::NtPlan<NPASS, KC>;
   const CUtensorMapSwizzle sw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tP, tQ;
@@ -166,13 +166,13 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
 int umma_backward(const dladmm_problem* p, const dladmm_cotangents* g, const Workspace& sw, void* ws_base, cudaStream_t st) {
   char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
   UBwdWorkspace w = ucarve_bwd(p, base);
-  const bool x3 = p->precision == DLADMM_PREC_TF32X3;
+  const bool x3 = p->precision == DLADMM_PREC_TF32X3, mix = p->precision == DLADMM_PREC_TF32_BF16X2;
   const int pm = param_mode(p);
 #define DL_BPM(F, NP)                                                                                                  \
   (pm == umma::PM_SCALAR ? backward_umma<F, NP, umma::PM_SCALAR>(p, g, sw, w, st)                                      \
                          : pm == umma::PM_ROWS ? backward_umma<F, NP, umma::PM_ROWS>(p, g, sw, w, st)                  \
                                                : backward_umma<F, NP, umma::PM_GENERAL>(p, g, sw, w, st))
-#define DL_BWD(F) (x3 ? DL_BPM(F, 3) : DL_BPM(F, 1))
+#define DL_BWD(F) (x3 ? DL_BPM(F, 3) : mix ? DL_BPM(F, 4) : DL_BPM(F, 1))
   switch (p->family) {
     case DLADMM_FAMILY_A: return DL_BWD(DLADMM_FAMILY_A);
     case DLADMM_FAMILY_B: return DL_BWD(DLADMM_FAMILY_B);

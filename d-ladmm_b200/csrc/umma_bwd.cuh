@@ -309,9 +309,43 @@ struct UEpiBG2 {
 // Both operands are K-major (batch contiguous).  One 128 x 256 output tile per CTA over a slice of the batch;
 // partial results are added to dW with fp32 reductions (red.global.add).
 constexpr int NT_EPI_WARPS = 16;          // epilogue warps of the dW kernel (atomics of a 128 x 256 tile): 4 per quadrant
+// Mixed mode (NPASS == 4) of the dW product: P.Q^T = trunc(P).trunc(Q)^T on kind::tf32 (the raw words) + bf16(P_small).bf16(Q)^T +
+// bf16(P).bf16(Q_small)^T on kind::f16.  Both operands are K-major rows of 16 floats (64 bytes, SWIZZLE_64B: 16-byte chunk c of
+// row r sits at chunk c ^ ((r >> 1) & 3)); the split writes, for every row, a 64-byte row [bf16(x)[16] | bf16(x_small)[16]] with the
+// same swizzle into the second half of the stage.  A thread owns half a row: 2 x 16 bytes in, 2 x 16 bytes out.
+template <int ROWS, int NTHREADS>
+__device__ __forceinline__ void split_rows_mix(const uint8_t* raw, uint8_t* packed, int tid) {
+  constexpr int UNITS = ROWS * 2;
+  constexpr int N = (UNITS + NTHREADS - 1) / NTHREADS;
+  float4 va[N], vb[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int u = tid + i * NTHREADS;
+    if (u < UNITS) {
+      const int r = u >> 1, h = u & 1, sw = (r >> 1) & 3;
+      va[i] = *reinterpret_cast<const float4*>(raw + r * 64 + (((2 * h) ^ sw) << 4));
+      vb[i] = *reinterpret_cast<const float4*>(raw + r * 64 + (((2 * h + 1) ^ sw) << 4));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int u = tid + i * NTHREADS;
+    if (u < UNITS) {
+      const int r = u >> 1, h = u & 1, sw = (r >> 1) & 3;
+      const float4 x0 = va[i], x1 = vb[i];
+      uint4 hi, lo;
+      hi.x = pack_bf16x2(x0.x, x0.y); hi.y = pack_bf16x2(x0.z, x0.w); hi.z = pack_bf16x2(x1.x, x1.y); hi.w = pack_bf16x2(x1.z, x1.w);
+      lo.x = pack_bf16x2(tf32_small(x0.x), tf32_small(x0.y)); lo.y = pack_bf16x2(tf32_small(x0.z), tf32_small(x0.w));
+      lo.z = pack_bf16x2(tf32_small(x1.x), tf32_small(x1.y)); lo.w = pack_bf16x2(tf32_small(x1.z), tf32_small(x1.w));
+      *reinterpret_cast<uint4*>(packed + r * 64 + ((h ^ sw) << 4)) = hi;
+      *reinterpret_cast<uint4*>(packed + r * 64 + (((2 + h) ^ sw) << 4)) = lo;
+    }
+  }
+}
+
 template <int NPASS, int KC>
 struct NtPlan {
-  static constexpr int NOPS = NPASS == 3 ? 2 : 1;
+  static constexpr int NOPS = NPASS >= 3 ? 2 : 1;
   static constexpr int A_BYTES = 128 * KC * 4;
   static constexpr int B_BYTES = TILE_N * KC * 4;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [P raw | Q raw] [P small | Q small]
@@ -355,7 +389,7 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmP); prefetch_tmap(&tmQ);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], NT_EPI_WARPS); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
@@ -397,11 +431,18 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             umma_tf32(tmem_base, desc_at(hi, a_lo + ks * 2), desc_at(hi, b_lo + ks * 2), idesc, (kc == 0 && ks == 0) ? 0u : 1u);
         }
         __syncwarp();
-        if (NPASS == 3) {
+        if (NPASS >= 3) {
           mbar_wait(&ready[s], ph);
           tc_fence_after();
         }
         if (elect_one()) {
+          if (NPASS == 4) {
+            // bf16 correction products (K = 16 = the chunk): packed rows [bf16(x) | bf16(x_small)], 32 bytes each
+            constexpr uint32_t idesc16 = make_idesc(128, TILE_N, 0, 0, 1u);
+            const uint32_t a16 = a_lo + (Plan::RAW_BYTES >> 4), b16 = b_lo + (Plan::RAW_BYTES >> 4);
+            umma_f16(tmem_base, desc_at(hi, a16 + 2), desc_at(hi, b16), idesc16, 1u);      // P_small . Q
+            umma_f16(tmem_base, desc_at(hi, a16), desc_at(hi, b16 + 2), idesc16, 1u);      // P . Q_small
+          }
           if (NPASS == 3) {
 #pragma unroll
             for (int ks = 0; ks < KC / UMMA_K; ++ks) {
@@ -419,20 +460,25 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else if (warp >= SPLIT_WARP0) {
-      if (NPASS == 3 && warp < SPLIT_WARP0 + SPLIT_WARPS) {   // split both operand tiles (adjacent) in shared memory
-        const int tid = threadIdx.x - SPLIT_WARP0 * 32;
+      // (the four dedicated splitter warps of the common role layout idle here: the split is done by the 16 epilogue warps, below)
+    } else {
+      // During the mainloop the epilogue warps have nothing to do (one accumulator, drained once at the end): all 16 of them
+      // split the operand tiles of every stage in shared memory -- 24 KB per chunk spread over 512 threads instead of 128, which takes
+      // the split off the stage turn-around (TMA -> split -> MMA -> free), the bound of this kernel's mainloop.
+      if (NPASS >= 3) {
+        const int tid = threadIdx.x - EPI_WARP0 * 32;
         int s = 0; uint32_t ph = 0;
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(&full[s], ph);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
-          split_tile<Plan::RAW_BYTES, SPLIT_WARPS * 32>(st, st + Plan::RAW_BYTES, tid);
+          if (NPASS == 3) split_tile<Plan::RAW_BYTES, NT_EPI_WARPS * 32>(st, st + Plan::RAW_BYTES, tid);
+          else split_rows_mix<(Plan::RAW_BYTES / 64), NT_EPI_WARPS * 32>(st, st + Plan::RAW_BYTES, tid);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ready[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
-    } else {
       const int q = warp & 3;
       const int half = (warp - EPI_WARP0) >> 2;
       const int row = i0 + q * 32 + lane;               // row of dW (TMEM lane)

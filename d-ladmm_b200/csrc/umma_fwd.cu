@@ -200,7 +200,7 @@ static bool persistent_allowed() {
 
 static bool persistent_eligible(const dladmm_problem* p) {
   if (!persistent_allowed()) return false;
-  if (p->precision != DLADMM_PREC_TF32X3 && p->precision != DLADMM_PREC_TF32) return false;
+  if (p->precision != DLADMM_PREC_TF32X3 && p->precision != DLADMM_PREC_TF32 && p->precision != DLADMM_PREC_TF32_BF16X2) return false;
   if (p->K < 1 || p->K > umma::PF_MAX_LAYERS) return false;
   // Tensor-bound shapes gain nothing from the merged schedule (their per-layer launches already run ~90 % of the tensor peak and
   // the one-launch version measured 5 % slower at m 1000, d 2000: 50.3 vs 47.7 ms per 32 768-column forward on the same box);
@@ -282,9 +282,9 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const CUtensorMapSwizzle asw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, nsw = CU_TENSOR_MAP_SWIZZLE_NONE;
   if ((rc = umma::make_tmap_2d(&mp->A_big, w.Ab, w.m256, w.dp, w.dp, KC, umma::TILE_N, wsw))) return rc;
-  if ((rc = umma::make_tmap_2d(&mp->A_small, NPASS == 3 ? w.As : w.Ab, w.m256, w.dp, w.dp, KC, umma::TILE_N, wsw))) return rc;
+  if ((rc = umma::make_tmap_2d(&mp->A_small, NPASS >= 3 ? w.As : w.Ab, w.m256, w.dp, w.dp, KC, umma::TILE_N, wsw))) return rc;
   if ((rc = umma::make_tmap_3d(&mp->W_big, w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, umma::TILE_N, wsw))) return rc;
-  if ((rc = umma::make_tmap_3d(&mp->W_small, NPASS == 3 ? w.Ws : w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, umma::TILE_N, wsw))) return rc;
+  if ((rc = umma::make_tmap_3d(&mp->W_small, NPASS >= 3 ? w.Ws : w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, umma::TILE_N, wsw))) return rc;
   if ((rc = umma::make_tmap_2d(&mp->actZ0, p->Z0, d, B, B, 32, KC, asw))) return rc;
   if ((rc = umma::make_tmap_3d(&mp->actZ, p->Z, depth, d, B, B, s.zs, 32, KC, asw))) return rc;
   if ((rc = umma::make_tmap_3d(&mp->actV, pp->V, p->Vsave ? K : 1, m, B, B, s.ms, 32, KC, asw))) return rc;
@@ -329,13 +329,13 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
 int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {
   char* base = (char*)(((uintptr_t)ws_base + 1023) & ~(uintptr_t)1023);
   UWorkspace w = ucarve(p, base);
-  const bool x3 = p->precision == DLADMM_PREC_TF32X3, bf = p->precision == DLADMM_PREC_BF16;
+  const bool x3 = p->precision == DLADMM_PREC_TF32X3, bf = p->precision == DLADMM_PREC_BF16, mix = p->precision == DLADMM_PREC_TF32_BF16X2;
   const int pm = param_mode(p);
 #define DL_PM(FN, F, NP)                                                                                  \
   (pm == umma::PM_SCALAR ? FN<F, NP, umma::PM_SCALAR>(p, w, st)                                           \
                          : pm == umma::PM_ROWS ? FN<F, NP, umma::PM_ROWS>(p, w, st) : FN<F, NP, umma::PM_GENERAL>(p, w, st))
   if (persistent_eligible(p)) {
-#define DL_PF(F) (x3 ? DL_PM(forward_persistent, F, 3) : DL_PM(forward_persistent, F, 1))
+#define DL_PF(F) (x3 ? DL_PM(forward_persistent, F, 3) : mix ? DL_PM(forward_persistent, F, 4) : DL_PM(forward_persistent, F, 1))
     switch (p->family) {
       case DLADMM_FAMILY_A: return DL_PF(DLADMM_FAMILY_A);
       case DLADMM_FAMILY_B: return DL_PF(DLADMM_FAMILY_B);
@@ -343,7 +343,7 @@ int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {
     }
 #undef DL_PF
   }
-#define DL_FWD(F) (x3 ? DL_PM(forward_umma, F, 3) : bf ? DL_PM(forward_umma, F, 2) : DL_PM(forward_umma, F, 1))
+#define DL_FWD(F) (x3 ? DL_PM(forward_umma, F, 3) : mix ? DL_PM(forward_umma, F, 4) : bf ? DL_PM(forward_umma, F, 2) : DL_PM(forward_umma, F, 1))
   switch (p->family) {
     case DLADMM_FAMILY_A: return DL_FWD(DLADMM_FAMILY_A);
     case DLADMM_FAMILY_B: return DL_FWD(DLADMM_FAMILY_B);

@@ -119,6 +119,49 @@ __device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* small, i
   for (int i = 0; i < N; ++i)
     dst[tid + i * NTHREADS] = make_float4(tf32_small(v[i].x), tf32_small(v[i].y), tf32_small(v[i].z), tf32_small(v[i].w));
 }
+// Mixed mode (NPASS == 4, DLADMM_PREC_TF32_BF16X2): x*w = trunc_tf32(x)*rna_tf32(w) on kind::tf32 plus the two first-order correction
+// products on kind::f16 at twice the rate -- bf16(x)*bf16(w - rna_tf32(w)) and bf16(x - trunc_tf32(x))*bf16(rna_tf32(w)); the
+// correction operands only need ~8 significant bits because they are already 2^-11 of the product.  The splitter warps read the
+// raw fp32 activation tile (four boxes of 32 batch columns x 16 k-rows, 128-byte rows whose 32-byte chunks are XOR-permuted by
+// row % 4: the TMA SWIZZLE_128B_ATOM_32B image) and write the two bf16 tiles next to it in the MN-major SWIZZLE_128B image of
+// the bf16 mode (two boxes of 64 batch columns x 16 k-rows, 128-byte rows whose 16-byte chunks are XOR-permuted by row % 8).
+// A thread owns 8 consecutive batch columns of one k-row: 32 bytes in, 16 + 16 bytes out; the two 16-byte loads of a thread are
+// issued in opposite order by neighbouring column groups so that a quarter warp covers all 32 banks.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <int NTHREADS>
+__device__ __forceinline__ void split_tile_mix(const uint8_t* raw, uint8_t* hi, uint8_t* lo, int tid) {
+  constexpr int UNITS = 16 * (TILE_B / 8);               // (k-row, group of 8 batch columns)
+  constexpr int N = UNITS / NTHREADS;
+  static_assert(N * NTHREADS == UNITS, "units must divide over the splitter threads");
+  float4 va[N], vb[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int u = tid + i * NTHREADS;
+    const int c8 = u & 15, r = u >> 4;                   // column group 0..15, k-row 0..15
+    const int g = c8 >> 2, c32 = c8 & 3;
+    const float4* src = reinterpret_cast<const float4*>(raw + g * 2048 + r * 128 + ((c32 ^ (r & 3)) << 5));
+    const int sw = g & 1;
+    va[i] = src[sw]; vb[i] = src[sw ^ 1];
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int u = tid + i * NTHREADS;
+    const int c8 = u & 15, r = u >> 4;
+    const bool sw = ((c8 >> 2) & 1) != 0;
+    const float4 x0 = sw ? vb[i] : va[i], x1 = sw ? va[i] : vb[i];      // columns 0..3, 4..7 of the group
+    uint4 h, l;
+    h.x = pack_bf16x2(x0.x, x0.y); h.y = pack_bf16x2(x0.z, x0.w); h.z = pack_bf16x2(x1.x, x1.y); h.w = pack_bf16x2(x1.z, x1.w);
+    l.x = pack_bf16x2(tf32_small(x0.x), tf32_small(x0.y)); l.y = pack_bf16x2(tf32_small(x0.z), tf32_small(x0.w));
+    l.z = pack_bf16x2(tf32_small(x1.x), tf32_small(x1.y)); l.w = pack_bf16x2(tf32_small(x1.z), tf32_small(x1.w));
+    const int off = (c8 >> 3) * 2048 + r * 128 + (((c8 & 7) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
 // Single-pass TF32: the tensor core TRUNCATES fp32 operands to tf32 -- a bias toward zero that is coherent from layer to layer
 // (measured: 7.7e-4 per product, but 2.2e-2 on the iterates after 15 layers; bf16 operands rounded to nearest: 2.4e-3 per
 // product, 5.6e-3 after 15 layers).  The splitter warps therefore round the activation tile to the nearest tf32 in place.
@@ -311,7 +354,13 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmShape& gs, i64 tile) {
 // ring by TMA: a dedicated producer thread streams (CHUNK rows x 128 columns) boxes of every input array, several
 // chunks -- and tiles -- ahead of the epilogue warps, so the epilogue never waits a DRAM round trip in registers.
 constexpr int MAX_EIN = 10;              // staged input arrays per epilogue
-constexpr int RING_BYTES = 72 * 1024;    // staging ring; depth = RING_BYTES / (present arrays * CHUNK * 512 B)
+#ifndef UMMA_RING_BYTES
+#define UMMA_RING_BYTES (72 * 1024)
+#endif
+#ifndef UMMA_STAGES
+#define UMMA_STAGES 3
+#endif
+constexpr int RING_BYTES = UMMA_RING_BYTES;    // staging ring; depth = RING_BYTES / (present arrays * CHUNK * 512 B)
 
 struct EMaps { CUtensorMap m[MAX_EIN]; CUtensorMap mk; };   // float inputs + the 1-byte prox mask of the chunk
 constexpr uint32_t EIN_MASK_BIT = 1u << 31;                 // in_mask bit: the mask bytes are staged too
@@ -319,12 +368,12 @@ constexpr uint32_t EIN_MASK_BIT = 1u << 31;                 // in_mask bit: the 
 template <int NPASS, int KC>
 struct SmemPlan {
   static constexpr int EB = NPASS == 2 ? 2 : 4;                      // operand element bytes (bf16 mode: 2)
-  static constexpr int NOPS = NPASS == 3 ? 2 : 1;                    // big (+ small)
+  static constexpr int NOPS = NPASS >= 3 ? 2 : 1;                    // big (+ small; mixed mode: + the two bf16 correction operands)
   static constexpr int A_BYTES = TILE_B * KC * EB;                   // one operand part
   static constexpr int B_BYTES = TILE_N * KC * EB;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | A small] [B big | B small]
   static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = UMMA_STAGES;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int ROWTAB = 8192;                                  // per-row parameter table of the epilogue (umma_epilogues.cuh)
   static constexpr int TOTAL = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + ROWTAB + 1024;   // + alignment slack
@@ -410,7 +459,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB_big);
-    if (NPASS == 3) prefetch_tmap(&tmB_small);
+    if (NPASS >= 3) prefetch_tmap(&tmB_small);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], SPLIT_WARPS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     for (int s = 0; s < depth; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 4); }
@@ -450,7 +499,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // weights, pre-split by the prep kernel: one box of (KC k x 256 rows) per part
           uint8_t* b_dst = st + Plan::NOPS * Plan::A_BYTES;
           tma_load_2d(b_dst, &tmB_big, &full[s], kc * KC, j0);
-          if (NPASS == 3) tma_load_2d(b_dst + Plan::B_BYTES, &tmB_small, &full[s], kc * KC, j0);
+          if (NPASS >= 3) tma_load_2d(b_dst + Plan::B_BYTES, &tmB_small, &full[s], kc * KC, j0);
           UMMA_TR(gs, trp, 1);
         }
         ++trp;
@@ -497,17 +546,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t db_small = desc_at(b_hi, b_lo + (Plan::B_BYTES >> 4) + ks * (32 >> 4));
               umma_tf32(d_tmem, da_big, db_small, idesc, first);
               umma_tf32(d_tmem, da_big, db_big, idesc, 1u);
+            } else if (NPASS == 4) {
+              umma_tf32(d_tmem, da_big, db_big, idesc, first);       // trunc_tf32(x) * rna_tf32(w): reads the raw words
             } else if (NPASS == 2) {
               umma_op<BF>(d_tmem, da_big, db_big, idesc, first);
             }
           }
         }
         __syncwarp();
-        if (NPASS == 3 || NPASS == 1) {
+        if (NPASS == 3 || NPASS == 1 || NPASS == 4) {
           mbar_wait(&ready[s], ph);                    // small part written (3 passes) / tile rounded to tf32 (1 pass) by the splitters
           tc_fence_after();
         }
         if (elect_one()) {
+          if (NPASS == 4) {
+            // the two correction products on kind::f16 (K = 16 = the whole chunk): bf16(x) * bf16(w_small), bf16(x_small) * bf16(w_big).
+            // Operand images: [raw fp32 8 KB | bf16(x) 4 KB | bf16(x_small) 4 KB] and, behind the tf32 weights, 64-byte rows of
+            // [bf16(w_big)[16] | bf16(w_small)[16]] written by the prep kernel (same box, same SWIZZLE_64B as the tf32 part).
+            constexpr uint32_t a16_hi = desc_hi(1024, LAYOUT_SW128);
+            constexpr uint32_t idesc16 = make_idesc(TILE_B, TILE_N, 1, 0, 1u), idesc16_half = make_idesc(TILE_B, TILE_N / 2, 1, 0, 1u);
+            const uint32_t id16 = idesc == idesc_full ? idesc16 : idesc16_half;
+            const uint32_t a16 = a_lo + (Plan::A_BYTES >> 4), b16 = b_lo + (Plan::B_BYTES >> 4);
+            umma_f16(d_tmem, desc_at(a16_hi, a16), desc_at(b_hi, b16 + (32 >> 4)), id16, 1u);
+            umma_f16(d_tmem, desc_at(a16_hi, a16 + (Plan::A_BYTES >> 5)), desc_at(b_hi, b16), id16, 1u);
+          }
           if (NPASS == 1) {
 #pragma unroll
             for (int ks = 0; ks < KC / MMA_K; ++ks)
@@ -569,7 +631,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= SPLIT_WARP0) {
     // ===== operand splitters (3-pass mode): small = x - trunc_tf32(x) of the activation tile, in shared memory =====
-    if (NPASS == 3 || NPASS == 1) {
+    if (NPASS == 3 || NPASS == 1 || NPASS == 4) {
       const int tid = threadIdx.x - SPLIT_WARP0 * 32;
       int s = 0; uint32_t ph = 0; int trs = 0; (void)trs;
       for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -578,6 +640,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (tid == 0) UMMA_TR(gs, trs, 2);
           uint8_t* st = smem + s * Plan::STAGE_BYTES;
           if (NPASS == 3) split_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, tid);
+          else if (NPASS == 4) split_tile_mix<SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, st + Plan::A_BYTES + Plan::A_BYTES / 2, tid);
           else round_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, tid);
           fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
           __syncwarp();

@@ -142,6 +142,14 @@ static __global__ void __launch_bounds__(256) prep_split_kernel(SplitJobs jobs, 
       const float b = umma::tf32_rna(v);
       jb.big[(i64)r * Cpad + c] = b;
       jb.small[(i64)r * Cpad + c] = v - b;
+    } else if (NPASS == 4) {
+      // mixed mode: tf32 part as above; the "small" array holds, per 16-element k-chunk, a 64-byte row of
+      // [bf16(big)[16] | bf16(small)[16]] -- the K-major operands of the two kind::f16 correction products
+      const float b = umma::tf32_rna(v);
+      jb.big[(i64)r * Cpad + c] = b;
+      __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(jb.small) + ((i64)r * Cpad + (c & ~15)) * 2 + (c & 15);
+      pk[0] = __float2bfloat16_rn(b);
+      pk[16] = __float2bfloat16_rn(v - b);
     } else if (NPASS == 2) {
       reinterpret_cast<__nv_bfloat16*>(jb.big)[(i64)r * Cpad + c] = __float2bfloat16_rn(v);
     } else {
@@ -172,6 +180,14 @@ static __global__ void __launch_bounds__(256) prep_split_t_kernel(SplitJobs jobs
       const float b = umma::tf32_rna(v);
       jb.big[(i64)r * Cpad + c] = b;
       jb.small[(i64)r * Cpad + c] = v - b;
+    } else if (NPASS == 4) {
+      // mixed mode: tf32 part as above; the "small" array holds, per 16-element k-chunk, a 64-byte row of
+      // [bf16(big)[16] | bf16(small)[16]] -- the K-major operands of the two kind::f16 correction products
+      const float b = umma::tf32_rna(v);
+      jb.big[(i64)r * Cpad + c] = b;
+      __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(jb.small) + ((i64)r * Cpad + (c & ~15)) * 2 + (c & 15);
+      pk[0] = __float2bfloat16_rn(b);
+      pk[16] = __float2bfloat16_rn(v - b);
     } else if (NPASS == 2) {
       reinterpret_cast<__nv_bfloat16*>(jb.big)[(i64)r * Cpad + c] = __float2bfloat16_rn(v);
     } else {
@@ -292,7 +308,7 @@ static int device_sm_count() {
 // C[j,b] = sum_k Wt[j,k] Act[k,b] with a fused epilogue.  act_* are (Kdim x B) batch-contiguous; w_* are prepared
 // (n_pad x k_pad) K-major arrays.
 // NPASS: 3 = 3xTF32, 1 = TF32, 2 = BF16 (act / w_big are then bf16 arrays; act has pitch `act_pitch` elements).
-template <int NPASS> struct KChunk { static constexpr int value = NPASS == 3 ? 16 : (NPASS == 2 ? 64 : 32); };
+template <int NPASS> struct KChunk { static constexpr int value = NPASS >= 3 ? 16 : (NPASS == 2 ? 64 : 32); };
 
 template <class Epi, int NPASS>
 static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, const void* w_small,
@@ -309,7 +325,7 @@ static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, c
     if ((rc = umma::make_tmap_2d(&tA, (const float*)act, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     if ((rc = umma::make_tmap_2d(&tBb, (const float*)w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
-    if (NPASS == 3) {
+    if (NPASS >= 3) {
       if ((rc = umma::make_tmap_2d(&tBs, (const float*)w_small, n_pad, k_pad, k_pad, KC, umma::TILE_N, wsw))) return rc;
     } else {
       tBs = tBb;

@@ -226,7 +226,8 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
   constexpr int EPI_WARPS = 8, EPI_PARTS = 2;
   constexpr int SPLIT_WARP0 = EPI_WARP0 + EPI_WARPS, EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS, PUB_WARP = EIN_WARP + 1;
   constexpr int PUB_SLOTS = 4;
-  static_assert(NPASS == 3 || NPASS == 1, "tf32x3 or single-pass tf32");
+  static_assert(NPASS == 3 || NPASS == 1 || NPASS == 4, "tf32x3, single-pass tf32 or tf32 + two bf16 correction passes");
+  static_assert(NPASS != 4 || KC == 16, "mixed mode: 16-row chunks");
   constexpr int MMA_K = 8;
   constexpr uint32_t B_LAYOUT = KC * 4 == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
   constexpr uint32_t B_SBO = 8 * KC * 4;
@@ -304,7 +305,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
 #pragma unroll
             for (int g = 0; g < TILE_B / 32; ++g) tma_load_3d(st + g * (KC * 128), &maps.actV, &full[s], b0 + g * 32, kc * KC, vslab);
             tma_load_3d(b_dst, &maps.W_big, &full[s], kc * KC, un.j0, widx);
-            if (NPASS == 3) tma_load_3d(b_dst + Plan::B_BYTES, &maps.W_small, &full[s], kc * KC, un.j0, widx);
+            if (NPASS >= 3) tma_load_3d(b_dst + Plan::B_BYTES, &maps.W_small, &full[s], kc * KC, un.j0, widx);
           } else {
             if (un.type == PF_T0) {
 #pragma unroll
@@ -314,7 +315,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
               for (int g = 0; g < TILE_B / 32; ++g) tma_load_3d(st + g * (KC * 128), &maps.actZ, &full[s], b0 + g * 32, kc * KC, zslab);
             }
             tma_load_2d(b_dst, &maps.A_big, &full[s], kc * KC, un.j0);
-            if (NPASS == 3) tma_load_2d(b_dst + Plan::B_BYTES, &maps.A_small, &full[s], kc * KC, un.j0);
+            if (NPASS >= 3) tma_load_2d(b_dst + Plan::B_BYTES, &maps.A_small, &full[s], kc * KC, un.j0);
           }
         }
         __syncwarp();
@@ -357,11 +358,26 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
           }
           __syncwarp();
         }
+        if (NPASS == 4) {
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < KC / MMA_K; ++ks)
+              umma_tf32(d_tmem, desc_at(a_hi, a_lo + ks * (A_KSTEP >> 4)), desc_at(b_hi, b_lo + ks * (32 >> 4)), idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+          }
+          __syncwarp();
+        }
         mbar_wait(&ready[s], ph);
         tc_fence_after();
         if (elect_one()) {
+          if (NPASS == 4) {         // the two bf16 correction products (umma_gemm.cuh, split_tile_mix)
+            constexpr uint32_t a16_hi = desc_hi(1024, LAYOUT_SW128);
+            constexpr uint32_t idesc16 = make_idesc(TILE_B, TILE_N, 1, 0, 1u);
+            const uint32_t a16 = a_lo + (Plan::A_BYTES >> 4), b16 = b_lo + (Plan::B_BYTES >> 4);
+            umma_f16(d_tmem, desc_at(a16_hi, a16), desc_at(b_hi, b16 + (32 >> 4)), idesc16, 1u);
+            umma_f16(d_tmem, desc_at(a16_hi, a16 + (Plan::A_BYTES >> 5)), desc_at(b_hi, b16), idesc16, 1u);
+          }
 #pragma unroll
-          for (int ks = 0; ks < KC / MMA_K; ++ks) {
+          for (int ks = 0; ks < (NPASS == 4 ? 0 : KC / MMA_K); ++ks) {
             const uint64_t db_big = desc_at(b_hi, b_lo + ks * (32 >> 4));
             if (NPASS == 3) {
               umma_tf32(d_tmem, desc_at(a_hi, a_lo + (Plan::A_BYTES >> 4) + ks * (A_KSTEP >> 4)), db_big, idesc, 1u);
@@ -527,6 +543,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         mbar_wait(&full[s], ph);
         uint8_t* st = smem + s * Plan::STAGE_BYTES;
         if (NPASS == 3) split_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, tid);
+        else if (NPASS == 4) split_tile_mix<SPLIT_WARPS * 32>(st, st + Plan::A_BYTES, st + Plan::A_BYTES + Plan::A_BYTES / 2, tid);
         else round_tile<Plan::A_BYTES, SPLIT_WARPS * 32>(st, tid);
         fence_proxy_async();
         __syncwarp();

@@ -48,8 +48,24 @@ _SLOT_OF = {
 _FAMILY_KEY = {_lib.FAMILY_A: "A", _lib.FAMILY_B: "B", _lib.FAMILY_C: "C"}
 
 
+# Shapes from which the split-precision mode (one kind::tf32 pass + two bf16 correction passes) is both faster and more accurate
+# than three kind::tf32 passes.  Measured error models per product with reduction length K (profiles/r02_precision_table.md):
+#   tf32x3       7.5e-9 * K   -- the tensor core adds into its fp32 accumulator with round-toward-zero, once per MMA (3 K / 8 MMAs)
+#   tf32_bf16x2  5e-9 * K (K / 4 MMAs) plus ~1e-6 of unbiased bf16 rounding of the correction operands, independent of K
+# They cross at K ~ 180.
+AUTO_MIXED_MIN_DIM = 192
+
+
 def default_precision():
-    return os.environ.get("DLADMM_PRECISION", "tf32x3")
+    """DLADMM_PRECISION, or "auto": tf32_bf16x2 when min(m, d) >= AUTO_MIXED_MIN_DIM, else tf32x3 (the more accurate fp32-class mode
+    at that shape; below ~200 rows the products are latency-bound and the pass count does not matter)."""
+    return os.environ.get("DLADMM_PRECISION", "auto")
+
+
+def resolve_precision(precision, m, d):
+    if precision == "auto":
+        return "tf32_bf16x2" if min(m, d) >= AUTO_MIXED_MIN_DIM else "tf32x3"
+    return precision
 
 
 def _param_table(variant, m, d, bs):
@@ -86,7 +102,9 @@ class DLADMMNet(nn.Module):
 
     ``variant`` selects which of the reference's re-declared classes is mirrored (default ``scalar``);
     the per-variant subclasses below fix it so a script can swap its inline class for an import.
-    ``precision``: "fp32" (CUDA-core FFMA), "tf32x3" / "tf32" (tcgen05).
+    ``precision``: "auto" (default: "tf32_bf16x2" from min(m, d) >= 192, "tf32x3" below), "tf32_bf16x2" (tcgen05, one kind::tf32
+    pass + two bf16 correction passes, fp32-level products), "tf32x3" (three kind::tf32 passes), "tf32" / "bf16" (single pass,
+    stated-tolerance options), "fp32" (CUDA-core FFMA).
     """
     variant = "scalar"
 
@@ -108,7 +126,7 @@ class DLADMMNet(nn.Module):
         self.m, self.n, self.d = m, n, d
         self.batch_size = batch_size
         self.layers = layers
-        self.precision = precision or default_precision()
+        self.precision = resolve_precision(precision or default_precision(), int(m), int(d))
         if self.precision not in _lib.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
         if device is None:

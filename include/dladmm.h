@@ -58,9 +58,14 @@ typedef enum dladmm_precision {
   DLADMM_PREC_FP32 = 0,     /* CUDA-core FFMA, fp32 products and accumulation */
   DLADMM_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3 passes (big*big + big*small + small*big), fp32 accumulate in TMEM */
   DLADMM_PREC_TF32 = 2,     /* tcgen05 kind::tf32, single pass (stated-tolerance option: ~1e-3 relative per product) */
-  DLADMM_PREC_BF16 = 3      /* tcgen05 kind::f16 on bf16 operands, single pass, fp32 accumulate (stated-tolerance option:
+  DLADMM_PREC_BF16 = 3,     /* tcgen05 kind::f16 on bf16 operands, single pass, fp32 accumulate (stated-tolerance option:
                                ~4e-3 relative per product).  Iterates stay fp32 in HBM (the reference's API); operands are
                                rounded to bf16 in shared memory by the consumer, weights once per call. */
+  DLADMM_PREC_TF32_BF16X2 = 4 /* split-precision, 2 tensor-pass equivalents instead of 3: trunc_tf32(x) * rna_tf32(w) on kind::tf32 plus
+                               the two first-order corrections bf16(x) * bf16(w - rna_tf32(w)) and bf16(x - trunc_tf32(x)) *
+                               bf16(rna_tf32(w)) on kind::f16 (twice the rate), all accumulated in the same fp32 TMEM accumulator.
+                               The corrections are 2^-11 of the product, so their bf16 rounding is a ~2^-20 (unbiased) relative
+                               error: fp32-level products like TF32X3 (measured table: profiles/r02_precision_table.md). */
 } dladmm_precision;
 
 /* Per-layer metrics accumulated inside the product epilogues (ABI v5): out[k * DLADMM_MET_COUNT + i] = sum over the

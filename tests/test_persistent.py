@@ -47,7 +47,8 @@ def _model(variant, m, d, B, K, precision, seed=3):
     return model, data
 
 
-CASES = [("scalar", 250, 500, 20000, 5, "tf32x3"), ("scalar", 250, 500, 132, 4, "tf32"), ("full", 250, 500, 1028, 4, "tf32x3"),
+CASES = [("scalar", 250, 500, 20000, 5, "tf32_bf16x2"), ("full", 250, 500, 1028, 4, "tf32_bf16x2"), ("lasso", 120, 300, 516, 3, "tf32_bf16x2"),
+         ("scalar", 250, 500, 20000, 5, "tf32x3"), ("scalar", 250, 500, 132, 4, "tf32"), ("full", 250, 500, 1028, 4, "tf32x3"),
          ("tied", 96, 200, 4100, 6, "tf32x3"), ("lasso", 250, 500, 2048, 3, "tf32x3"), ("ltheta", 64, 100, 512, 3, "tf32x3"),
          ("lena", 256, 512, 20 * 60, 3, "tf32x3"), ("scalar", 40, 72, 24, 2, "tf32x3"), ("full", 1000, 2000, 256, 2, "tf32x3")]
 

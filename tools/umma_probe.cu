@@ -26,6 +26,7 @@ struct EpiStore {
   static constexpr int WARPS = PROBE_EPI_WARPS;
   static constexpr int CHUNK = CH;
   static constexpr int NIN = 0;
+  static constexpr int NROWP = 0;
   struct State {};
   struct Pre {};
   float* C; i64 B; uint32_t in_mask;
@@ -43,6 +44,7 @@ struct EpiStore {
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
+static uint16_t bf16_rn(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x7FFFu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); }
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
 static float rna_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
 
@@ -54,9 +56,14 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   for (int j = 0; j < n_feat; ++j)
     for (int k = 0; k < Kdim; ++k) {
       float w = W[(size_t)j * Kdim + k];
-      float big = NPASS == 3 ? rna_tf32(w) : w;
+      float big = NPASS >= 3 ? rna_tf32(w) : w;
       Wb[(size_t)j * kpad + k] = big;
-      Ws[(size_t)j * kpad + k] = w - big;
+      if (NPASS == 4) {          // packed bf16 rows [bf16(big)[16] | bf16(small)[16]] per 16-element k-chunk
+        uint16_t* pk = reinterpret_cast<uint16_t*>(Ws.data()) + ((size_t)j * kpad + (k & ~15)) * 2 + (k & 15);
+        pk[0] = bf16_rn(big); pk[16] = bf16_rn(w - big);
+      } else {
+        Ws[(size_t)j * kpad + k] = w - big;
+      }
     }
   for (size_t i = 0; i < As.size(); ++i) As[i] = Act[i] - trunc_tf32(Act[i]);
   float *dWb, *dWs, *dA, *dAs, *dC;
@@ -117,6 +124,14 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
     for (int r = 0; r < reps; ++r) kern<<<grid, roles_threads(EpiStore::WARPS), smem>>>(tAb, tBb, tBs, em, gs, epi);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    // SM clock under this load: CTA 0's stamps of the LAST launch (first event of chunk 0 .. MMAs of its last traced chunk)
+    std::vector<long long> tr(256 * 8);
+    CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
+    const i64 my_tiles = (gs.n_tiles + grid - 1) / grid;
+    const i64 nchunks = std::min<i64>(256, my_tiles * gs.k_chunks);
+    const long long cyc = tr[(nchunks - 1) * 8 + 5] - tr[0];
+    printf("  CTA 0: %lld chunks in %lld cycles = %.0f cycles per chunk; if that is the whole launch: %.0f MHz\n", (long long)nchunks, cyc,
+           (double)cyc / nchunks, nchunks == my_tiles * gs.k_chunks ? cyc / (ms * 1e3) : 0.0);
   }
   printf("%s NPASS=%d KC=%d smem=%d grid=%d: rel_l2=%.3e maxabs=%.3e nonfinite=%zu  time=%.3f ms  %.1f TFLOP/s\n", "single", NPASS, KC,
          smem, grid, rel, maxabs, nbad, ms, ms > 0 ? 2.0 * n_feat * Kdim * B / ms / 1e9 : 0.0);
@@ -147,5 +162,6 @@ int main(int argc, char** argv) {
   }
   run<1, 32>(n_feat, Kdim, B, W, Act, ref, reps);
   run<3, 16>(n_feat, Kdim, B, W, Act, ref, reps);
+  run<4, 16>(n_feat, Kdim, B, W, Act, ref, reps);
   return 0;
 }
