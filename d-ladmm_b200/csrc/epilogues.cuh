@@ -56,6 +56,7 @@ struct EpiZ {
     for (int j = 0; j < 4; ++j) {
       float wv = ss1.p ? fmul(s1, acc[j]) : acc[j];
       z[j] = soft_act(fsub(zp.v[j], wv), th[j], bits[j]);
+      bits[j] |= (z[j] > 0.f ? 4u : 0u) | (z[j] < 0.f ? 8u : 0u);      // sign(Z_k), see dladmm_problem.maskZ
     }
     store4(Zk, off, z, nvalid, vec);
     if (maskZ) store4_u8(maskZ, off, bits, nvalid, vec);

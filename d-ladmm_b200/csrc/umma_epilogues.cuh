@@ -135,7 +135,7 @@ struct UEpiZ {
       const float z = soft_act(fsub(slot[i * TILE_B + col], wv), st.th1.at(row, b), bits);
       Zk[off] = z;
       if (Zh) Zh[(i64)row * ldh + b] = __float2bfloat16_rn(z);
-      if (maskZ) maskZ[off] = (uint8_t)bits;
+      if (maskZ) maskZ[off] = (uint8_t)(bits | (z > 0.f ? 4u : 0u) | (z < 0.f ? 8u : 0u));    // bits 2, 3: sign(Z_k) for the fused-loss backward
       if (obj_part) st.obj += fabsf(z);
       if (sq_part) { const float dl = slot[SUBF(CHUNK) + i * TILE_B + col] - z; st.sq += dl * dl; }   // warp-uniform branch
     }

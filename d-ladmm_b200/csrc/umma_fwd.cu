@@ -213,18 +213,33 @@ static bool persistent_eligible(const dladmm_problem* p) {
   if (p->metrics && p->metrics->want) return false;
   {   // the kernel numbers its units with 32 bits
     const i64 nbt = (p->B + umma::TILE_B - 1) / umma::TILE_B;
-    const i64 per = (p->d + umma::TILE_N - 1) / umma::TILE_N + (p->m + umma::TILE_N - 1) / umma::TILE_N;
+    const i64 per = (p->d + 31) / 32 + (p->m + 31) / 32;       // (an upper bound: 32-row tiles)
     if (nbt * per * (p->K + 1) >= ((i64)1 << 31)) return false;
   }
   return true;
 }
 
+// Feature rows per tile of the persistent forward.  256 (one tcgen05.mma of N = 256 per k-step) is the throughput shape.  With few
+// batch tiles a stage is one or two 256-row units: 146 SMs idle and each unit walks its 16-32 k-chunks through a 3-stage ring one
+// TMA latency at a time (~26 us per stage whatever the batch).  32-row tiles spread a stage over 8x as many CTAs, each with a
+// 7-stage ring (20 KB per stage) and an 8x shorter epilogue.  DLADMM_PF_TN=32|256 forces either.
+static int pf_tile_rows(const dladmm_problem* p) {
+  if (p->precision != DLADMM_PREC_TF32X3 && p->precision != DLADMM_PREC_TF32_BF16X2) return umma::TILE_N;
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("DLADMM_PF_TN"); forced = e ? atoi(e) : 0; }
+  const i64 nbt = (p->B + umma::TILE_B - 1) / umma::TILE_B;
+  const i64 units256 = nbt * ((p->m + umma::TILE_N - 1) / umma::TILE_N);     // units of an A Z stage at 256 rows per tile
+  if (units256 * 4 > 1024) return umma::TILE_N;                                // (the workspace is sized for 32-row tiles up to here: ucarve)
+  if (forced == 32 || forced == umma::TILE_N) return forced;
+  return units256 * 4 <= device_sm_count() ? 32 : umma::TILE_N;
+}
+
 static umma::BPc to_bpc(const dladmm_bparam& q) { umma::BPc b; b.p = q.ptr; b.rs = q.row_stride; b.period = q.col_period; return b; }
 
-template <int FAM, int NPASS, int PS>
-static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
+template <int FAM, int NPASS, int PS, int TN>
+static int forward_persistent_tn(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
   constexpr int KC = KChunk<NPASS>::value;
-  using Plan = umma::SmemPlan<NPASS, KC>;
+  using Plan = umma::SmemPlan<NPASS, KC, TN>;
   Slabs s(p);
   const int m = p->m, d = p->d, K = p->K;
   const i64 B = p->B;
@@ -238,7 +253,8 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   memset(pp, 0, sizeof(*pp));
   pp->m = m; pp->d = d; pp->K = K; pp->last_only = p->last_only;
   pp->B = B; pp->n_btiles = (B + umma::TILE_B - 1) / umma::TILE_B;
-  pp->nt_z = (d + umma::TILE_N - 1) / umma::TILE_N; pp->nt_e = (m + umma::TILE_N - 1) / umma::TILE_N;
+  pp->tn = TN;
+  pp->nt_z = (d + TN - 1) / TN; pp->nt_e = (m + TN - 1) / TN;
   pp->kc_z = (m + KC - 1) / KC; pp->kc_e = (d + KC - 1) / KC;
   pp->units_t0 = pp->n_btiles * pp->nt_e; pp->units_z = pp->n_btiles * pp->nt_z; pp->units_e = pp->n_btiles * pp->nt_e;
   pp->total_units = pp->units_t0 + (i64)K * (pp->units_z + pp->units_e);
@@ -253,6 +269,7 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   pp->spin_limit = 4000000000ll;                    // ~2 s of SM clocks
   // DLADMM_PF_PREFETCH=D: L2 prefetch distance of the staging producer in chunks (0 = off)
   { const char* e = getenv("DLADMM_PF_PREFETCH"); pp->prefetch = e ? atoi(e) : 0; }
+  { const char* e = getenv("DLADMM_PF_SCOUT_SLEEP"); pp->scout_sleep_ns = e ? (unsigned)atoi(e) : 0u; }
   pp->trace = pf_trace_buffer();
   { const char* e = getenv("DLADMM_PF_XRESIDENT"); pp->x_resident = (e && e[0] == '0') ? 0 : ((i64)m * B * 4 <= (i64)96 << 20); }
   // two CTA sets half a layer period apart once every SM has several tiles of each half (see PfParams::nstreams)
@@ -281,10 +298,10 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   const int depth = p->last_only ? 2 : K;
   const CUtensorMapSwizzle wsw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const CUtensorMapSwizzle asw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, nsw = CU_TENSOR_MAP_SWIZZLE_NONE;
-  if ((rc = umma::make_tmap_2d(&mp->A_big, w.Ab, w.m256, w.dp, w.dp, KC, umma::TILE_N, wsw))) return rc;
-  if ((rc = umma::make_tmap_2d(&mp->A_small, NPASS >= 3 ? w.As : w.Ab, w.m256, w.dp, w.dp, KC, umma::TILE_N, wsw))) return rc;
-  if ((rc = umma::make_tmap_3d(&mp->W_big, w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, umma::TILE_N, wsw))) return rc;
-  if ((rc = umma::make_tmap_3d(&mp->W_small, NPASS >= 3 ? w.Ws : w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, umma::TILE_N, wsw))) return rc;
+  if ((rc = umma::make_tmap_2d(&mp->A_big, w.Ab, w.m256, w.dp, w.dp, KC, TN, wsw))) return rc;
+  if ((rc = umma::make_tmap_2d(&mp->A_small, NPASS >= 3 ? w.As : w.Ab, w.m256, w.dp, w.dp, KC, TN, wsw))) return rc;
+  if ((rc = umma::make_tmap_3d(&mp->W_big, w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, TN, wsw))) return rc;
+  if ((rc = umma::make_tmap_3d(&mp->W_small, NPASS >= 3 ? w.Ws : w.Wb, w.nW, w.d256, w.mp, w.mp, (i64)w.d256 * w.mp, KC, TN, wsw))) return rc;
   if ((rc = umma::make_tmap_2d(&mp->actZ0, p->Z0, d, B, B, 32, KC, asw))) return rc;
   if ((rc = umma::make_tmap_3d(&mp->actZ, p->Z, depth, d, B, B, s.zs, 32, KC, asw))) return rc;
   if ((rc = umma::make_tmap_3d(&mp->actV, pp->V, p->Vsave ? K : 1, m, B, B, s.ms, 32, KC, asw))) return rc;
@@ -296,11 +313,11 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
   if ((rc = umma::make_tmap_2d(&mp->sZ0, p->Z0, d, B, B, umma::TILE_B, 16, nsw))) return rc;
   if ((rc = umma::make_tmap_3d(&mp->sZ, p->Z, depth, d, B, B, s.zs, umma::TILE_B, 16, nsw))) return rc;
 
-  auto kern = umma::umma_forward_persistent_kernel<FAM, PS, NPASS, KC>;
+  auto kern = umma::umma_forward_persistent_kernel<FAM, PS, NPASS, KC, TN>;
   static bool attr_set[MAX_DEVICES] = {false};
   const int dev = current_device_index();
   if (!attr_set[dev]) {
-    DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (umma::pf_smem_total<NPASS, KC>())));
+    DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (umma::pf_smem_total<NPASS, KC, TN>())));
     attr_set[dev] = true;
   }
   const int grid = pp->nstreams == 2 ? device_sm_count() : (int)std::min<i64>(std::max(pp->units_z, pp->units_e), device_sm_count());
@@ -308,7 +325,7 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
     LaunchScope ls(DLADMM_KIND_FWD_PERSISTENT, st);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::roles_threads(8) + 32); cfg.dynamicSmemBytes = (umma::pf_smem_total<NPASS, KC>()); cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::roles_threads(8) + 32); cfg.dynamicSmemBytes = (umma::pf_smem_total<NPASS, KC, TN>()); cfg.stream = st;
     // the CTAs wait on one another's counters: a cooperative launch makes the driver guarantee (or refuse) that the whole grid is
     // resident at once, whatever else shares the device
     cudaLaunchAttribute attr[1];
@@ -324,6 +341,14 @@ static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cuda
     DL_CUDA(cudaGetLastError());
   }
   return DLADMM_OK;
+}
+
+template <int FAM, int NPASS, int PS>
+static int forward_persistent(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st) {
+  if constexpr (NPASS >= 3) {
+    if (pf_tile_rows(p) == 32) return forward_persistent_tn<FAM, NPASS, PS, 32>(p, w, st);
+  }
+  return forward_persistent_tn<FAM, NPASS, PS, umma::TILE_N>(p, w, st);
 }
 
 int umma_forward(const dladmm_problem* p, void* ws_base, cudaStream_t st) {

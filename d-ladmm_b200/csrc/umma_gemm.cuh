@@ -365,12 +365,12 @@ constexpr int RING_BYTES = UMMA_RING_BYTES;    // staging ring; depth = RING_BYT
 struct EMaps { CUtensorMap m[MAX_EIN]; CUtensorMap mk; };   // float inputs + the 1-byte prox mask of the chunk
 constexpr uint32_t EIN_MASK_BIT = 1u << 31;                 // in_mask bit: the mask bytes are staged too
 
-template <int NPASS, int KC>
+template <int NPASS, int KC, int TN = TILE_N>
 struct SmemPlan {
   static constexpr int EB = NPASS == 2 ? 2 : 4;                      // operand element bytes (bf16 mode: 2)
   static constexpr int NOPS = NPASS >= 3 ? 2 : 1;                    // big (+ small; mixed mode: + the two bf16 correction operands)
   static constexpr int A_BYTES = TILE_B * KC * EB;                   // one operand part
-  static constexpr int B_BYTES = TILE_N * KC * EB;
+  static constexpr int B_BYTES = TN * KC * EB;                       // TN feature rows per tile (256; the persistent kernel's small-batch variant: 32)
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [A raw | A small] [B big | B small]
   static constexpr int TX_BYTES = A_BYTES + NOPS * B_BYTES;          // what TMA delivers (A small is computed in place)
   static constexpr int STAGES = UMMA_STAGES;
@@ -400,11 +400,11 @@ struct RingPos {
 // never read) -- called by all epilogue threads (etid of nthr); the caller synchronises the epilogue warps around it.
 // Table layout: parameter i at tab + i * TILE_N, indexed by row - j0.
 template <int NP>
-__device__ __forceinline__ void fill_rowtab(const BP (&q)[NP], float* tab, int j0, int n_feat, int etid, int nthr) {
+__device__ __forceinline__ void fill_rowtab(const BP (&q)[NP], float* tab, int j0, int n_feat, int etid, int nthr, int nrows = TILE_N) {
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     if (q[i].p == nullptr) continue;
-    for (int r = etid; r < TILE_N; r += nthr) {
+    for (int r = etid; r < nrows; r += nthr) {
       const int row = j0 + r;
       tab[i * TILE_N + r] = row < n_feat ? __ldg(q[i].p + (i64)row * q[i].rs) : 0.f;
     }

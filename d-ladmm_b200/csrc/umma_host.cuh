@@ -77,7 +77,9 @@ static UWorkspace ucarve(const dladmm_problem* p, char* base) {
   w.Lh = (__nv_bfloat16*)take(bf && atl ? (size_t)(p->m * w.ldh + 1) / 2 : 0);
   {
     const i64 nbt = (p->B + umma::TILE_B - 1) / umma::TILE_B;
-    const i64 nt_z = (p->d + umma::TILE_N - 1) / umma::TILE_N, nt_e = (p->m + umma::TILE_N - 1) / umma::TILE_N;
+    // (sized for the small-batch variant's 32-row tiles when the batch is small enough for it: see pf_tile_rows, umma_fwd.cu)
+    const int tn = nbt * ((p->m + umma::TILE_N - 1) / umma::TILE_N) * 4 <= 1024 ? 32 : umma::TILE_N;
+    const i64 nt_z = (p->d + tn - 1) / tn, nt_e = (p->m + tn - 1) / tn;
     const i64 units = nbt * (nt_e + (i64)p->K * (nt_z + nt_e));
     w.pf_flag_bytes = (size_t)(2 * p->K + 1) * nbt * sizeof(unsigned);
     w.pf_flags = (unsigned*)take((size_t)(2 * p->K + 1) * nbt);

@@ -49,7 +49,8 @@ struct PfMaps {
 struct PfParams {
   int m, d, K, last_only;
   i64 B, n_btiles;
-  int nt_z, nt_e;                      // feature tiles of the W V product (ceil(d / 256)) and of the A Z product (ceil(m / 256))
+  int tn;                              // feature rows per tile (the kernel's TN template argument)
+  int nt_z, nt_e;                      // feature tiles of the W V product (ceil(d / tn)) and of the A Z product (ceil(m / tn))
   int kc_z, kc_e;                      // k-chunks: ceil(m / KC), ceil(d / KC)
   i64 units_t0, units_z, units_e, total_units;   // of the whole batch (objective bookkeeping: unit index u of the single-stream order)
   // Two CTA sets ("streams"): even CTAs own the batch tiles [0, split), odd CTAs [split, n_btiles); each set walks its own
@@ -67,6 +68,7 @@ struct PfParams {
   long long spin_limit;                // clock64 ticks a producer may wait for a counter before it traps
   int prefetch;                        // D > 0: the staging producer requests every chunk's boxes into L2 D chunks ahead
   int x_resident;                      // 1: loads of X carry an L2 evict_last policy
+  unsigned scout_sleep_ns;             // pause between two polls of the scout lane's readiness spin
   long long* trace;                    // debugging (DLADMM_PF_TRACE=1): [PF_TRACE_CTAS][PF_TRACE_UNITS][8] clock64 stamps, or NULL
   PfLayer layer[PF_MAX_LAYERS];
 };
@@ -97,7 +99,7 @@ struct PfWalk {
     const uint32_t nt_e = p.nt_e, nt_z = p.nt_z;
     if (v < u_t0) {
       const uint32_t q = v / nt_e, rem = v - q * nt_e;
-      r.type = PF_T0; r.k = 0; r.stage = 0; r.bt = bt0 + q; r.j0 = (int)rem * TILE_N;
+      r.type = PF_T0; r.k = 0; r.stage = 0; r.bt = bt0 + q; r.j0 = (int)rem * p.tn;
       r.u = (i64)r.bt * nt_e + rem;
       return r;
     }
@@ -107,11 +109,11 @@ struct PfWalk {
     const i64 layer0 = p.units_t0 + (i64)k * (p.units_z + p.units_e);       // first unit of layer k in the whole-batch numbering
     if (w < u_z) {
       const uint32_t q = w / nt_z, rem = w - q * nt_z;
-      r.type = PF_Z; r.stage = 2 * r.k + 1; r.bt = bt0 + q; r.j0 = (int)rem * TILE_N;
+      r.type = PF_Z; r.stage = 2 * r.k + 1; r.bt = bt0 + q; r.j0 = (int)rem * p.tn;
       r.u = layer0 + (i64)r.bt * nt_z + rem;
     } else {
       const uint32_t x = w - u_z, q = x / nt_e, rem = x - q * nt_e;
-      r.type = PF_E; r.stage = 2 * r.k + 2; r.bt = bt0 + q; r.j0 = (int)rem * TILE_N;
+      r.type = PF_E; r.stage = 2 * r.k + 2; r.bt = bt0 + q; r.j0 = (int)rem * p.tn;
       r.u = layer0 + p.units_z + (i64)r.bt * nt_e + rem;
     }
     return r;
@@ -189,8 +191,13 @@ __device__ __forceinline__ void pf_wait_ready(const PfParams& p, const PfUnit& u
 #endif
 constexpr int PF_SLOT_BYTES = 3 * 8 * TILE_B * 4;         // one staging-ring slot: three arrays x 8 rows (T_0, E/T/L) or one x 16 rows (Z)
 constexpr int PF_DEPTH = PF_RING_BYTES / PF_SLOT_BYTES;   // 6
-template <int NPASS, int KC>
-constexpr int pf_smem_total() { return PF_STAGES * SmemPlan<NPASS, KC>::STAGE_BYTES + PF_RING_BYTES + SmemPlan<NPASS, KC>::BAR_BYTES + SmemPlan<NPASS, KC>::ROWTAB + 1024; }
+// operand stages of the kernel's (NPASS, KC, TN) variant: PF_STAGES of the 256-row tiles' 48 KB; the 32-row tiles of the small-batch
+// variant are 20 KB per stage, so the same shared memory holds 7 of them -- with one batch tile per unit the mainloop is a latency
+// chain (TMA -> split -> MMA -> free), and its rate is the number of chunks in flight
+template <int NPASS, int KC, int TN>
+__host__ __device__ constexpr int pf_stages() { return TN == TILE_N ? PF_STAGES : (PF_STAGES * SmemPlan<NPASS, KC, TILE_N>::STAGE_BYTES) / SmemPlan<NPASS, KC, TN>::STAGE_BYTES; }
+template <int NPASS, int KC, int TN = TILE_N>
+__host__ __device__ constexpr int pf_smem_total() { return pf_stages<NPASS, KC, TN>() * SmemPlan<NPASS, KC, TN>::STAGE_BYTES + PF_RING_BYTES + SmemPlan<NPASS, KC, TN>::BAR_BYTES + SmemPlan<NPASS, KC, TN>::ROWTAB + 1024; }
 static_assert(PF_DEPTH % 2 == 0, "ring depth must be a multiple of the epilogue parts");
 
 // the epilogue of ONE unit for one epilogue warp (rows [jw, jw + rpw) of the tile)
@@ -218,11 +225,12 @@ __device__ __forceinline__ void pf_run_epilogue(const Epi& epi, typename Epi::St
   }
 }
 
-template <int FAM, int PS, int NPASS, int KC>
+template <int FAM, int PS, int NPASS, int KC, int TN>
 __global__ void __launch_bounds__(roles_threads(8) + 32, 1)
 umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid_constant__ PfParams p) {
-  using Plan = SmemPlan<NPASS, KC>;
-  constexpr int STAGES = PF_STAGES;
+  using Plan = SmemPlan<NPASS, KC, TN>;
+  constexpr int STAGES = pf_stages<NPASS, KC, TN>();
+  static_assert(TN == TILE_N || TN == 32 || TN == 64, "feature rows per tile");
   constexpr int EPI_WARPS = 8, EPI_PARTS = 2;
   constexpr int SPLIT_WARP0 = EPI_WARP0 + EPI_WARPS, EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS, PUB_WARP = EIN_WARP + 1;
   constexpr int PUB_SLOTS = 4;
@@ -249,6 +257,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
   uint32_t* tmem_slot = (uint32_t*)(rempty + PUB_SLOTS);
   float* rowtab = (float*)(ring + PF_RING_BYTES + Plan::BAR_BYTES);
   static_assert((3 * STAGES + 4 + 2 * MAX_RING_DEPTH + 4 * PUB_SLOTS) * 8 + 8 <= Plan::BAR_BYTES, "barrier block");
+  static_assert(2 * TN <= 512, "two accumulators in TMEM");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   PfWalk walk; walk.init(p);
@@ -324,7 +333,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(TILE_B, TILE_N, 1, 0, 2u);
+    constexpr uint32_t idesc = make_idesc(TILE_B, TN, 1, 0, 2u);
     constexpr uint32_t a_hi = desc_hi(A_ATOM_BYTES, LAYOUT_SW128_BASE32B);
     constexpr uint32_t A_KSTEP = MMA_K * 128;
     constexpr uint32_t b_hi = desc_hi(B_SBO, B_LAYOUT);
@@ -339,7 +348,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
       mbar_wait(&tempty[acc], aph ^ 1);
       tc_fence_after();
       if (lane == 0) PF_TR(ui, 1, clock64());
-      const uint32_t d_tmem = tmem_base + acc * TILE_N;
+      const uint32_t d_tmem = tmem_base + acc * TN;
       for (int kc = 0; kc < kcs; ++kc) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -371,7 +380,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         if (elect_one()) {
           if (NPASS == 4) {         // the two bf16 correction products (umma_gemm.cuh, split_tile_mix)
             constexpr uint32_t a16_hi = desc_hi(1024, LAYOUT_SW128);
-            constexpr uint32_t idesc16 = make_idesc(TILE_B, TILE_N, 1, 0, 1u);
+            constexpr uint32_t idesc16 = make_idesc(TILE_B, TN, 1, 0, 1u);
             const uint32_t a16 = a_lo + (Plan::A_BYTES >> 4), b16 = b_lo + (Plan::B_BYTES >> 4);
             umma_f16(d_tmem, desc_at(a16_hi, a16), desc_at(b_hi, b16 + (32 >> 4)), idesc16, 1u);
             umma_f16(d_tmem, desc_at(a16_hi, a16 + (Plan::A_BYTES >> 5)), desc_at(b_hi, b16), idesc16, 1u);
@@ -427,7 +436,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         const int wslab = p.last_only ? ((w.k - 1) & 1) : (w.k - 1);
 #pragma unroll
         for (int h = 0; h < EPI_PARTS; ++h) {
-          const int row0 = w.j0 + h * (TILE_N / EPI_PARTS) + c * wchk;
+          const int row0 = w.j0 + h * (TN / EPI_PARTS) + c * wchk;
           if (row0 >= wfeat) continue;
           if (w.type == PF_T0) {
             tma_prefetch_2d(&maps.sE0, wb0, row0); tma_prefetch_2d(&maps.sX, wb0, row0); tma_prefetch_2d(&maps.sL0, wb0, row0);
@@ -443,7 +452,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
       const int b0 = (int)(un.bt * TILE_B);
       const int chk = un.type == PF_Z ? 16 : 8;
       const int n_feat = un.type == PF_Z ? p.d : p.m;
-      const int rpw = TILE_N / EPI_PARTS;
+      const int rpw = TN / EPI_PARTS;
       const int nch = rpw / chk;
       const int pslab = p.last_only ? ((un.k - 1) & 1) : (un.k - 1);      // slab of the previous layer's iterate (k >= 1)
       const bool has_ep = FAM == DLADMM_FAMILY_B;
@@ -451,7 +460,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         if (p.prefetch > 0 && elect_one()) {
           const int cp = c + p.prefetch;
           if (cp < nch) prefetch_chunk(un, cp);
-          else if (nx_ok && cp - nch < (TILE_N / EPI_PARTS) / (nx.type == PF_Z ? 16 : 8)) prefetch_chunk(nx, cp - nch);
+          else if (nx_ok && cp - nch < (TN / EPI_PARTS) / (nx.type == PF_Z ? 16 : 8)) prefetch_chunk(nx, cp - nch);
         }
         __syncwarp();
         for (int h = 0; h < EPI_PARTS; ++h, rp.advance(1, PF_DEPTH)) {
@@ -524,6 +533,9 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
             const long long t0 = clock64();
             while (ld_acquire_u32(f) < target) {
               if (clock64() - t0 > p.spin_limit) __trap();
+              // the scout runs up to PUB_SLOTS units ahead of the producers, so a coarse poll costs no latency; an unthrottled
+              // acquire spin executed 6.9 M ld.acquire + CCTL.IVALL per forward (ncu), issue slots and power of a power-capped kernel
+              if (p.scout_sleep_ns > 0) __nanosleep(p.scout_sleep_ns);
             }
           }
         }
@@ -562,7 +574,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
     int ps = 0; uint32_t pph = 0;
     int tab_key = -1;
     RingPos rp; rp.init(half, PF_DEPTH);
-    const int rpw = TILE_N / EPI_PARTS;
+    const int rpw = TN / EPI_PARTS;
     for (uint32_t v = walk.first; v < walk.total; v += walk.stride) {
       const PfUnit un = walk.decode(p, v);
       const i64 b = un.bt * TILE_B + col;
@@ -571,9 +583,9 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
       const int k = un.k;
       const PfLayer& ly = p.layer[k];
       const int slab = p.last_only ? (k & 1) : k;
-      const uint32_t t0 = tmem_base + acc * TILE_N + half * rpw + ((uint32_t)(q * 32) << 16);
+      const uint32_t t0 = tmem_base + acc * TN + half * rpw + ((uint32_t)(q * 32) << 16);
       float* objp = p.obj_part ? p.obj_part + un.u * EPI_WARPS : nullptr;
-      const int key = (un.stage << 8) | (un.j0 >> 8);   // PM_ROWS: which (stage, feature tile) the parameter table holds
+      const int key = (un.stage << 16) | (un.j0 / TN);    // PM_ROWS: which (stage, feature tile) the parameter table holds
       if (un.type == PF_T0) {
         UEpiT0<PS> epi;
         epi.E0 = p.E0; epi.X = p.X; epi.L0 = p.L0; epi.T0 = p.T;
@@ -585,7 +597,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
           if (tab_key != key) {                           // (uniform over the epilogue warps)
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");    // the previous unit's readers are done with the table
             BP qv[1]; epi.row_params(qv);
-            fill_rowtab<1>(qv, rowtab, un.j0, p.m, etid, EPI_WARPS * 32);
+            fill_rowtab<1>(qv, rowtab, un.j0, p.m, etid, EPI_WARPS * 32, TN);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
             tab_key = key;
           }
@@ -606,7 +618,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
           if (tab_key != key) {                           // (uniform over the epilogue warps)
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");    // the previous unit's readers are done with the table
             BP qv[1]; epi.row_params(qv);
-            fill_rowtab<1>(qv, rowtab, un.j0, p.d, etid, EPI_WARPS * 32);
+            fill_rowtab<1>(qv, rowtab, un.j0, p.d, etid, EPI_WARPS * 32, TN);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
             tab_key = key;
           }
@@ -635,7 +647,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
           if (tab_key != key) {                           // (uniform over the epilogue warps)
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");    // the previous unit's readers are done with the table
             BP qv[6]; epi.row_params(qv);
-            fill_rowtab<6>(qv, rowtab, un.j0, p.m, etid, EPI_WARPS * 32);
+            fill_rowtab<6>(qv, rowtab, un.j0, p.m, etid, EPI_WARPS * 32, TN);
             asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
             tab_key = key;
           }

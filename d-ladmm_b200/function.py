@@ -166,12 +166,26 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
     training mode (`want_masks`), "Vsave" (the kept W V operands the backward reuses) and "padded" (the inputs and
     outputs at the padded pitch, see padded_batch; the returned Z, E, L, T are then views narrowed to B columns)."""
     lib = _lib.load()
-    _check_inputs(spec, A, X, Z0, E0, L0, params)
+    # The layer table (K x 8 broadcast parameters + weight pointers as ctypes structs) only depends on where the parameters live:
+    # it is kept on the spec and reused while every parameter still sits at the same address (in-place optimizer steps keep it;
+    # at the reference scripts' batch sizes building it was half of the 0.3 ms host time of a call).
+    ptrs = tuple([t.data_ptr() for t in params])
+    hit = getattr(spec, "_layer_cache", None)
+    if hit is not None and hit[0] == ptrs:
+        layers = hit[1]
+        _check_inputs(spec, A, X, Z0, E0, L0, ())
+    else:
+        _check_inputs(spec, A, X, Z0, E0, L0, params)
+        layers = None
     B_user = X.shape[1]
     Bp = padded_batch(spec, B_user)
     X, Z0, E0, L0 = _pad_cols(X, Bp), _pad_cols(Z0, Bp), _pad_cols(E0, Bp), _pad_cols(L0, Bp)
     A = A.contiguous()
-    params = [t.contiguous() for t in params]
+    if layers is None:
+        contig = all(t.is_contiguous() for t in params)
+        params = [t.contiguous() for t in params]
+        layers = _build_layers(spec, params, None)
+        spec._layer_cache = (ptrs, layers) if contig else None      # (a non-contiguous parameter is copied per call: no reuse)
     m, d, K, B = spec.m, spec.d, spec.K, Bp
     dev = X.device
     depth = 2 if last_only else K
@@ -193,7 +207,6 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
     keep_v = want_masks and extras is not None and spec.precision != _lib.PRECISIONS["fp32"] and B % 4 == 0
     Vsave = torch.empty((K, m, B), dtype=torch.float32, device=dev) if keep_v else None
     obj = torch.empty(K, dtype=torch.float32, device=dev) if objective_alpha is not None else None
-    layers = _build_layers(spec, params, None)
     mt = mt_out = mt_keep = None
     if metrics is not None:
         mt, mt_out, mt_keep = _metrics_desc(metrics, m, d, B_user, Bp, K, dev)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLADMM_ABI_VERSION 5
+#define DLADMM_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define DLADMM_API __attribute__((visibility("default")))
@@ -144,7 +144,9 @@ typedef struct dladmm_problem {
   float* E;               /* out (K,m,B)   */
   float* L;               /* out (K,m,B)   */
   float* T;               /* out (K+1,m,B), T[0] = A Z0 + E0 - X */
-  uint8_t* maskZ;         /* out (K,d,B) or NULL: bit0 = [x-theta>0], bit1 = [-x-theta>0] of the Z prox (training) */
+  uint8_t* maskZ;         /* out (K,d,B) or NULL: bit0 = [x-theta>0], bit1 = [-x-theta>0] of the Z prox (training); ABI v6: bit2 = [Z_k>0],
+                             bit3 = [Z_k<0], so that the backward of the fused losses takes sign(Z_k) from the mask byte it reads anyway
+                             instead of re-reading Z_k (theta may be negative: then bits 0 and 1 do not determine the sign) */
   uint8_t* maskE;         /* out (K,m,B) or NULL: same for the E prox (families A,B) */
   void* workspace;
   size_t workspace_bytes;

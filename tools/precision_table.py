@@ -56,13 +56,14 @@ def one_product(m, d, B):
     z = torch.zeros(m, B, device="cuda")
     want = A.double() @ Z.double()
     print("\n## one product (%d x %d)(%d x %d), dense Gaussian operands: relative L2 error vs fp64\n" % (m, d, d, B))
-    print("| mode | rel. error |\n|---|---|")
-    for mode in ("fp32", "tf32x3", "tf32", "bf16"):
+    print("| mode | rel. L2 error | mean signed error (toward zero < 0) |\n|---|---|---|")
+    for mode in ("fp32", "tf32_bf16x2", "tf32x3", "tf32", "bf16"):
         model = dl.DLADMMNetScalar(m, 1, d, B, A, Z, z, z, 1, precision=mode)
         got = model._t0(z)
-        print("| %s | %.2e |" % (mode, ((got.double() - want).norm() / want.norm()).item()))
+        print("| %s | %.2e | %.2e |" % (mode, ((got.double() - want).norm() / want.norm()).item(), (((got.double() - want) * want.sign()).sum() / want.abs().sum()).item()))
     torch.backends.cuda.matmul.allow_tf32 = False
-    print("| aten fp32 (cuBLAS SGEMM) | %.2e |" % (((A @ Z).double() - want).norm() / want.norm()).item())
+    got = A @ Z
+    print("| aten fp32 (cuBLAS SGEMM) | %.2e | %.2e |" % (((got.double() - want).norm() / want.norm()).item(), (((got.double() - want) * want.sign()).sum() / want.abs().sum()).item()))
 
 
 if __name__ == "__main__":
@@ -70,5 +71,8 @@ if __name__ == "__main__":
     one_product(250, 500, 4096)
     one_product(500, 250, 4096)
     one_product(1000, 2000, 4096)
-    table(250, 500, 15, 4096, ("fp32", "tf32x3", "tf32", "bf16"))
-    table(1000, 2000, 40, 1024, ("tf32x3", "tf32", "bf16"))
+    table(250, 500, 15, 4096, ("fp32", "tf32_bf16x2", "tf32x3", "tf32", "bf16"))
+    table(1000, 2000, 40, 1024, ("tf32_bf16x2", "tf32x3", "tf32", "bf16"))
+    one_product(24, 40, 4096)
+    one_product(64, 128, 4096)
+    one_product(128, 256, 4096)
