@@ -19,6 +19,7 @@ static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const 
   split = (int)((B + chunk - 1) / chunk);
   umma::NtShape ns;
   ns.M = M; ns.N = N; ns.B = B; ns.chunk = chunk; ns.ldc = ldc;
+  ns.acc_unit = umma::acc_comp_unit() * (float)umma::mma_per_chunk(NPASS);
   auto kern = umma::umma_nt_kernel<NPASS, KC>;
   static bool attr_set[MAX_DEVICES] = {false};
   const int dev = current_device_index();

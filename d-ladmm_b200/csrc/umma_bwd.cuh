@@ -359,6 +359,7 @@ struct NtShape {
   i64 B;
   i64 chunk;           // batch columns per CTA (multiple of KC)
   int ldc;
+  float acc_unit;      // ACC_RZ_BIAS_PER_MMA x MMAs per k-chunk (0: no compensation)
 };
 
 template <int NPASS, int KC>
@@ -481,7 +482,8 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
       }
       const int q = warp & 3;
       const int half = (warp - EPI_WARP0) >> 2;
-      const float alpha = sign * (s1ptr ? __ldg(s1ptr) : 1.f);
+      // (acc_unit: accumulator compensation per k-chunk of this CTA's batch slice, see ACC_RZ_BIAS_PER_MMA in umma_gemm.cuh)
+      const float alpha = sign * (s1ptr ? __ldg(s1ptr) : 1.f) * (1.0f + ns.acc_unit * (float)k_chunks);
       mbar_wait(tfull, 0);                              // every MMA has retired: the operand stages are free
       tc_fence_after();
       const uint32_t t0 = tmem_base + half * (TILE_N / EPI_PARTS) + ((uint32_t)(q * 32) << 16);

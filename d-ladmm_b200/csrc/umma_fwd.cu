@@ -256,6 +256,8 @@ static int forward_persistent_tn(const dladmm_problem* p, const UWorkspace& w, c
   pp->tn = TN;
   pp->nt_z = (d + TN - 1) / TN; pp->nt_e = (m + TN - 1) / TN;
   pp->kc_z = (m + KC - 1) / KC; pp->kc_e = (d + KC - 1) / KC;
+  pp->acc_scale_z = umma::acc_comp_scale(pp->kc_z * umma::mma_per_chunk(NPASS));
+  pp->acc_scale_e = umma::acc_comp_scale(pp->kc_e * umma::mma_per_chunk(NPASS));
   pp->units_t0 = pp->n_btiles * pp->nt_e; pp->units_z = pp->n_btiles * pp->nt_z; pp->units_e = pp->n_btiles * pp->nt_e;
   pp->total_units = pp->units_t0 + (i64)K * (pp->units_z + pp->units_e);
   pp->X = p->X; pp->E0 = p->E0; pp->L0 = p->L0; pp->Z0 = p->Z0;

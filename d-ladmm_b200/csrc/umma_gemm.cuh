@@ -30,6 +30,7 @@
 #pragma once
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dladmm {
@@ -321,7 +322,24 @@ constexpr uint32_t A_ATOM_BYTES = 512;
 #define UMMA_TR(gs, idx, ev) do { } while (0)
 #endif
 
+// The tensor core adds every tcgen05.mma into its fp32 TMEM accumulator with round-toward-zero: each accumulating instruction
+// shrinks the running sum by a fraction of an ulp.  Measured on B200 (profiles/r02_precision_table.md, mean signed error of one
+// product against fp64): 1.7e-8 .. 1.9e-8 of the result per MMA instruction, the same for kind::tf32 and kind::f16 and for
+// reduction lengths 250 .. 2000 -- a BIAS, and the dominant error of the fp32-class modes (2.3e-6 of 2.8e-6 at K = 500), which
+// being coherent from layer to layer is what grows with depth.  The epilogues therefore scale the accumulator they read by
+// 1 + ACC_RZ_BIAS_PER_MMA * (accumulating MMAs of the element): a first-order compensation of the expected loss (exact for no
+// element; it removes the mean).  DLADMM_ACC_COMP=0 switches it off (scale 1.0f: bit-identical to the uncompensated kernels).
+constexpr float ACC_RZ_BIAS_PER_MMA = 1.8e-8f;
+__host__ __device__ constexpr int mma_per_chunk(int npass) { return npass == 3 ? 6 : 4; }   // 3xTF32: 2 k-steps x 3; the others: 4 per chunk
+inline float acc_comp_unit() {         // the per-MMA constant, or 0 when the compensation is switched off
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DLADMM_ACC_COMP"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on ? ACC_RZ_BIAS_PER_MMA : 0.0f;
+}
+inline float acc_comp_scale(int n_mma) { return 1.0f + acc_comp_unit() * (float)n_mma; }
+
 struct GemmShape {
+  float acc_scale;   // accumulator compensation (see ACC_RZ_BIAS_PER_MMA); 1.0f = none
 #ifdef UMMA_TRACE
   long long* trace;  // [256][8] clock64 stamps of CTA 0: 0 producer got the stage, 1 TMA issued, 2 splitter saw full, 3 split done,
                      //                                    4 MMA saw ready, 5 MMAs issued
@@ -697,6 +715,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (row0 < gs.n_feat) {                          // warp-uniform
           float v[CHK];
           tmem_ld(t0 + c * CHK, v);
+#pragma unroll
+          for (int i = 0; i < CHK; ++i) v[i] = __fmul_rn(v[i], gs.acc_scale);
           const float* slot = reinterpret_cast<const float*>(ring + s * slot_bytes);
           if (row0 + CHK <= gs.n_feat)                   // every row of the chunk exists: branch-free rows, interleaved by the compiler
             epi.template apply<true>(state, slot, col, pre, row0, b, valid, v, gs.n_feat, bt * (TILE_B / 32) + q);

@@ -367,6 +367,7 @@ static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, c
   gs.n_feat = n_feat;
   gs.n_ntiles = (n_feat + umma::TILE_N - 1) / umma::TILE_N;
   gs.k_chunks = (Kdim + KC - 1) / KC;
+  gs.acc_scale = umma::acc_comp_scale(gs.k_chunks * umma::mma_per_chunk(NPASS));
   gs.B = B;
   gs.n_btiles = (B + umma::TILE_B - 1) / umma::TILE_B;
   auto kern = umma::umma_gemm_kernel<Epi, NPASS, KC>;

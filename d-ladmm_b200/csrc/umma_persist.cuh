@@ -69,6 +69,7 @@ struct PfParams {
   int prefetch;                        // D > 0: the staging producer requests every chunk's boxes into L2 D chunks ahead
   int x_resident;                      // 1: loads of X carry an L2 evict_last policy
   unsigned scout_sleep_ns;             // pause between two polls of the scout lane's readiness spin
+  float acc_scale_z, acc_scale_e;      // accumulator compensation of the W V / A Z products (umma_gemm.cuh, ACC_RZ_BIAS_PER_MMA)
   long long* trace;                    // debugging (DLADMM_PF_TRACE=1): [PF_TRACE_CTAS][PF_TRACE_UNITS][8] clock64 stamps, or NULL
   PfLayer layer[PF_MAX_LAYERS];
 };
@@ -204,7 +205,7 @@ static_assert(PF_DEPTH % 2 == 0, "ring depth must be a multiple of the epilogue 
 template <class Epi>
 __device__ __forceinline__ void pf_run_epilogue(const Epi& epi, typename Epi::State& state, const PfParams& p, int n_feat, uint32_t t0,
                                                 int jw, int rpw, i64 bt, int q, int col, i64 b, bool valid, uint8_t* ring,
-                                                uint64_t* efull, uint64_t* eempty, RingPos& rp, int lane) {
+                                                uint64_t* efull, uint64_t* eempty, RingPos& rp, int lane, float acc_scale) {
   constexpr int CHK = Epi::CHUNK;
   const int nch = rpw / CHK;
   typename Epi::Pre pre;
@@ -216,6 +217,8 @@ __device__ __forceinline__ void pf_run_epilogue(const Epi& epi, typename Epi::St
     if (row0 < n_feat) {
       float v[CHK];
       tmem_ld(t0 + c * CHK, v);
+#pragma unroll
+      for (int i = 0; i < CHK; ++i) v[i] = __fmul_rn(v[i], acc_scale);
       const float* slot = reinterpret_cast<const float*>(ring + s * PF_SLOT_BYTES);
       if (row0 + CHK <= n_feat) epi.template apply<true>(state, slot, col, pre, row0, b, valid, v, n_feat, bt * (TILE_B / 32) + q);
       else epi.template apply<false>(state, slot, col, pre, row0, b, valid, v, n_feat, bt * (TILE_B / 32) + q);
@@ -606,7 +609,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
         if (ewarp == 0 && lane == 0) PF_TR(ui, 4, clock64());
-        pf_run_epilogue(epi, state, p, p.m, t0, jw, rpw, un.bt, q, col, b, valid, ring, efull, eempty, rp, lane);
+        pf_run_epilogue(epi, state, p, p.m, t0, jw, rpw, un.bt, q, col, b, valid, ring, efull, eempty, rp, lane, p.acc_scale_e);
       } else if (un.type == PF_Z) {
         UEpiZ<PS> epi;
         epi.Zp = nullptr; epi.Zk = p.Z + p.zs * slab; epi.maskZ = p.maskZ ? p.maskZ + p.zs * slab : nullptr;
@@ -627,7 +630,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
         if (ewarp == 0 && lane == 0) PF_TR(ui, 4, clock64());
-        pf_run_epilogue(epi, state, p, p.d, t0, jw, rpw, un.bt, q, col, b, valid, ring, efull, eempty, rp, lane);
+        pf_run_epilogue(epi, state, p, p.d, t0, jw, rpw, un.bt, q, col, b, valid, ring, efull, eempty, rp, lane, p.acc_scale_z);
         epi.end(state, ewarp, lane);
       } else {
         UEpiELT<FAM, PS, false> epi;
@@ -656,7 +659,7 @@ umma_forward_persistent_kernel(const __grid_constant__ PfMaps maps, const __grid
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
         if (ewarp == 0 && lane == 0) PF_TR(ui, 4, clock64());
-        pf_run_epilogue(epi, state, p, p.m, t0, jw, rpw, un.bt, q, col, b, valid, ring, efull, eempty, rp, lane);
+        pf_run_epilogue(epi, state, p, p.m, t0, jw, rpw, un.bt, q, col, b, valid, ring, efull, eempty, rp, lane, p.acc_scale_e);
         epi.end(state, ewarp, lane);
       }
       if (ewarp == 0 && lane == 0) PF_TR(ui, 5, clock64());

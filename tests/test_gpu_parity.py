@@ -1,19 +1,22 @@
 """GPU parity: the CUDA path (through the nn.Module -> autograd.Function -> C ABI) against the committed
 reference outputs/gradients and against the fp64 oracle on identical inputs and weights.
 
-Tolerances (floating point; stated per the north star):
+Tolerances (floating point; stated per the north star; measured maxima: tools/tol_survey.py, profiles/r02_tol_survey.log):
   fp32 (FFMA)  : per-layer relative L2 error vs the fp64 oracle <= 5e-6 (the reference's own fp32-vs-fp64
                  floor is 2.5e-7..6e-7, up to 3.5e-6 on T)
-  tf32x3       : <= 2e-5: products are fp32-exact to ~2^-21 but the tensor core's fp32 accumulator truncates on
-                 every MMA (measured on B200: 1.9e-6 at K=250, 3.7e-6 at K=500 on dense data, growing ~linearly in K)
-  tf32_bf16x2  : <= 6e-5 on these SMALL fixtures (m 20..64): the two correction products round their operands to bf16, an
-                 unbiased ~1e-6 error per product relative to the OPERAND magnitudes that does not shrink with K, and L_k / T_k
-                 are differences of nearly cancelling terms (|L| ~ |X| / 15 here).  From K ~ 180 on this mode is the more
-                 accurate one (fewer truncating accumulations: measured 2.8e-6 vs 3.8e-6 per product at K = 500) and the module's
-                 "auto" default only picks it there (net.py::resolve_precision); it is tested here below that size on purpose.
+  tf32x3       : <= 8e-6 on Z_k, E_k (measured <= 3.0e-6 over every fixture) and 4x that on L_k, a difference of nearly cancelling
+                 terms (measured <= 1.1e-5, lena_c4shape).  The three-pass products are exact to ~2^-21; the tensor core's fp32
+                 accumulator rounds toward zero on every MMA (a bias of 1.8e-8 per instruction, linear in K), which the epilogues
+                 compensate to first order (umma_gemm.cuh, ACC_RZ_BIAS_PER_MMA): round 1 needed 2e-5 here.
+  tf32_bf16x2  : <= 1.5e-5 (4x on L_k) on these SMALL fixtures (m 20..64; measured <= 5.7e-6, L <= 3.9e-5): the two correction
+                 products round their operands to bf16, an unbiased ~1e-6 error per product relative to the OPERAND magnitudes
+                 that does not shrink with K.  At the config shapes (K = 250 / 500) both modes measure the same 1.2e-6 .. 1.8e-6
+                 per product and the module's "auto" default only picks this mode from min(m, d) >= 192
+                 (net.py::resolve_precision); it is tested here below that size on purpose.
   tf32         : <= 2e-2 (single-pass, 10-bit mantissa operands; stated-tolerance option)
-  support masks: equal except where both values are inside a 1e-5 guard band around the threshold.
-  gradients    : relative L2 error <= 2e-4 (fp32), 5e-4 (tf32x3), 0.2 (tf32: a 1e-3 forward error flips prox
+  support masks: equal except where both values are inside a 1e-5 (fp32, tf32x3) / 2e-5 (tf32_bf16x2) guard band around the
+                 threshold (no mismatch at all in the committed fixtures).
+  gradients    : relative L2 error <= 2e-4 (fp32), 5e-4 (tf32x3, tf32_bf16x2), 0.2 (tf32: a 1e-3 forward error flips prox
                  masks near the threshold, which moves gradients of these tiny problems by several percent).
 """
 import os
@@ -28,9 +31,10 @@ from _util import GOLDEN_NAMES, SMALL_GOLDEN, Golden, build_model, rel_l2, syn
 pytestmark = pytest.mark.gpu
 
 PRECISIONS = ["fp32"] + (["tf32_bf16x2", "tf32x3", "tf32"] if os.environ.get("DLADMM_TEST_UMMA", "1") == "1" else [])
-FWD_TOL = {"fp32": 5e-6, "tf32_bf16x2": 6e-5, "tf32x3": 2e-5, "tf32": 2e-2}
+FWD_TOL = {"fp32": 5e-6, "tf32_bf16x2": 1.5e-5, "tf32x3": 8e-6, "tf32": 2e-2}
+L_FACTOR = {"fp32": 1.0, "tf32_bf16x2": 4.0, "tf32x3": 4.0, "tf32": 1.0}       # L_k: a difference of nearly cancelling terms
 GRAD_TOL = {"fp32": 2e-4, "tf32_bf16x2": 5e-4, "tf32x3": 5e-4, "tf32": 0.5}
-GUARD = {"fp32": 1e-5, "tf32_bf16x2": 1e-4, "tf32x3": 4e-5, "tf32": 1e-2}
+GUARD = {"fp32": 1e-5, "tf32_bf16x2": 2e-5, "tf32x3": 1e-5, "tf32": 1e-2}
 
 
 def _skip_if_unavailable(precision):
@@ -74,7 +78,7 @@ def test_forward_matches_reference_and_oracle(name, precision):
         # vs the fp64 oracle
         assert rel_l2(z, Zo[k], floor=1e-3) < tol, (name, k, "Z", rel_l2(z, Zo[k]))
         assert rel_l2(e, Eo[k], floor=1e-3 * xn) < tol, (name, k, "E")
-        assert rel_l2(l, Lo[k], floor=1e-3 * xn) < tol, (name, k, "L")
+        assert rel_l2(l, Lo[k], floor=1e-3 * xn) < L_FACTOR[precision] * tol, (name, k, "L")
         # vs the reference's own fp32 outputs (fixture)
         assert rel_l2(z, g.Z[k], floor=1e-3) < 2 * tol and rel_l2(e, g.E[k], floor=1e-3 * xn) < 2 * tol
         _check_support(z, Zo[k], GUARD[precision])

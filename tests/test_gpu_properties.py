@@ -206,7 +206,7 @@ def test_native_library_is_the_code_that_runs():
     assert caps["supported"] == 1 and caps["cc_major"] == 10 and caps["sm_count"] >= 100
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("precision", ["tf32_bf16x2", "tf32x3", "fp32"])
 def test_config5_shape_multiple_feature_tiles(precision):
     """BASELINE config 5 shape (m=1000, d=2000): several 256-row feature tiles per product, K-loop over 2000;
     forward against the fp32 oracle and training gradients against fp64 autograd, at a batch the CPU finishes fast."""
@@ -219,7 +219,8 @@ def test_config5_shape_multiple_feature_tiles(precision):
     loss, outs = model.l1l1_loss(X.cuda(), 0.001, [0.5, 0.5, 1.0])
     loss.backward()
     Zo, Eo, Lo, To = orc.forward("scalar", sd, A, X, Z0, E0, L0, K)
-    tol = 5e-5 if precision == "tf32x3" else 1e-5
+    # (K = 2000: 500 .. 750 accumulating MMAs per element; 7e-6 per product once their round-toward-zero bias is compensated)
+    tol = 2.5e-5 if precision != "fp32" else 1e-5
     for k in range(K):
         assert rel_l2(outs[0][k].cpu(), Zo[k], floor=1e-3) < tol, (k, rel_l2(outs[0][k].cpu(), Zo[k]))
         assert rel_l2(outs[2][k].cpu(), Lo[k], floor=1e-2) < tol
@@ -231,7 +232,7 @@ def test_config5_shape_multiple_feature_tiles(precision):
         floor = 2e-3 if p.numel() == 1 else 1e-4 * max(1.0, float(gref[n].abs().max()) * p.numel() ** 0.5)
         # the L1 objective is non-smooth: sign(E_k - T_{k+1}) and the prox masks flip for entries within rounding of
         # zero, and with only 256 columns a handful of flips moves dW by ~0.5 % in 3xTF32
-        assert rel_l2(p.grad.cpu(), gref[n], floor=floor) < (2e-2 if precision == "tf32x3" else 2e-3), n
+        assert rel_l2(p.grad.cpu(), gref[n], floor=floor) < (2e-2 if precision != "fp32" else 2e-3), n
 
 
 @pytest.mark.parametrize("variant,B", [("scalar", 21504), ("full", 21444), ("lasso", 21504)])

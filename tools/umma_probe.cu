@@ -85,6 +85,7 @@ static double run(int n_feat, int Kdim, i64 B, const std::vector<float>& W, cons
   long long* dtr; CK(cudaMalloc(&dtr, 256 * 8 * 8)); CK(cudaMemset(dtr, 0, 256 * 8 * 8));
   gs.trace = dtr;
   gs.n_feat = n_feat; gs.n_ntiles = npad / TILE_N; gs.k_chunks = (Kdim + KC - 1) / KC; gs.B = B;
+  gs.acc_scale = acc_comp_scale(gs.k_chunks * mma_per_chunk(NPASS));
   gs.n_btiles = (B + TILE_B - 1) / TILE_B;
   EpiStore epi{dC, B, 0u};
   static EMaps em; for (int i = 0; i < MAX_EIN; ++i) em.m[i] = tBb; em.mk = tBb;
