@@ -159,8 +159,9 @@ struct UEpiBG1 {
 template <int FAM, int PM>
 struct UEpiBG2 {
   static constexpr bool PS = PM == PM_SCALAR;
-  static constexpr int WARPS = 8;                  // 7 staged arrays: two parts keep 2 ring slots each in flight (16 warps: 1 each, slower)
+  static constexpr int WARPS = 16;                 // 7 staged arrays: with the 120 KB ring (OP_STAGES = 2) four parts keep 2 slots each in flight
   static constexpr int CHUNK = 4;     // up to 7 staged arrays + mask per element: keep one ring slot small (depth >= EPI_PARTS)
+  static constexpr int OP_STAGES = 2; // 2 operand stages, 120 KB staging ring (8 slots of 14.8 KB instead of 4): see op_stages_of
   static constexpr int NIN = 7;    // L_{k-1} (tied), T_k, cL | cE, E_{k-1}, L_{k-2}, E_{k-2}(B)   (the last four only below the top layer)
                                    // upstream cotangents gL, gE, gT (generic autograd path only) are read straight from global memory
   struct State { float red[6]; float rv[PS ? 1 : 32]; uint32_t gmask; PV<PM> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };

@@ -429,12 +429,23 @@ __device__ __forceinline__ void fill_rowtab(const BP (&q)[NP], float* tab, int j
   }
 }
 
+// Shared memory is split between the operand stages of the mainloop and the staging ring of the epilogue inputs; an epilogue
+// functor may trade one for the other with `static constexpr int OP_STAGES` (default: SmemPlan::STAGES = 3).  The dV epilogue of the
+// backward is HBM-latency-bound on its seven staged arrays with the tensor pipe 19 % busy (ncu): it runs on 2 operand stages and a
+// 120 KB ring.
+template <class E, class = void> struct op_stages_of { static constexpr int value = UMMA_STAGES; };
+template <class E> struct op_stages_of<E, decltype((void)E::OP_STAGES)> { static constexpr int value = E::OP_STAGES; };
+template <class Epi, int NPASS, int KC>
+constexpr int ring_bytes_of() { return RING_BYTES + (UMMA_STAGES - op_stages_of<Epi>::value) * SmemPlan<NPASS, KC>::STAGE_BYTES; }
+
 template <class Epi, int NPASS, int KC>
 __global__ void __launch_bounds__(roles_threads(Epi::WARPS), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_big,
                  const __grid_constant__ CUtensorMap tmB_small, const __grid_constant__ EMaps emaps, GemmShape gs, Epi epi) {
   using Plan = SmemPlan<NPASS, KC>;
-  constexpr int STAGES = Plan::STAGES;
+  constexpr int STAGES = op_stages_of<Epi>::value;
+  constexpr int RING_TOTAL = RING_BYTES + (Plan::STAGES - STAGES) * Plan::STAGE_BYTES;
+  static_assert(STAGES >= 2 && STAGES <= Plan::STAGES, "operand stages");
   constexpr int EPI_WARPS = Epi::WARPS, EPI_PARTS = EPI_WARPS / 4;
   constexpr int SPLIT_WARP0 = EPI_WARP0 + EPI_WARPS, EIN_WARP = SPLIT_WARP0 + SPLIT_WARPS;
   static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
@@ -451,7 +462,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1 KB alignment as an offset from the __shared__ symbol: keeps the address space visible to the compiler (LDS/STS, not generic)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem + STAGES * Plan::STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(ring + RING_BYTES);
+  uint64_t* bars = (uint64_t*)(ring + RING_TOTAL);
   uint64_t* full = bars;                   // [STAGES]
   uint64_t* empty = bars + STAGES;         // [STAGES]
   uint64_t* ready = bars + 2 * STAGES;     // [STAGES] activation split done (3-pass mode)
@@ -460,7 +471,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* efull = bars + 3 * STAGES + 4;                   // [MAX_RING_DEPTH]
   uint64_t* eempty = bars + 3 * STAGES + 4 + MAX_RING_DEPTH;  // [MAX_RING_DEPTH]
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4 + 2 * MAX_RING_DEPTH);
-  float* rowtab = (float*)(ring + RING_BYTES + Plan::BAR_BYTES);
+  float* rowtab = (float*)(ring + RING_TOTAL + Plan::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 ntiles = gs.n_tiles;
@@ -471,7 +482,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // The depth is a multiple of EPI_PARTS, so that a ring slot is always consumed by the same part: mbarrier waits only
   // see the phase PARITY, and a part that shared a slot with another part could reach the slot's wrap w+2 while wrap w+1
   // (the other part's) was still in flight -- its wait would pass on the stale phase.  (The host refuses depth < EPI_PARTS.)
-  int depth = nin > 0 ? RING_BYTES / slot_bytes : EPI_PARTS;
+  int depth = nin > 0 ? RING_TOTAL / slot_bytes : EPI_PARTS;
   if (depth > MAX_RING_DEPTH) depth = MAX_RING_DEPTH;
   depth -= depth % EPI_PARTS;
 

@@ -358,7 +358,7 @@ static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, c
     // would see that slot's barrier as already completed)
     const int nin = __builtin_popcount(epi.in_mask & ~umma::EIN_MASK_BIT);
     const int slot_bytes = nin * Epi::CHUNK * umma::TILE_B * 4 + ((epi.in_mask & umma::EIN_MASK_BIT) ? Epi::CHUNK * umma::TILE_B : 0);
-    if (nin > 0 && umma::RING_BYTES / slot_bytes < Epi::WARPS / 4) {
+    if (nin > 0 && umma::ring_bytes_of<Epi, NPASS, KC>() / slot_bytes < Epi::WARPS / 4) {
       set_error("epilogue staging ring too small: %d bytes per slot, %d parts", slot_bytes, Epi::WARPS / 4);
       return DLADMM_ERR_INVALID;
     }

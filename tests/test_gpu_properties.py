@@ -340,3 +340,44 @@ def test_sync_gradients_is_inert_without_a_process_group():
     loss, _ = model.l1l1_loss(data.X, 0.01)
     loss.backward()
     assert all(rel_l2(p.grad, r, floor=1e-7) < 1e-5 for p, r in zip(model.parameters(), ref))    # dW atomics: order only
+
+
+def test_mask_sign_bits_and_layer_table_cache():
+    """ABI v6: bits 2 / 3 of the maskZ bytes are [Z_k > 0] / [Z_k < 0] (the fused-loss backward reads sign(Z_k) from them), next to
+    the two prox indicators in bits 0 / 1 -- also with negative thresholds, where bits 0 and 1 can both be set.  And the host-side
+    layer table is reused between calls only while every parameter sits at the same address."""
+    from dladmm_b200.function import run_forward
+    torch.manual_seed(5)
+    model, data = _model("full", 96, 200, 516, 3, seed=2, precision="tf32x3")
+    with torch.no_grad():
+        model.active_para[1].mul_(-0.5)                                          # negative thresholds in layer 1
+    spec, params = model._spec_and_params()
+    params = [p.detach() for p in params]
+    Z, E, L, T, maskZ, maskE = run_forward(spec, model.A, data.X, model.Z0, model.E0, model.L0, params, want_masks=True, extras={})
+    assert torch.equal((maskZ & 4) != 0, Z > 0) and torch.equal((maskZ & 8) != 0, Z < 0)
+    assert ((maskZ[1] & 3) == 3).any()                                           # both indicators set somewhere under theta < 0
+    assert int(maskZ.max()) < 16 and int(maskE.max()) < 4
+    table = spec._layer_cache[1]
+    run_forward(spec, model.A, data.X, model.Z0, model.E0, model.L0, params, want_masks=False)
+    assert spec._layer_cache[1] is table                                         # same addresses: reused
+    moved = list(params); moved[0] = params[0].clone()
+    Z2, _, _, _, _, _ = run_forward(spec, model.A, data.X, model.Z0, model.E0, model.L0, moved, want_masks=False)
+    assert spec._layer_cache[1] is not table and torch.equal(Z2, Z)              # a parameter moved: rebuilt, same result
+
+
+def test_accumulator_compensation_removes_the_round_toward_zero_bias():
+    """The tensor core accumulates with round-toward-zero: one product shrinks by ~1.8e-8 per MMA (mean SIGNED error vs fp64).  The
+    epilogues' first-order compensation (umma_gemm.cuh, ACC_RZ_BIAS_PER_MMA) must remove that mean in both fp32-class modes and
+    bring the product to <= 2.5e-6 at K = 500 (measured 1.6e-6 / 1.8e-6; uncompensated 2.8e-6 / 3.8e-6 with a mean of -2.3e-6 /
+    -3.3e-6: profiles/r02_precision_table*.md)."""
+    torch.manual_seed(3)
+    m, d, B = 250, 500, 4096
+    A = torch.randn(m, d, device="cuda"); A = A / A.norm(dim=0, keepdim=True)
+    Zd = torch.randn(d, B, device="cuda")
+    z = torch.zeros(m, B, device="cuda")
+    want = A.double() @ Zd.double()
+    for mode in ("tf32_bf16x2", "tf32x3"):
+        got = dl.DLADMMNetScalar(m, 1, d, B, A, Zd, z, z, 1, precision=mode)._t0(z).double()
+        err = ((got - want).norm() / want.norm()).item()
+        bias = (((got - want) * want.sign()).sum() / want.abs().sum()).item()
+        assert err < 2.5e-6 and abs(bias) < 4e-7, (mode, err, bias)

@@ -158,3 +158,24 @@ def test_call_description_cache_tracks_replaced_parameters():
     _, pb = news._spec_and_params(3, drop_last_estep=True)
     nograd = [p for p in pb if not p.requires_grad]
     assert len(nograd) == 4 and all(any(q.data_ptr() == p.data_ptr() for q in news.parameters()) for p in nograd)
+
+
+def test_auto_precision_resolves_by_shape(monkeypatch):
+    """precision="auto" (the default): the split-precision mode from min(m, d) >= 192, three-pass tf32x3 below
+    (net.py::resolve_precision; error models in DESIGN.md 3.2); DLADMM_PRECISION overrides the default, an explicit
+    precision= overrides both; unknown names are refused."""
+    import dladmm_b200 as dl
+    monkeypatch.delenv("DLADMM_PRECISION", raising=False)
+    assert dl.default_precision() == "auto"
+    assert dl.resolve_precision("auto", 250, 500) == "tf32_bf16x2" and dl.resolve_precision("auto", 1000, 2000) == "tf32_bf16x2"
+    assert dl.resolve_precision("auto", 24, 40) == "tf32x3" and dl.resolve_precision("auto", 191, 4000) == "tf32x3"
+    assert dl.resolve_precision("bf16", 24, 40) == "bf16"
+    g = Golden("scalar_small")
+    assert build_model(g, "cpu").precision == "tf32x3"                         # m = 20..64 fixtures
+    big = dl.DLADMMNetScalar(250, 1, 500, 4, torch.randn(250, 500), torch.zeros(500, 4), torch.zeros(250, 4), torch.zeros(250, 4), 2,
+                             device="cpu")
+    assert big.precision == "tf32_bf16x2"
+    monkeypatch.setenv("DLADMM_PRECISION", "tf32")
+    assert build_model(g, "cpu").precision == "tf32" and build_model(g, "cpu", "fp32").precision == "fp32"
+    with pytest.raises(ValueError):
+        build_model(g, "cpu", "fp16")
