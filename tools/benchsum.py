@@ -18,7 +18,7 @@ if "c5" in d:
     c = d["c5"]
     print("c5 all %.2f ms (%.3f of peak %.1f) last_only %.2f ms" % (c["all_iterates"]["ms_per_step"], c["all_iterates"]["frac_of_tensor_peak"], c["tensor_peak_tflops"], c["last_only"]["ms_per_step"]),
           "| 1M:", c.get("total_1m", {}).get("ms"), "| train:", c.get("train", {}).get("ms_per_step"))
-if "small_batch" in d: print("small:", [(c["columns"], round(c["fwd_ms"], 3)) for c in d["small_batch"]["cases"]])
+if "small_batch" in d: print("small:", [(c["columns"], round(c["fwd_ms"], 3), round(c.get("fwd_ms_back_to_back", 0), 3)) for c in d["small_batch"]["cases"]])
 if "safeguard" in d: print("safeguard %.2f ms" % d["safeguard"]["ms"])
 if "eager_b200" in d: print("eager:", [(c["variant"], c["columns"], round(c["fwd_ms"], 2), round(c.get("train_ms") or 0, 2)) for c in d["eager_b200"]["cases"]])
 print("cpu_baseline:", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("kind"))
