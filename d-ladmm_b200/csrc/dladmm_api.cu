@@ -55,6 +55,7 @@ static int validate(const dladmm_problem* p, int for_backward) {
   DL_REQUIRE(p->abi_version == DLADMM_ABI_VERSION, "ABI version mismatch: got %d, library is %d", p->abi_version,
              DLADMM_ABI_VERSION);
   DL_REQUIRE(p->family >= 0 && p->family <= 2, "unknown family %d", p->family);
+  DL_REQUIRE(p->B < ((int64_t)1 << 28), "batch of %lld columns: the kernels address rows inside a chunk with 32 bits (B < 2^28)", (long long)p->B);
   DL_REQUIRE(p->precision >= 0 && p->precision <= 4, "unknown precision %d", p->precision);
   DL_REQUIRE(p->m > 0 && p->d > 0 && p->K >= 0, "m, d must be positive and K non-negative (m=%d d=%d K=%d)", p->m, p->d, p->K);
   DL_REQUIRE(p->K > 0 || !for_backward, "backward needs K > 0");

@@ -134,12 +134,15 @@ struct UEpiBG1 {
 #pragma unroll
       for (int i = 0; i < CHUNK; ++i) st.rv[i] = 0.f;
     }
+    // one 64-bit address per chunk, 32-bit row offsets inside it (the host refuses batches of 2^28 columns and more): a 64-bit
+    // row * B + b per row and array was 12 of the 41 instructions per element row of this issue-bound epilogue (ncu source page)
+    float* const dx1c = dx1 + ((i64)row0 * B + b);
+    const unsigned Bu = (unsigned)B;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;         // warp-uniform
       const bool ok = valid;
-      const i64 off = (i64)row * B + b;
       float dz = v[i];
       if (st.o_gz >= 0) dz += slot[st.o_gz + i * TILE_B + col];
       if (st.o_cz >= 0) dz += slot[st.o_cz + i * TILE_B + col];
@@ -148,7 +151,7 @@ struct UEpiBG1 {
       const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_put<PS, 0, 1>(st, th1, i, row, b, ok, dz * (mn - mp));
-      if (ok) dx1[off] = o;
+      if (ok) dx1c[(unsigned)i * Bu] = o;
     }
     { const int slots[1] = {SL_TH1}; red_flush<PS, 1, CHUNK, CHUNK>(st, ro, slots, st.gmask, row0, n_feat, group, st.lane); }
   }
@@ -243,12 +246,15 @@ struct UEpiBG2 {
   template <bool FAST>
   __device__ __forceinline__ void rows_body(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                             const float (&v)[CHUNK], int n_feat, i64 group) const {
+    const i64 off0 = (i64)row0 * B + b;              // one 64-bit offset per chunk, 32-bit row offsets inside it (see UEpiBG1)
+    float* const dRc = dR + off0; float* const cEc = cE + off0; float* const cLc = cL + off0;
+    const unsigned Bu = (unsigned)B;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FAST && row >= n_feat) continue;         // warp-uniform
       const bool ok = valid;
-      const i64 off = (i64)row * B + b;
+      const i64 off = off0 + (unsigned)i * Bu;
       const float vb1 = st.b1.at(row, b);
       const float lp = in(st, slot, 0, i, col), tk = in(st, slot, 1, i, col);
       const float var = lp + vb1 * tk;                // V_k recomputed
@@ -298,9 +304,9 @@ struct UEpiBG2 {
         dRv = dTt - v1 * dEt; nE = 0.f; nL = dL - v2 * dEt;
       }
       if (ok) {
-        dR[off] = dRv;
-        cE[off] = nE;
-        cL[off] = nL;
+        dRc[(unsigned)i * Bu] = dRv;
+        cEc[(unsigned)i * Bu] = nE;
+        cLc[(unsigned)i * Bu] = nL;
       }
     }
   }

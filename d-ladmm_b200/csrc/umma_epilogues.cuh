@@ -74,17 +74,21 @@ struct UEpiT0 {
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
+    // one 64-bit offset per chunk, 32-bit row offsets inside it (B < 2^28, checked by the host): see UEpiBG1 in umma_bwd.cuh
+    const i64 off0 = (i64)row0 * B + b;
+    const unsigned Bu = (unsigned)B;
+    float* const T0c = T0 + off0; float* const Vc = V + off0;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;
-      const i64 off = (i64)row * B + b;
+      const unsigned ro = (unsigned)i * Bu;
       const float e0 = slot[i * TILE_B + col], x = slot[SUBF(CHUNK) + i * TILE_B + col], l0 = slot[2 * SUBF(CHUNK) + i * TILE_B + col];
       const float t = fsub(fadd(v[i], e0), x);
-      T0[off] = t;
+      T0c[ro] = t;
       if (V || Vh) {                                             // (K = 0: T_0 only, no layer to feed)
         const float vv = fadd(l0, fmul(st.b1.at(row, b), t));
-        if (V) V[off] = vv;
+        if (V) Vc[ro] = vv;
         if (Vh) Vh[(i64)row * ldh + b] = __float2bfloat16_rn(vv);
       }
     }
@@ -125,17 +129,20 @@ struct UEpiZ {
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
+    const i64 off0 = (i64)row0 * B + b;              // (one 64-bit offset per chunk, 32-bit row offsets inside it)
+    const unsigned Bu = (unsigned)B;
+    float* const Zkc = Zk + off0; uint8_t* const mZc = maskZ + off0;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;
-      const i64 off = (i64)row * B + b;
+      const unsigned ro = (unsigned)i * Bu;
       const float wv = ss1.p ? fmul(st.s1, v[i]) : v[i];
       unsigned bits;
       const float z = soft_act(fsub(slot[i * TILE_B + col], wv), st.th1.at(row, b), bits);
-      Zk[off] = z;
+      Zkc[ro] = z;
       if (Zh) Zh[(i64)row * ldh + b] = __float2bfloat16_rn(z);
-      if (maskZ) maskZ[off] = (uint8_t)(bits | (z > 0.f ? 4u : 0u) | (z < 0.f ? 8u : 0u));    // bits 2, 3: sign(Z_k) for the fused-loss backward
+      if (maskZ) mZc[ro] = (uint8_t)(bits | (z > 0.f ? 4u : 0u) | (z < 0.f ? 8u : 0u));    // bits 2, 3: sign(Z_k) for the fused-loss backward
       if (obj_part) st.obj += fabsf(z);
       if (sq_part) { const float dl = slot[SUBF(CHUNK) + i * TILE_B + col] - z; st.sq += dl * dl; }   // warp-uniform branch
     }
@@ -203,11 +210,15 @@ struct UEpiELT {
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
+    const i64 off0 = (i64)row0 * B + b;              // (one 64-bit offset per chunk, 32-bit row offsets inside it)
+    const unsigned Bu = (unsigned)B;
+    float* const Ekc = Ek + off0; float* const Tnc = Tn + off0; float* const Lkc = Lk + off0; float* const Vc = V + off0;
+    uint8_t* const mEc = maskE + off0;
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;
-      const i64 off = (i64)row * B + b;
+      const unsigned ro = (unsigned)i * Bu;
       const float x = slot[i * TILE_B + col], lp = slot[SUBF(CHUNK) + i * TILE_B + col], acc = v[i];
       float e;
       unsigned bits = 0;
@@ -226,7 +237,7 @@ struct UEpiELT {
       }
       const float t = fsub(fadd(acc, e), x);
       const float l = fadd(lp, fmul(st.bL.at(row, b), t));
-      Ek[off] = e; Tn[off] = t; Lk[off] = l;
+      Ekc[ro] = e; Tnc[ro] = t; Lkc[ro] = l;
       if (obj_part) { const float r = fsub(e, t); st.obj += obj_kind == 2 ? 0.5f * r * r : fabsf(r); }
       if (MET) {
         const float r = fsub(e, t);
@@ -236,10 +247,10 @@ struct UEpiELT {
         st.met[4] += fabsf(e); st.met[5] += l * x;
         st.met[6] += softplus_t(l - 1.f) + softplus_t(-l - 1.f);
       }
-      if (FAM != DLADMM_FAMILY_C && maskE) maskE[off] = (uint8_t)bits;
+      if (FAM != DLADMM_FAMILY_C && maskE) mEc[ro] = (uint8_t)bits;
       if (has_next) {
         const float vv = fadd(l, fmul(st.b1n.at(row, b), t));
-        if (V) V[off] = vv;
+        if (V) Vc[ro] = vv;
         if (Vh) Vh[(i64)row * ldh + b] = __float2bfloat16_rn(vv);
       }
     }
