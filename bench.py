@@ -47,6 +47,12 @@ try:      # round 2: the persistent kernel's capture (profiles/r02_ncu_persisten
     TRAFFIC_NCU[("tf32x3", "fwd_persistent")] = _j["dram__bytes_read.sum"] + _j["dram__bytes_write.sum"]
 except Exception:
     pass
+try:      # ... and of the default split-precision mode (profiles/r02_ncu_persistent_mixed.json)
+    with open(os.path.join(ROOT, "profiles", "r02_ncu_persistent_mixed.json")) as _fh:
+        _j = json.load(_fh)
+    TRAFFIC_NCU[("tf32_bf16x2", "fwd_persistent")] = _j["dram__bytes_read.sum"] + _j["dram__bytes_write.sum"]
+except Exception:
+    pass
 
 
 def _peaks():
