@@ -205,7 +205,7 @@ static int backward_simt(const dladmm_problem* p, const dladmm_cotangents* g, co
   // top layer: elementwise cotangent flow with nothing carried
   {
     M1Args a = make_m1(p, g, w, K - 1);
-    dim3 grid(w.ncolTiles, (m + 7) / 8);
+    dim3 grid((w.ncolTiles + 7) / 8, m);
     { LaunchScope ls(DLADMM_KIND_BWD_ELEM, st); m1_kernel<FAM><<<grid, 256, 0, st>>>(m, B, a, w.part, w.ncolTiles, w.prow); }
     DL_CUDA(cudaGetLastError());
     ReduceJobs jobs; jobs.n = 0;

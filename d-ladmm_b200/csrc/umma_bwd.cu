@@ -66,7 +66,7 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
   // top layer: elementwise cotangent flow with nothing carried (FFMA-path kernel), then split dR
   {
     M1Args a = make_m1(p, g, sw, K - 1);
-    dim3 grid(sw.ncolTiles, (m + 7) / 8);
+    dim3 grid((sw.ncolTiles + 7) / 8, m);
     { LaunchScope ls(DLADMM_KIND_BWD_ELEM, st); m1_kernel<FAM><<<grid, 256, 0, st>>>(m, B, a, sw.part, sw.ncolTiles, sw.prow); }
     DL_CUDA(cudaGetLastError());
     ReduceJobs jobs; jobs.n = 0;
