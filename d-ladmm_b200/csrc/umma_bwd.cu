@@ -11,9 +11,9 @@ static int launch_nt(const float* P, int M, const float* Q, int N, i64 B, const 
   const CUtensorMapSwizzle sw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tP, tQ;
   int rc;
-  if ((rc = umma::make_tmap_2d(&tP, P, M, B, B, KC, 128, sw))) return rc;
+  if ((rc = umma::make_tmap_2d(&tP, P, M, B, B, KC, umma::NT_PROWS, sw))) return rc;
   if ((rc = umma::make_tmap_2d(&tQ, Q, N, B, B, KC, umma::TILE_N, sw))) return rc;
-  const int mt = (M + 127) / 128, nt = (N + umma::TILE_N - 1) / umma::TILE_N;
+  const int mt = (M + umma::NT_PROWS - 1) / umma::NT_PROWS, nt = (N + umma::TILE_N - 1) / umma::TILE_N;
   int split = std::max(1, device_sm_count() / (mt * nt));
   i64 chunk = round_up64((B + split - 1) / split, KC);
   split = (int)((B + chunk - 1) / chunk);

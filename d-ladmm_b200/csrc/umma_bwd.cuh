@@ -315,7 +315,11 @@ struct UEpiBG2 {
 // ---- dW[i,j] += alpha * sum_b P[i,b] * Q[j,b]  (P = dx1 (d x B), Q = V_k (m x B)), K = batch ------------------
 // Both operands are K-major (batch contiguous).  One 128 x 256 output tile per CTA over a slice of the batch;
 // partial results are added to dW with fp32 reductions (red.global.add).
-constexpr int NT_EPI_WARPS = 16;          // epilogue warps of the dW kernel (atomics of a 128 x 256 tile): 4 per quadrant
+constexpr int NT_EPI_WARPS = 16;          // epilogue warps of the dW kernel (atomics of a 256 x 256 tile): 4 per quadrant
+// Rows of dW per CTA: 256 = two tcgen05.mma of M = 128 per k-step into two TMEM accumulators, both reading the same Q tile.  The kernel
+// is bound by shared-memory bandwidth (ncu: l1tex 71 %, tensor pipe 39 %: TMA writes + in-smem split + operand reads = 120 KB per
+// 16-column chunk of a 128 x 256 tile); per flop the 256-row tile moves 96 KB -- Q is staged and split once for twice the products.
+constexpr int NT_PROWS = 256;
 // Mixed mode (NPASS == 4) of the dW product: P.Q^T = trunc(P).trunc(Q)^T on kind::tf32 (the raw words) + bf16(P_small).bf16(Q)^T +
 // bf16(P).bf16(Q_small)^T on kind::f16.  Both operands are K-major rows of 16 floats (64 bytes, SWIZZLE_64B: 16-byte chunk c of
 // row r sits at chunk c ^ ((r >> 1) & 3)); the split writes, for every row, a 64-byte row [bf16(x)[16] | bf16(x_small)[16]] with the
@@ -353,7 +357,7 @@ __device__ __forceinline__ void split_rows_mix(const uint8_t* raw, uint8_t* pack
 template <int NPASS, int KC>
 struct NtPlan {
   static constexpr int NOPS = NPASS >= 3 ? 2 : 1;
-  static constexpr int A_BYTES = 128 * KC * 4;
+  static constexpr int A_BYTES = NT_PROWS * KC * 4;                   // P tile: two M = 128 halves that share the Q tile of the stage
   static constexpr int B_BYTES = TILE_N * KC * 4;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);     // [P raw | Q raw] [P small | Q small]
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES;                 // what TMA delivers
@@ -388,7 +392,8 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
   uint64_t* ready = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * 128;
+  const int i0 = blockIdx.x * NT_PROWS;
+  const int halves = ns.M - i0 > 128 ? 2 : 1;         // (a last tile of <= 128 valid rows skips its second half)
   const int n0 = blockIdx.z * TILE_N;                 // tile of Q rows (columns of dW)
   const i64 b_begin = (i64)blockIdx.y * ns.chunk;
   i64 b_end = b_begin + ns.chunk;
@@ -401,7 +406,7 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -433,10 +438,13 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + s * (Plan::STAGE_BYTES >> 4), b_lo = b_lo0 + s * (Plan::STAGE_BYTES >> 4);
         // raw * raw (big * big) needs no split: issued while the splitters work on the stage
+        constexpr uint32_t HALF = (128 * KC * 4) >> 4;        // descriptor offset of the second 128 rows of the P tile
         if (elect_one()) {
+          for (int h = 0; h < halves; ++h) {
 #pragma unroll
-          for (int ks = 0; ks < KC / UMMA_K; ++ks)
-            umma_tf32(tmem_base, desc_at(hi, a_lo + ks * 2), desc_at(hi, b_lo + ks * 2), idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < KC / UMMA_K; ++ks)
+              umma_tf32(tmem_base + h * TILE_N, desc_at(hi, a_lo + h * HALF + ks * 2), desc_at(hi, b_lo + ks * 2), idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+          }
         }
         __syncwarp();
         if (NPASS >= 3) {
@@ -447,18 +455,23 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
           if (NPASS == 4) {
             // bf16 correction products (K = 16 = the chunk): packed rows [bf16(x) | bf16(x_small)], 32 bytes each
             constexpr uint32_t idesc16 = make_idesc(128, TILE_N, 0, 0, 1u);
-            const uint32_t a16 = a_lo + (Plan::RAW_BYTES >> 4), b16 = b_lo + (Plan::RAW_BYTES >> 4);
-            umma_f16(tmem_base, desc_at(hi, a16 + 2), desc_at(hi, b16), idesc16, 1u);      // P_small . Q
-            umma_f16(tmem_base, desc_at(hi, a16), desc_at(hi, b16 + 2), idesc16, 1u);      // P . Q_small
+            const uint32_t b16 = b_lo + (Plan::RAW_BYTES >> 4);
+            for (int h = 0; h < halves; ++h) {
+              const uint32_t a16 = a_lo + h * HALF + (Plan::RAW_BYTES >> 4);
+              umma_f16(tmem_base + h * TILE_N, desc_at(hi, a16 + 2), desc_at(hi, b16), idesc16, 1u);      // P_small . Q
+              umma_f16(tmem_base + h * TILE_N, desc_at(hi, a16), desc_at(hi, b16 + 2), idesc16, 1u);      // P . Q_small
+            }
           }
           if (NPASS == 3) {
+            for (int h = 0; h < halves; ++h) {
 #pragma unroll
             for (int ks = 0; ks < KC / UMMA_K; ++ks) {
-              const uint64_t da = desc_at(hi, a_lo + ks * 2), db = desc_at(hi, b_lo + ks * 2);
-              const uint64_t das = desc_at(hi, a_lo + (Plan::RAW_BYTES >> 4) + ks * 2);
+              const uint64_t da = desc_at(hi, a_lo + h * HALF + ks * 2), db = desc_at(hi, b_lo + ks * 2);
+              const uint64_t das = desc_at(hi, a_lo + h * HALF + (Plan::RAW_BYTES >> 4) + ks * 2);
               const uint64_t dbs = desc_at(hi, b_lo + (Plan::RAW_BYTES >> 4) + ks * 2);
-              umma_tf32(tmem_base, das, db, idesc, 1u);
-              umma_tf32(tmem_base, da, dbs, idesc, 1u);
+              umma_tf32(tmem_base + h * TILE_N, das, db, idesc, 1u);
+              umma_tf32(tmem_base + h * TILE_N, da, dbs, idesc, 1u);
+            }
             }
           }
           umma_commit(&empty[s]);
@@ -493,14 +506,16 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
       const float alpha = sign * (s1ptr ? __ldg(s1ptr) : 1.f) * (1.0f + ns.acc_unit * (float)k_chunks);
       mbar_wait(tfull, 0);                              // every MMA has retired: the operand stages are free
       tc_fence_after();
-      const uint32_t t0 = tmem_base + half * (TILE_N / EPI_PARTS) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t00 = tmem_base + half * (TILE_N / EPI_PARTS) + ((uint32_t)(q * 32) << 16);
       // A TMEM lane is a ROW of dW, so a warp's 32 lanes hold 32 rows x (consecutive columns): adding straight from the
       // registers touches 32 sectors per instruction.  Each 32 x 32 block is transposed through shared memory (the free operand
       // stages, 33-float pitch) so that one reduction instruction covers 32 consecutive columns of one row (4-5 sectors): 8x
       // fewer L2 reduction operations for the same 148 x 32 K partial sums.
       float* tr = reinterpret_cast<float*>(smem) + (warp - EPI_WARP0) * (32 * 33);
       static_assert(NT_EPI_WARPS * 32 * 33 * 4 <= Plan::STAGES * Plan::STAGE_BYTES, "transpose scratch fits the operand ring");
-      const int row0 = i0 + q * 32;
+      for (int hh = 0; hh < halves; ++hh) {
+      const int row0 = i0 + hh * 128 + q * 32;
+      const uint32_t t0 = t00 + hh * TILE_N;
 #pragma unroll 1
       for (int c = 0; c < (TILE_N / EPI_PARTS) / 32; ++c) {
         const int j0 = n0 + half * (TILE_N / EPI_PARTS) + c * 32;
@@ -517,11 +532,12 @@ umma_nt_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         }
         __syncwarp();
       }
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace umma
