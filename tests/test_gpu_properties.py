@@ -381,3 +381,24 @@ def test_accumulator_compensation_removes_the_round_toward_zero_bias():
         err = ((got - want).norm() / want.norm()).item()
         bias = (((got - want) * want.sign()).sum() / want.abs().sum()).item()
         assert err < 2.5e-6 and abs(bias) < 4e-7, (mode, err, bias)
+
+
+@pytest.mark.parametrize("m,d,B", [(96, 200, 1000), (130, 260, 516), (300, 700, 2048), (64, 128, 40)])
+@pytest.mark.parametrize("precision", ["tf32_bf16x2", "tf32x3"])
+def test_weight_gradient_tiles_at_odd_shapes(m, d, B, precision):
+    """The dW kernel works on 256 x 256 tiles of (d x m): one or two M = 128 halves per CTA, several tiles in both directions,
+    ragged last tiles, batch slices that do not divide evenly.  Every parameter gradient (dW above all) of both fp32-class modes
+    against the FFMA (fp32) path, which the fixtures pin to the reference."""
+    K = 2
+    res = {}
+    for prec in ("fp32", precision):
+        model, data = _model("scalar", m, d, B, K, seed=4, precision=prec)
+        loss, _ = model.l1l1_loss(data.X, 0.01, [0.5, 1.0])
+        loss.backward()
+        res[prec] = (loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()})
+    (l0, g0), (l1, g1) = res["fp32"], res[precision]
+    assert abs(l0 - l1) < 2e-5 * abs(l0)
+    G = max(v.norm().item() for n, v in g0.items() if v.numel() == 1)
+    for n in g0:
+        assert torch.isfinite(g1[n]).all(), n
+        assert rel_l2(g1[n], g0[n], floor=1e-2 * G if g0[n].numel() == 1 else 1e-5) < 1e-2, (n, rel_l2(g1[n], g0[n]))
