@@ -274,13 +274,25 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceJobs 
     }
     if (threadIdx.x == 0) atomicAdd(jb.grad, sm[0]);   // one add per (parameter, launch); atomic because a C-ABI caller may alias grads between slots
   } else {
-    // one warp per row
-    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= jb.rows) return;
-    float s = 0.f;
-    for (int ct = threadIdx.x & 31; ct < ncolTiles; ct += 32) s += base[(i64)ct * prow + row];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) atomicAdd(jb.grad + row, s);
+    // 8 consecutive rows per block: thread t reads row (t & 7) of column tiles (t >> 3), (t >> 3) + 32, ... -- a warp's load covers
+    // four tiles x 8 rows = four full 32-byte sectors (one warp per row with the lanes over the tiles used 4 bytes of every sector it
+    // touched: 0.66 ms per `full` K = 20 step); fixed summation order
+    const int r = threadIdx.x & 7, c = threadIdx.x >> 3;
+    const int row = blockIdx.x * 8 + r;
+    float s0 = 0.f, s1 = 0.f;
+    if (row < jb.rows) {
+      for (int ct = c; ct < ncolTiles; ct += 64) {
+        s0 += base[(i64)ct * prow + row];
+        if (ct + 32 < ncolTiles) s1 += base[(i64)(ct + 32) * prow + row];
+      }
+    }
+    sm[threadIdx.x] = s0 + s1;                       // [c][r]
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+      if (c < o) sm[c * 8 + r] += sm[(c + o) * 8 + r];
+      __syncthreads();
+    }
+    if (c == 0 && row < jb.rows) atomicAdd(jb.grad + row, sm[r]);
   }
 }
 
