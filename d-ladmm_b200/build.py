@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdladmm.so")
-SOURCES = ["dladmm_api.cu", "umma_fwd.cu", "umma_bwd.cu", "gen_syn.cu", "safeguard.cu"]
+SOURCES = ["dladmm_api.cu", "umma_fwd.cu", "umma_pfwd.cu", "umma_bwd.cu", "gen_syn.cu", "safeguard.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

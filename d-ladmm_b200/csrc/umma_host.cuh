@@ -43,6 +43,11 @@ struct UWorkspace {
   size_t bytes;
   int m256, d256, mp, dp, nW;
 };
+// The all-layer persistent forward lives in its own translation unit (umma_pfwd.cu); returns DLADMM_PF_NOT_TAKEN when the call is
+// not eligible for it (the caller then runs the per-layer schedule of umma_fwd.cu).
+constexpr int DLADMM_PF_NOT_TAKEN = 1000;
+int umma_forward_persistent(const dladmm_problem* p, const UWorkspace& w, cudaStream_t st);
+
 static inline bool wants_metric(const dladmm_problem* p, int i) { return p->metrics && ((p->metrics->want >> i) & 1u); }
 constexpr int OBJ_ENTRIES = 256 * umma::MAX_EPI_WARPS;   // upper bound of (grid x epilogue warps)
 
