@@ -56,7 +56,9 @@ static int launch_elt(const dladmm_problem* p, const UWorkspace& w, const Slabs&
   epi.met_stride = OBJ_ENTRIES;              // the ELT-side metrics are DLADMM_MET_L1_RES .. DLADMM_MET_DGAP_L, in order
   epi.Vh = (NPASS == 2 && Vnext_h) ? Vnext_h : nullptr; epi.ldh = w.ldh;
   if (NPASS == 2 && !p->Vsave) epi.V = nullptr;      // bf16 mode: the fp32 V is only kept for a backward
-  return launch_umma<umma::UEpiELT<FAM, PS, MET>, NPASS>(DLADMM_KIND_GEMM_ELT, Zk, p->d, w.Ab, w.As, w.m256, w.dp, p->m, p->B, epi, st, 0, w.ldh);
+  const i64 nbt = (p->B + umma::TILE_B - 1) / umma::TILE_B;
+  const int grid_e = (int)std::min<i64>(nbt * ((p->m + umma::TILE_N - 1) / umma::TILE_N), device_sm_count());
+  return launch_umma<umma::UEpiELT<FAM, PS, MET>, NPASS>(DLADMM_KIND_GEMM_ELT, Zk, p->d, w.Ab, w.As, w.m256, w.dp, p->m, p->B, epi, st, grid_e, w.ldh);
 }
 
 template <int FAM, int NPASS, int PS>
@@ -68,6 +70,10 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
   const bool met = mt != nullptr && mt->want != 0;
   int rc;
   if ((rc = uprepare_weights<NPASS>(p, w, st, met && (mt->want >> DLADMM_MET_DGAP_ATL) & 1u))) return rc;
+  // per-CTA partial sums of the fused objective / metrics: the reductions count grid x warps entries per layer; a CTA-pair launch
+  // runs an even grid (one CTA fewer when that count is odd), so the entries start at zero
+  if (p->objective && K > 0) DL_CUDA(cudaMemsetAsync(w.objp, 0, sizeof(float) * (size_t)K * 2 * OBJ_ENTRIES, st));
+  if (met && K > 0) DL_CUDA(cudaMemsetAsync(w.metp, 0, sizeof(float) * (size_t)K * DLADMM_MET_COUNT * OBJ_ENTRIES, st));
   // V_k: one reused scratch slab, or every layer's kept for the backward (dladmm_problem.Vsave)
   auto Vslab = [&](int k) { return p->Vsave ? p->Vsave + s.ms * k : w.V; };
   const i64 nbt = (B + umma::TILE_B - 1) / umma::TILE_B;
@@ -120,7 +126,7 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
       // bf16 mode: weights are bf16 arrays of the same (d256 x mp) element count, at half the byte stride
       const void* wk = BF ? (const void*)((const __nv_bfloat16*)w.Wb + wi * w.d256 * w.mp) : (const void*)(w.Wb + wi * w.d256 * w.mp);
       const void* vop = BF ? (const void*)w.Vh : (const void*)Vslab(k);
-      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, vop, m, wk, w.Ws + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st, 0, w.ldh)))
+      if ((rc = launch_umma<umma::UEpiZ<PS>, NPASS>(DLADMM_KIND_GEMM_Z, vop, m, wk, w.Ws + wi * w.d256 * w.mp, w.d256, w.mp, d, B, epi, st, grid_z, w.ldh)))
         return rc;
     }
     if (estep) {
@@ -133,7 +139,7 @@ static int forward_umma(const dladmm_problem* p, const UWorkspace& w, cudaStream
         umma::UEpiDgap epi; epi.a = mt->dual_alpha; epi.part = met_slot(w, k, DLADMM_MET_DGAP_ATL);
         const void* lop = s.Lout(k);
         if (BF) { if ((rc = to_bf16(s.Lout(k), m, w.Lh))) return rc; lop = w.Lh; }
-        if ((rc = launch_umma<umma::UEpiDgap, NPASS>(DLADMM_KIND_METRIC_GEMM, lop, m, w.Atb, w.Ats, w.d256, w.mp, d, B, epi, st, 0, w.ldh))) return rc;
+        if ((rc = launch_umma<umma::UEpiDgap, NPASS>(DLADMM_KIND_METRIC_GEMM, lop, m, w.Atb, w.Ats, w.d256, w.mp, d, B, epi, st, grid_z, w.ldh))) return rc;
       }
     }
   }

@@ -4,6 +4,7 @@
 #include "umma_gemm.cuh"
 #include "umma_epilogues.cuh"
 #include "umma_persist.cuh"
+#include "umma_pair.cuh"
 
 namespace dladmm {
 
@@ -317,11 +318,94 @@ static int device_sm_count() {
 // NPASS: 3 = 3xTF32, 1 = TF32, 2 = BF16 (act / w_big are then bf16 arrays; act has pitch `act_pitch` elements).
 template <int NPASS> struct KChunk { static constexpr int value = NPASS >= 3 ? 16 : (NPASS == 2 ? 64 : 32); };
 
+// DLADMM_PAIR=0: never use the CTA-pair kernel; DLADMM_PAIR=1: use it for every split-precision product with at least two batch
+// tiles (tests); default: for reduction lengths >= PAIR_MIN_K (mainloop-bound products: the large-scale shape)
+static bool pair_wanted(int Kdim, i64 B) {
+  const char* e = getenv("DLADMM_PAIR");             // (read per launch: the tests switch it inside one process)
+  const int mode = e ? (e[0] == '0' ? 0 : 1) : 2;
+  if (mode == 0 || B <= umma::TILE_B) return false;
+  return mode == 1 || Kdim >= umma::PAIR_MIN_K;
+}
+
+// the split-precision product on CTA pairs (umma_pair.cuh); same arguments as launch_umma below
+template <class Epi>
+static int launch_umma_pair(int kind, const void* act, int Kdim, const void* w_big, const void* w_pack, int n_pad, int k_pad, int n_feat,
+                            i64 B, Epi epi, cudaStream_t st, int grid_override) {
+  constexpr int KC = umma::PAIR_KC;
+  CUtensorMap tA, tBb, tBp;
+  int rc;
+  if ((rc = umma::make_tmap_2d(&tA, (const float*)act, Kdim, B, B, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = umma::make_tmap_2d(&tBb, (const float*)w_big, n_pad, k_pad, k_pad, KC, umma::TILE_N / 2, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = umma::make_tmap_2d(&tBp, (const float*)w_pack, n_pad, k_pad, k_pad, KC, umma::TILE_N / 2, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  umma::EMaps em;
+  {
+    const float* ptrs[umma::MAX_EIN] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    epi.host_inputs(ptrs);
+    epi.in_mask = 0;
+    for (int i = 0; i < Epi::NIN; ++i) {
+      if (!ptrs[i]) continue;
+      epi.in_mask |= 1u << i;
+      if ((rc = umma::make_tmap_2d(&em.m[i], ptrs[i], n_feat, B, B, umma::TILE_B, Epi::CHUNK, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    }
+    for (int i = 0; i < umma::MAX_EIN; ++i)
+      if (!(epi.in_mask & (1u << i))) em.m[i] = tBb;
+    em.mk = tBb;
+    if (epi.host_mask() && epi.in_mask != 0 && (B % 16) == 0) {
+      if ((rc = umma::make_tmap_2d_u8(&em.mk, epi.host_mask(), n_feat, B, B, umma::TILE_B, Epi::CHUNK))) return rc;
+      epi.in_mask |= umma::EIN_MASK_BIT;
+    }
+    const int nin = __builtin_popcount(epi.in_mask & ~umma::EIN_MASK_BIT);
+    const int slot_bytes = nin * Epi::CHUNK * umma::TILE_B * 4 + ((epi.in_mask & umma::EIN_MASK_BIT) ? Epi::CHUNK * umma::TILE_B : 0);
+    if (nin > 0 && umma::PairPlan<Epi::WARPS>::RING / slot_bytes < Epi::WARPS / 4) {
+      set_error("epilogue staging ring too small (pair kernel): %d bytes per slot, %d parts", slot_bytes, Epi::WARPS / 4);
+      return DLADMM_ERR_INVALID;
+    }
+  }
+  umma::GemmShape gs;
+  memset(&gs, 0, sizeof(gs));
+  gs.n_feat = n_feat;
+  gs.n_ntiles = (n_feat + umma::TILE_N - 1) / umma::TILE_N;
+  gs.k_chunks = (Kdim + KC - 1) / KC;
+  gs.acc_scale = umma::acc_comp_scale(gs.k_chunks * umma::mma_per_chunk(4));
+  gs.B = B;
+  gs.n_btiles = (B + umma::TILE_B - 1) / umma::TILE_B;
+  gs.n_full = gs.n_tiles = gs.n_btiles * gs.n_ntiles;
+  auto kern = umma::umma_gemm_pair_kernel<Epi>;
+  static bool attr_set[MAX_DEVICES] = {false};
+  const int dev = current_device_index();
+  if (!attr_set[dev]) {
+    DL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::PairPlan<Epi::WARPS>::SMEM));
+    attr_set[dev] = true;
+  }
+  const i64 n_ptiles = ((gs.n_btiles + 1) / 2) * gs.n_ntiles;
+  int grid = grid_override > 0 ? grid_override : (int)std::min<i64>(2 * n_ptiles, device_sm_count());
+  grid &= ~1;
+  if (grid < 2) grid = 2;
+  {
+    LaunchScope ls(kind, st);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::roles_threads(Epi::WARPS)); cfg.dynamicSmemBytes = umma::PairPlan<Epi::WARPS>::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    DL_CUDA(cudaLaunchKernelEx(&cfg, kern, tA, tBb, tBp, em, gs, epi));
+  }
+  DL_CUDA(cudaGetLastError());
+  return DLADMM_OK;
+}
+
 template <class Epi, int NPASS>
 static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, const void* w_small,
                        int n_pad, int k_pad, int n_feat, i64 B, Epi epi, cudaStream_t st, int grid_override = 0, i64 act_pitch = 0) {
   constexpr int KC = KChunk<NPASS>::value;
   using Plan = umma::SmemPlan<NPASS, KC>;
+  if constexpr (NPASS == 4) {
+    if (pair_wanted(Kdim, B)) return launch_umma_pair<Epi>(kind, act, Kdim, w_big, w_small, n_pad, k_pad, n_feat, B, epi, st, grid_override);
+  }
   CUtensorMap tA, tBb, tBs;
   int rc;
   if (NPASS == 2) {

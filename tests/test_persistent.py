@@ -123,3 +123,58 @@ def test_host_drain_returns_every_result_in_order():
     got += [h.clone() for h in drain.flush()]
     assert len(got) == 7 and all(torch.equal(a, b) for a, b in zip(got, want))
     assert drain.bytes_copied == 7 * 33 * 1000 * 4
+
+
+class env(object):
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("variant,m,d,B,K", [("scalar", 250, 500, 2048, 3), ("full", 250, 500, 1100, 2), ("lasso", 300, 1000, 644, 2),
+                                             ("ltheta", 64, 100, 516, 3), ("tied", 1000, 2000, 384, 1)])
+def test_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(variant, m, d, B, K):
+    """tcgen05.mma.cta_group::2 (umma_pair.cuh): two CTAs share the weight tile of a stage.  Per element the MMAs are issued in the same
+    order with the same operands as in the single-CTA kernel, so every iterate and prox mask must be bit-identical, and the fused objective and -- through the
+    backward products, which take the same path -- every gradient must agree to summation order; odd numbers of batch tiles, ragged
+    batches, per-row parameters, several feature tiles.  (Default use: reduction lengths >= 768; DLADMM_PAIR=1 forces it here.)"""
+    model, data = _model(variant, m, d, B, K, "tf32_bf16x2")
+    spec, params = model._spec_and_params()
+    det = [p.detach() for p in params]
+    res = {}
+    for pair in ("0", "1"):
+        with env(DLADMM_PAIR=pair, DLADMM_NO_PERSISTENT="1"):
+            ex = {}
+            out = run_forward(spec, model.A, data.X, model.Z0, model.E0, model.L0, det, want_masks=True, objective_alpha=0.01, extras=ex)
+            model.zero_grad(set_to_none=True)
+            if variant == "lasso":
+                loss, _ = model.lasso_loss(data.X, 0.01)
+            elif variant == "ltheta":
+                Z, E, L = model(data.X)
+                loss = sum(z.abs().sum() for z in Z) + sum(e.abs().sum() for e in E)
+            else:
+                loss, _ = model.l1l1_loss(data.X, 0.01)
+            loss.backward()
+            res[pair] = (out, ex["objective"].clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    (o0, j0, l0, g0), (o1, j1, l1, g1) = res["0"], res["1"]
+    for name, x, y in zip(("Z", "E", "L", "T", "maskZ", "maskE"), o0, o1):
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert torch.equal(x, y), (variant, name)
+    # (the fused objective is a sum of per-CTA partial sums: another tile -> CTA assignment, another summation order)
+    assert torch.allclose(j0, j1, rtol=2e-6) and abs(l0 - l1) <= 2e-6 * abs(l0)
+    for n in g0:
+        if n.startswith("fc"):      # dW goes through fp32 reductions in L2 in whatever order the CTAs arrive
+            assert torch.allclose(g0[n], g1[n], rtol=1e-4, atol=1e-6 * float(g0[n].abs().max())), n
+        else:
+            assert torch.allclose(g0[n], g1[n], rtol=2e-5, atol=1e-7 * max(1.0, float(g0[n].abs().max()))), n
