@@ -97,6 +97,7 @@ template <int PM>
 struct UEpiBG1 {
   static constexpr bool PS = PM == PM_SCALAR;
   static constexpr int WARPS = 16;                 // measured: 1.97 -> 1.67 ms per 15 layers against 8 warps
+  static constexpr int PAIR_MIN_K = 192;           // CTA-pair kernel from this reduction length on (C1: 1.58 -> 1.45 ms per 15 layers)
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 2;                    // gZ_k, carried dZ -- each optional (the fused loss takes sign(Z_k) from bits 2, 3 of the mask)
   struct State { float red[1]; float rv[PS ? 1 : CHUNK]; uint32_t gmask; int lane; float lsc; int o_gz, o_cz, o_zk, o_mk; };

@@ -320,11 +320,16 @@ template <int NPASS> struct KChunk { static constexpr int value = NPASS >= 3 ? 1
 
 // DLADMM_PAIR=0: never use the CTA-pair kernel; DLADMM_PAIR=1: use it for every split-precision product with at least two batch
 // tiles (tests); default: for reduction lengths >= PAIR_MIN_K (mainloop-bound products: the large-scale shape)
-static bool pair_wanted(int Kdim, i64 B) {
+// (an epilogue functor may lower the threshold with `static constexpr int PAIR_MIN_K`: the dZ product of the backward gains 8 % from
+//  the pair kernel already at K = 250 -- its 16-warp epilogue is issue-bound and the pair kernel's leaner stage loop leaves it more
+//  issue slots -- while dV, HBM-bound on its staging ring, loses 30 % there)
+template <class E, class = void> struct pair_min_k_of { static constexpr int value = umma::PAIR_MIN_K; };
+template <class E> struct pair_min_k_of<E, decltype((void)E::PAIR_MIN_K)> { static constexpr int value = E::PAIR_MIN_K; };
+static bool pair_wanted(int Kdim, i64 B, int min_k) {
   const char* e = getenv("DLADMM_PAIR");             // (read per launch: the tests switch it inside one process)
   const int mode = e ? (e[0] == '0' ? 0 : 1) : 2;
   if (mode == 0 || B <= umma::TILE_B) return false;
-  return mode == 1 || Kdim >= umma::PAIR_MIN_K;
+  return mode == 1 || Kdim >= min_k;
 }
 
 // the split-precision product on CTA pairs (umma_pair.cuh); same arguments as launch_umma below
@@ -404,7 +409,7 @@ static int launch_umma(int kind, const void* act, int Kdim, const void* w_big, c
   constexpr int KC = KChunk<NPASS>::value;
   using Plan = umma::SmemPlan<NPASS, KC>;
   if constexpr (NPASS == 4) {
-    if (pair_wanted(Kdim, B)) return launch_umma_pair<Epi>(kind, act, Kdim, w_big, w_small, n_pad, k_pad, n_feat, B, epi, st, grid_override);
+    if (pair_wanted(Kdim, B, pair_min_k_of<Epi>::value)) return launch_umma_pair<Epi>(kind, act, Kdim, w_big, w_small, n_pad, k_pad, n_feat, B, epi, st, grid_override);
   }
   CUtensorMap tA, tBb, tBs;
   int rc;
