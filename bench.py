@@ -632,15 +632,30 @@ def run_ours(args):
                 tm5.zero_grad(set_to_none=True)
                 loss, _ = tm5.l1l1_loss(Xt5, 0.001)
                 loss.backward()
-            step5t()
-            barrier()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for _ in range(2):
+
+            def time5t():
                 step5t()
-            t1.record()
-            barrier()
-            c5["train_ms"] = t0.elapsed_time(t1) / 2
+                step5t()
+                barrier()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(4):
+                    step5t()
+                t1.record()
+                barrier()
+                return t0.elapsed_time(t1) / 4
+            if world > 1:
+                # the same step with the opt-in schedule: weight gradients reduced in 32 MB buckets from a side stream while the
+                # layers below run; then the default, ONE collective after the backward; same sums asserted
+                tm5.sync_gradients(True, bucket_mb=32)
+                c5["train_bucketed_ms"] = time5t()
+                g_bucketed = [p_.grad.clone() for p_ in tm5.parameters()]
+                tm5.sync_gradients(True)
+            c5["train_ms"] = time5t()
+            if world > 1:
+                worst = max(((a - b.grad).norm() / a.norm().clamp_min(1e-20)).item() for a, b in zip(g_bucketed, tm5.parameters()))
+                assert worst < 1e-5, "bucketed and single-collective gradient sync disagree: %g" % worst
+                del g_bucketed
             c5["train_columns"] = Bt5
             del tm5, Xt5
         del model5, data5
@@ -651,7 +666,7 @@ def run_ours(args):
     if e2e_z:
         extra_keys.append(("e2e_z", e2e_z["ms_per_step"]))
     if c5:
-        extra_keys += [(k, c5[k]) for k in ("total_1m_ms", "train_ms") if k in c5]
+        extra_keys += [(k, c5[k]) for k in ("total_1m_ms", "train_ms", "train_bucketed_ms") if k in c5]
     stats = torch.tensor([ms_total, ms_e2e, train["ms_per_step"] if train else 0.0,
                           c5["all_iterates"] if c5 else 0.0, c5["last_only"] if c5 else 0.0] + [v for _, v in extra_keys],
                          device=dev, dtype=torch.float64)
@@ -811,6 +826,13 @@ def run_ours(args):
                                        "unit": "samples/s", "algorithmic_tflops_per_gpu": Bt5 * f5t / (extra["train_ms"] * 1e-3) / 1e12,
                                        "frac_of_tensor_peak": Bt5 * f5t / (extra["train_ms"] * 1e-3) / 1e12 / tp,
                                        "gradient_bytes_allreduced": int(4 * 40 * (1000 * 2000 + 6)) if world > 1 else 0}
+                if "train_bucketed_ms" in extra:
+                    line["c5"]["train"]["allreduce"] = {
+                        "schedule": "one collective on the step's flat gradient buffer, stream-ordered after the last backward kernel",
+                        "ms_per_step_bucketed_overlap": extra["train_bucketed_ms"],
+                        "bucketed_overlap": "opt-in sync_gradients(bucket_mb=32): weight gradients in 32 MB buckets (4 layers each), reverse layer "
+                                            "order, issued from a side stream when the library's per-layer event fires (timed first, on a "
+                                            "cooler chip; interleaved A/B: profiles/r02_c5_sync_sweep.md)"}
         if world == 1 and not args.quick:
             line["eager_b200"] = eager_b200_leg(dev, A_host, X)
             line["small_batch"] = small_batch_leg(dl, dev, A_host, X, precision)

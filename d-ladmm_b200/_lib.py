@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # (DLADMM_LIB_PATH: an alternative build of the same library, for A/B measurements of compile-time switches)
 LIB_PATH = os.environ.get("DLADMM_LIB_PATH") or os.path.join(HERE, "csrc", "libdladmm.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 FAMILY_A, FAMILY_B, FAMILY_C = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_BF16, PREC_TF32_BF16X2 = 0, 1, 2, 3, 4
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "bf16": PREC_BF16, "tf32_bf16x2": PREC_TF32_BF16X2}
@@ -48,7 +48,7 @@ class Metrics(C.Structure):
 class Cotangents(C.Structure):
     _fields_ = [("gZ", C.c_void_p), ("gE", C.c_void_p), ("gL", C.c_void_p), ("gT", C.c_void_p),
                 ("loss_kind", C.c_int32), ("loss_alpha", C.c_float), ("loss_layer_weight", C.POINTER(C.c_float)),
-                ("loss_scale", C.c_void_p)]
+                ("loss_scale", C.c_void_p), ("layer_events", C.POINTER(C.c_void_p))]
 
 
 class Caps(C.Structure):

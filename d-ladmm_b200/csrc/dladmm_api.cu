@@ -410,10 +410,14 @@ int dladmm_backward(const dladmm_problem* p, const dladmm_cotangents* g, void* s
   if (umma_eligible(p)) return umma_backward(p, g, w, (char*)p->workspace + w.bytes, st);
   if ((rc = prepare_weights(p, w, true, st))) return rc;
   switch (p->family) {
-    case DLADMM_FAMILY_A: return backward_simt<DLADMM_FAMILY_A>(p, g, w, st);
-    case DLADMM_FAMILY_B: return backward_simt<DLADMM_FAMILY_B>(p, g, w, st);
-    default: return backward_simt<DLADMM_FAMILY_C>(p, g, w, st);
+    case DLADMM_FAMILY_A: rc = backward_simt<DLADMM_FAMILY_A>(p, g, w, st); break;
+    case DLADMM_FAMILY_B: rc = backward_simt<DLADMM_FAMILY_B>(p, g, w, st); break;
+    default: rc = backward_simt<DLADMM_FAMILY_C>(p, g, w, st); break;
   }
+  if (rc == DLADMM_OK && g->layer_events)       // this path makes no per-layer promise: everything is final after its last kernel
+    for (int k = p->K - 1; k >= 0; --k)
+      if (g->layer_events[k]) DL_CUDA(cudaEventRecord((cudaEvent_t)g->layer_events[k], st));
+  return rc;
 }
 
 int dladmm_objective(const dladmm_problem* p, float alpha, float* out, void* stream) {

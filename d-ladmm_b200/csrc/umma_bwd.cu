@@ -113,6 +113,8 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       }
       if ((rc = launch_nt<NPASS>(sw.cZ, d, Vk, m, B, l.ss1.ptr, l.gW, m, st))) return rc;
     }
+    // gW of layer k is complete up to here (dladmm_cotangents.layer_events): a data-parallel caller starts its allreduce now
+    if (g->layer_events && g->layer_events[k]) DL_CUDA(cudaEventRecord((cudaEvent_t)g->layer_events[k], st));
     {
       umma::UEpiBG2<FAM, PS> epi;
       epi.Lp = s.Lin(k); epi.Tk = s.Tslab(k);

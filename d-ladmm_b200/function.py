@@ -224,33 +224,134 @@ def run_forward(spec, A, X, Z0, E0, L0, params, want_masks, last_only=False, T_i
     return Z, E, L, T, maskZ, maskE
 
 
-def _flat_zero_grads(params, needs):
+def _flat_zero_grads(params, needs, order=None):
     """Zero-initialised gradient buffers for the parameters that need one, carved out of ONE flat allocation (one fill
-    instead of one per parameter -- 106 launches at K=15; 16-byte aligned pieces).  autograd copies them into `.grad`."""
+    instead of one per parameter -- 106 launches at K=15; 16-byte aligned pieces).  autograd copies them into `.grad`.
+    `order`: the sequence in which the parameters are laid out (default: list order); the bucketed gradient sync puts
+    the weights first, in the order in which the backward finishes them."""
     sizes = [(-(-t.numel() // 4) * 4) if needs[i] else 0 for i, t in enumerate(params)]
     total = sum(sizes)
     if total == 0:
         return [None] * len(params), None
     flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
-    grads, off = [], 0
-    for i, t in enumerate(params):
+    grads, off = [None] * len(params), 0
+    for i in (range(len(params)) if order is None else order):
         if not needs[i]:
-            grads.append(None)
             continue
-        grads.append(flat[off:off + t.numel()].view(t.shape))
+        t = params[i]
+        grads[i] = flat[off:off + t.numel()].view(t.shape)
         off += sizes[i]
     return grads, flat
 
 
-def _sync_gradients(spec, flat):
+# Opt-in (model.sync_gradients(bucket_mb=...)): weight gradients are allreduced in buckets of at least this many bytes while the
+# layers below are still running.  The default stays ONE collective after the backward: measured at the large-scale shape (320 MB
+# of weight gradients, 2 and 8 B200s, profiles/r02_c5_sync_sweep.md) the overlapped collective hides 0.6-0.9 ms of allreduce and
+# costs the power-capped product kernels the same 0.6-1.1 ms.
+GRAD_BUCKET_BYTES = None
+
+
+class SyncPlan(object):
+    """Layout of the step's flat gradient buffer for the bucketed in-backward allreduce: `order` = parameter
+    indices, weights first by descending layer of completion (the backward runs K-1 ... 0; a weight shared by several
+    layers is final after the lowest of them), then everything else; `buckets` = [(layer whose event releases the bucket,
+    first element, one past the last element)] over the weight part; `rest` = first element of the remainder, which is
+    reduced after the last kernel of the backward."""
+
+    def __init__(self, order, buckets, rest):
+        self.order, self.buckets, self.rest = order, buckets, rest
+
+
+def plan_gradient_buckets(spec, params, needs, bucket_bytes=None):
+    """None when one collective after the backward is the right schedule (weight gradients below two buckets)."""
+    bucket_bytes = GRAD_BUCKET_BYTES if bucket_bytes is None else int(bucket_bytes)
+    if bucket_bytes is None:
+        return None
+    ready = {}
+    for k in range(spec.K):
+        wi = spec.weights[k]
+        if needs[wi]:
+            ready[wi] = min(ready.get(wi, k), k)
+    pad = lambda n: -(-n // 4) * 4
+    wbytes = 4 * sum(pad(params[wi].numel()) for wi in ready)
+    if not ready or wbytes < 2 * bucket_bytes:
+        return None
+    worder = sorted(ready, key=lambda wi: (-ready[wi], wi))
+    buckets, lo, off = [], 0, 0
+    for n, wi in enumerate(worder):
+        off += pad(params[wi].numel())
+        left = 4 * sum(pad(params[j].numel()) for j in worder[n + 1:])
+        # close a bucket once it is large enough, unless what is left would make an undersized last one
+        if 4 * (off - lo) >= bucket_bytes and (left == 0 or left >= bucket_bytes):
+            buckets.append((ready[wi], lo, off))
+            lo = off
+    if lo < off:
+        buckets.append((ready[worder[-1]], lo, off))
+    inw = set(worder)
+    order = worder + [i for i in range(len(params)) if i not in inw]
+    return SyncPlan(order, buckets, off)
+
+
+def _sync_world(spec):
+    if spec.grad_sync is None:
+        return 1
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(spec.grad_sync[0])
+    return 1
+
+
+def _sync_resources(spec, dev, nbuckets):
+    """Side stream and one event per bucket, kept on the spec (events are re-recorded every step)."""
+    res = getattr(spec, "_sync_res", None)
+    if res is None or res[0] != dev or len(res[2]) < nbuckets:
+        side = torch.cuda.Stream(device=dev)
+        events = [torch.cuda.Event() for _ in range(nbuckets)]
+        for ev in events:
+            ev.record(torch.cuda.current_stream(dev))       # creates the CUDA event behind the lazy torch object
+        res = spec._sync_res = (dev, side, events)
+    return res[1], res[2][:nbuckets]
+
+
+def _sync_prepare(spec, params, needs, cot, dev):
+    """Before the backward call: the bucket plan (or None) and the per-layer event table handed to the library."""
+    if _sync_world(spec) <= 1:
+        return None
+    plan = plan_gradient_buckets(spec, params, needs, getattr(spec, "grad_bucket_bytes", None))
+    if plan is None:
+        return None
+    side, events = _sync_resources(spec, dev, len(plan.buckets))
+    table = (C.c_void_p * spec.K)()
+    for (layer, _, _), ev in zip(plan.buckets, events):
+        table[layer] = ev.cuda_event
+    cot.layer_events = C.cast(table, C.POINTER(C.c_void_p))
+    plan.table, plan.side, plan.events = table, side, events
+    return plan
+
+
+def _sync_gradients(spec, flat, plan=None):
     """Data-parallel training over column shards: the parameter gradients of this rank's columns are one
     contiguous buffer, sum-allreduced in place (NCCL, stream-ordered after the backward kernels) before autograd hands
-    them to `.grad` -- no staging copy, one collective per backward."""
-    if spec.grad_sync is None or flat is None:
+    them to `.grad` -- no staging copy.  One collective per backward, or with a bucket plan one per bucket of finished
+    weight gradients, issued from a side stream as soon as the library's per-layer event fires (the layers below keep
+    running on the caller's stream), plus one for the remainder after the last kernel."""
+    if flat is None or _sync_world(spec) <= 1:
         return
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(spec.grad_sync[0]) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=spec.grad_sync[0])
+    group = spec.grad_sync[0]
+    if plan is None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return
+    works = []
+    for (_, lo, hi), ev in zip(plan.buckets, plan.events):
+        plan.side.wait_event(ev)
+        with torch.cuda.stream(plan.side):
+            works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    if plan.rest < flat.numel():
+        dist.all_reduce(flat[plan.rest:], op=dist.ReduceOp.SUM, group=group)
+    for w in works:
+        w.wait()                                   # the caller's stream waits for the collectives; the host does not
+    flat.record_stream(plan.side)
 
 
 class UnrolledLADMM(torch.autograd.Function):
@@ -284,8 +385,9 @@ class UnrolledLADMM(torch.autograd.Function):
             off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[6:]
-        grads, flat = _flat_zero_grads(params, needs)
         cot = _lib.Cotangents()
+        plan = _sync_prepare(spec, params, needs, cot, X.device)
+        grads, flat = _flat_zero_grads(params, needs, plan.order if plan else None)
         keep = []
         for name, g in (("gZ", gZ), ("gE", gE), ("gL", gL), ("gT", gT)):
             if g is not None:
@@ -299,7 +401,7 @@ class UnrolledLADMM(torch.autograd.Function):
             p, ws = _problem(spec, A, X, Z0, E0, L0, layers, Z, E, L, T, maskZ, maskE, False, True, Vsave=Vsave)
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
-            _sync_gradients(spec, flat)
+            _sync_gradients(spec, flat, plan)
         return (None, None, None, None, None, None) + tuple(grads)
 
 
@@ -363,9 +465,10 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             off = 12
         params = [t.contiguous() for t in saved[off:]]
         needs = ctx.needs_input_grad[9:]
-        grads, flat = _flat_zero_grads(params, needs)
-        scale = (gloss.detach().to(torch.float32) / float(max(ctx.B, 1))).reshape(1).contiguous()
         cot = _lib.Cotangents()
+        plan = _sync_prepare(spec, params, needs, cot, X.device)
+        grads, flat = _flat_zero_grads(params, needs, plan.order if plan else None)
+        scale = (gloss.detach().to(torch.float32) / float(max(ctx.B, 1))).reshape(1).contiguous()
         cot.loss_kind = ctx.kind
         cot.loss_alpha = ctx.alpha
         warr = (C.c_float * spec.K)(*ctx.weights)
@@ -378,6 +481,6 @@ class UnrolledLADMML1L1(torch.autograd.Function):
             _lib.check(lib.dladmm_backward(C.byref(p), C.byref(cot), torch.cuda.current_stream(dev).cuda_stream))
             ws.record_stream(torch.cuda.current_stream(dev))
             scale.record_stream(torch.cuda.current_stream(dev))
-            _sync_gradients(spec, flat)
+            _sync_gradients(spec, flat, plan)
         return (None,) * 9 + tuple(grads)
 

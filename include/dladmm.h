@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLADMM_ABI_VERSION 6
+#define DLADMM_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define DLADMM_API __attribute__((visibility("default")))
@@ -189,6 +189,13 @@ typedef struct dladmm_cotangents {
   float loss_alpha;
   const float* loss_layer_weight;   /* HOST array of K floats w_k */
   const float* loss_scale;          /* DEVICE pointer to one float */
+  /* ABI v7, optional: HOST array of K cudaEvent_t handles (NULL, or entries NULL).  Event k is recorded on `stream` right
+   * after the weight-gradient product of layer k has been enqueued (layers run K-1 ... 0): once it fires, gW of layer k
+   * holds the contributions of layers k ... K-1, i.e. it is final unless a layer below k shares the weight (tied / ptied).
+   * A data-parallel caller waits for these on a side stream to allreduce finished weight gradients while the layers
+   * below are still running (buckets in reverse layer order); every other gradient is final when the call's
+   * last kernel retires.  The FFMA path records all of them after its last kernel. */
+  void* const* layer_events;
 } dladmm_cotangents;
 
 typedef struct dladmm_caps {

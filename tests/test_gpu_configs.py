@@ -94,9 +94,11 @@ def test_forward_backward_against_fp64_oracle_at_config_size(variant, K, B, prec
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_in_backward_gradient_allreduce_two_ranks_nccl():
     """model.sync_gradients(): .grad after backward is the global sum on both ranks and equals one process over all
-    columns (tools/check_grad_sync.py under torchrun, 2 ranks, NCCL)."""
+    columns, with one collective after the backward and with the bucketed schedule that overlaps it
+    (tools/check_grad_sync.py under torchrun, 2 ranks, NCCL)."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29731", os.path.join(ROOT, "tools", "check_grad_sync.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("sync vs post-allreduce") == 2
+    assert r.stdout.count("[single]: sync vs post-allreduce") == 2          # one collective after the backward
+    assert r.stdout.count("[bucketed]: sync vs post-allreduce") == 2        # per-bucket collectives released by layer events

@@ -179,3 +179,52 @@ def test_auto_precision_resolves_by_shape(monkeypatch):
     assert build_model(g, "cpu").precision == "tf32" and build_model(g, "cpu", "fp32").precision == "fp32"
     with pytest.raises(ValueError):
         build_model(g, "cpu", "fp16")
+
+
+def _cpu_model(cls, m, d, K, **kw):
+    A = torch.randn(m, d)
+    z = lambda r: torch.zeros(r, 4)
+    return cls(m, 1, d, 4, A, z(d), z(m), z(m), K, device="cpu", **kw)
+
+
+def test_gradient_bucket_plan_layout():
+    """Bucketed in-backward allreduce: weights first in the order the backward finishes them (layer K-1 first),
+    contiguous buckets of at least the bucket size that tile the weight part, each released by its LOWEST layer's event;
+    below two buckets there is no plan (one collective after the backward)."""
+    from dladmm_b200.function import plan_gradient_buckets, _flat_zero_grads
+    m, d, K = 40, 64, 10
+    model = _cpu_model(dl.DLADMMNetScalar, m, d, K)
+    spec, params = model._spec_and_params()
+    needs = [True] * len(params)
+    wbytes = 4 * m * d
+    assert plan_gradient_buckets(spec, params, needs) is None                     # opt-in: no bucket size, no plan
+    assert plan_gradient_buckets(spec, params, needs, bucket_bytes=K * wbytes) is None
+    plan = plan_gradient_buckets(spec, params, needs, bucket_bytes=3 * wbytes)
+    # 10 weights, 3 per bucket, the undersized tail merged into the last bucket: layers 9-7, 6-4, 3-0
+    assert [b[0] for b in plan.buckets] == [7, 4, 0]
+    assert plan.buckets[0][1] == 0 and plan.buckets[-1][2] == plan.rest == K * m * d
+    assert all(a[2] == b[1] for a, b in zip(plan.buckets, plan.buckets[1:]))
+    assert [spec.weights.index(i) for i in plan.order[:K]] == list(range(K - 1, -1, -1))
+    assert sorted(plan.order) == list(range(len(params)))
+    grads, flat = _flat_zero_grads(params, needs, plan.order)
+    for k in range(K):                                   # layer k's weight gradient sits in the bucket its event releases
+        g = grads[spec.weights[k]]
+        off = (g.data_ptr() - flat.data_ptr()) // 4
+        layer, lo, hi = next(b for b in plan.buckets if b[0] <= k)
+        assert lo <= off and off + g.numel() <= hi, (k, off, lo, hi)
+    assert all(g.shape == p.shape for g, p in zip(grads, params))
+    small = [g for i, g in enumerate(grads) if i not in set(spec.weights)]
+    assert all((g.data_ptr() - flat.data_ptr()) // 4 >= plan.rest for g in small)
+    # a weight without a gradient is left out of the plan and of the buffer
+    needs2 = list(needs); needs2[spec.weights[K - 1]] = False
+    plan2 = plan_gradient_buckets(spec, params, needs2, bucket_bytes=3 * wbytes)
+    assert plan2.rest == (K - 1) * m * d and spec.weights[K - 1] not in plan2.order[:K - 1]
+
+
+def test_gradient_bucket_plan_tied_weight_waits_for_layer_zero():
+    from dladmm_b200.function import plan_gradient_buckets
+    model = _cpu_model(dl.DLADMMNetTied, 40, 64, 6)
+    spec, params = model._spec_and_params()
+    assert len(set(spec.weights)) == 1
+    plan = plan_gradient_buckets(spec, params, [True] * len(params), bucket_bytes=1)
+    assert plan is None or [b[0] for b in plan.buckets] == [0]     # the one shared weight is final after layer 0 only
