@@ -134,7 +134,7 @@ class HostDrain(object):
         for i, b in enumerate(pool):
             if b.shape == t.shape and b.dtype == t.dtype:
                 return pool.pop(i)
-        return torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        return torch.empty(t.shape, dtype=t.dtype, pin_memory=True)     # allocated pinned (no pageable copy first)
 
     def recycle(self, host_tensor):
         """Give a host tensor returned by push()/flush() back once it has been consumed."""
