@@ -125,6 +125,27 @@ def test_host_drain_returns_every_result_in_order():
     assert drain.bytes_copied == 7 * 33 * 1000 * 4
 
 
+def test_host_drain_keeps_its_pinned_buffers_across_loops():
+    """A drain that outlives one loop recycles its page-locked buffers: after the first loop no new host buffer appears
+    (page-locking 131 MB per step was 28 of the 31 ms of an earlier bench line) and every buffer is pinned."""
+    dev = torch.device("cuda:0")
+    drain = dl.HostDrain(dev)
+    seen = []
+    for loop in range(3):
+        ptrs = set()
+        for i in range(6):
+            t = torch.full((64, 512), float(10 * loop + i), device=dev)
+            h = drain.push(t)
+            if h is not None:
+                assert h.is_pinned() and float(h[0, 0]) == 10 * loop + i - 2
+                ptrs.add(h.data_ptr()); drain.recycle(h)
+        for h in drain.flush():
+            ptrs.add(h.data_ptr()); drain.recycle(h)
+        seen.append(ptrs)
+    assert len(seen[0]) == 3                              # depth 2 + the one being handed to the caller
+    assert seen[1] <= seen[0] and seen[2] <= seen[0]
+
+
 class env(object):
     def __init__(self, **kw):
         self.kw = kw
