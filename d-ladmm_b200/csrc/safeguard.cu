@@ -5,45 +5,76 @@
 
 namespace dladmm {
 
+// Column norms of the safeguard test.  A block owns 32 columns (one warp-wide, coalesced row segment per load) and NORM_RG row
+// groups: thread (cx, ry) sums rows ry, ry + NORM_RG, ... of column cx with four rows of loads in flight, the NORM_RG partial
+// sums of a column are added in a fixed order through shared memory (deterministic).  One thread per column over all rows -- the
+// first version -- is a chain of m dependent L2 round trips on 16 blocks: 132 us per call at 4 096 columns, 38 % of a safeguarded
+// evaluation's kernel time (profiles/r02_launches_summary.md).
+constexpr int NORM_RG = 16;
+constexpr int NORM_THREADS = 32 * NORM_RG;
+
 // out[b] = || [ beta * Tn[:,b] ; c * (En[:,b] - 2 Ek[:,b] + Ep[:,b]) ] ||_2      (test_syn_l1l1_scalar.py:173, two_norm)
-static __global__ void __launch_bounds__(256) sg_norm_kernel(int m, i64 B, float beta, float c, const float* __restrict__ Tn,
-                                                             const float* __restrict__ En, const float* __restrict__ Ek,
-                                                             const float* __restrict__ Ep, float* __restrict__ out) {
-  const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
-  if (b >= B) return;
+static __global__ void __launch_bounds__(NORM_THREADS) sg_norm_kernel(int m, i64 B, float beta, float c, const float* __restrict__ Tn,
+                                                                      const float* __restrict__ En, const float* __restrict__ Ek,
+                                                                      const float* __restrict__ Ep, float* __restrict__ out) {
+  __shared__ float part[NORM_RG][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const i64 b = (i64)blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int i = 0; i < m; ++i) {
-    const i64 off = (i64)i * B + b;
-    const float t = beta * Tn[off];
-    const float e = c * ((En[off] - 2.f * Ek[off]) + Ep[off]);
-    s += t * t + e * e;
+  if (b < B) {
+#pragma unroll 4
+    for (int i = ry; i < m; i += NORM_RG) {
+      const i64 off = (i64)i * B + b;
+      const float t = beta * Tn[off];
+      const float e = c * ((En[off] - 2.f * Ek[off]) + Ep[off]);
+      s += t * t + e * e;
+    }
   }
-  out[b] = sqrtf(s);
+  part[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && b < B) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < NORM_RG; ++r) a += part[r][cx];
+    out[b] = sqrtf(a);
+  }
 }
 
 // Snorm_ELZ (test_syn_l1l1_newS_Acols.py:174-192) with (Znn-Zn)^T P2 (Znn-Zn) = ||Znn-Zn||^2/(beta ss1) - ||A(Znn-Zn)||^2 and
-// A(Znn-Zn) = Tnn - Tn: one thread per column, coalesced over the batch, no d x d operator.
-static __global__ void __launch_bounds__(256) sg_norm_elz_kernel(int m, int d, i64 B, float inv_bss1, const float* __restrict__ Tnn,
-                                                                 const float* __restrict__ Tn, const float* __restrict__ Znn,
-                                                                 const float* __restrict__ Zn, const float* __restrict__ Esub,
-                                                                 const float* __restrict__ Eadd, float* __restrict__ out) {
-  const i64 b = (i64)blockIdx.x * 256 + threadIdx.x;
-  if (b >= B) return;
+// A(Znn-Zn) = Tnn - Tn: coalesced over the batch, no d x d operator.
+static __global__ void __launch_bounds__(NORM_THREADS) sg_norm_elz_kernel(int m, int d, i64 B, float inv_bss1, const float* __restrict__ Tnn,
+                                                                          const float* __restrict__ Tn, const float* __restrict__ Znn,
+                                                                          const float* __restrict__ Zn, const float* __restrict__ Esub,
+                                                                          const float* __restrict__ Eadd, float* __restrict__ out) {
+  __shared__ float part[3][NORM_RG][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const i64 b = (i64)blockIdx.x * 32 + cx;
   float s1 = 0.f, s3 = 0.f, s2 = 0.f;
-  for (int i = 0; i < m; ++i) {
-    const i64 off = (i64)i * B + b;
-    float t = Tnn[off];
-    if (Esub) t = (t - Esub[off]) + Eadd[off];                     // Tnn given as A Znn + E' - X: swap E' for En
-    const float dt = t - Tn[off];
-    s1 += t * t;
-    s3 += dt * dt;
+  if (b < B) {
+#pragma unroll 4
+    for (int i = ry; i < m; i += NORM_RG) {
+      const i64 off = (i64)i * B + b;
+      float t = Tnn[off];
+      if (Esub) t = (t - Esub[off]) + Eadd[off];                     // Tnn given as A Znn + E' - X: swap E' for En
+      const float dt = t - Tn[off];
+      s1 += t * t;
+      s3 += dt * dt;
+    }
+#pragma unroll 4
+    for (int i = ry; i < d; i += NORM_RG) {
+      const i64 off = (i64)i * B + b;
+      const float dz = Znn[off] - Zn[off];
+      s2 += dz * dz;
+    }
   }
-  for (int i = 0; i < d; ++i) {
-    const i64 off = (i64)i * B + b;
-    const float dz = Znn[off] - Zn[off];
-    s2 += dz * dz;
+  part[0][ry][cx] = s1; part[1][ry][cx] = s2; part[2][ry][cx] = s3;
+  __syncthreads();
+  if (ry == 0 && b < B) {
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int r = 0; r < NORM_RG; ++r) { a1 += part[0][r][cx]; a2 += part[1][r][cx]; a3 += part[2][r][cx]; }
+    out[b] = sqrtf(fmaxf(a1 + (inv_bss1 * a2 - a3), 0.f));
   }
-  out[b] = sqrtf(fmaxf(s1 + (inv_bss1 * s2 - s3), 0.f));
 }
 
 // keep + mu_k update + fallback count in one pass over the columns (mu_updater.py:18-72)
@@ -107,7 +138,7 @@ int dladmm_sg_norm(int32_t m, int64_t B, float beta, float c, const float* Tn, c
   if (B == 0) return DLADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
-    sg_norm_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, B, beta, c, Tn, En, Ek, Ep, out); }
+    sg_norm_kernel<<<(unsigned)((B + 31) / 32), NORM_THREADS, 0, st>>>(m, B, beta, c, Tn, En, Ek, Ep, out); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }
@@ -119,7 +150,7 @@ int dladmm_sg_norm_elz(int32_t m, int32_t d, int64_t B, float inv_beta_ss1, cons
   if (B == 0) return DLADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   { LaunchScope ls(DLADMM_KIND_SAFEGUARD, st);
-    sg_norm_elz_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(m, d, B, inv_beta_ss1, Tnn, Tn, Znn, Zn, E_sub, E_add, out); }
+    sg_norm_elz_kernel<<<(unsigned)((B + 31) / 32), NORM_THREADS, 0, st>>>(m, d, B, inv_beta_ss1, Tnn, Tn, Znn, Zn, E_sub, E_add, out); }
   DL_CUDA(cudaGetLastError());
   return DLADMM_OK;
 }

@@ -478,6 +478,30 @@ class DLADMMNet(nn.Module):
     def _scalar(self, v):
         return torch.full((1, 1), float(v), dtype=torch.float32, device=self.A.device)
 
+    def _sub_spec(self, spec, params, ks):
+        """The call description of layers `ks` alone, with ONLY their parameters (re-indexed), kept on the parent spec: the
+        single-layer calls of the safeguarded evaluation then validate ~8 tensors instead of the module's 7K and reuse their
+        layer table (run_forward's cache is per spec object)."""
+        if os.environ.get("DLADMM_SG_NOSUB"):          # A/B switch: a fresh description over the full parameter list per call
+            return LayerSpec(spec.family, self.m, self.d, len(ks), spec.precision, [spec.slots[k] for k in ks],
+                             [spec.weights[k] for k in ks], spec.fixed), params
+        cache = spec.__dict__.setdefault("_sub", {})
+        key = tuple(ks)
+        hit = cache.get(key)
+        if hit is None:
+            idx, remap = [], {}
+
+            def r(i):
+                if i not in remap:
+                    remap[i] = len(idx)
+                    idx.append(i)
+                return remap[i]
+            slots = [{name: r(i) for name, i in spec.slots[k].items() if i is not None} for k in ks]
+            weights = [r(spec.weights[k]) for k in ks]
+            hit = cache[key] = (LayerSpec(spec.family, self.m, self.d, len(ks), spec.precision, slots, weights, spec.fixed), idx)
+        sub, idx = hit
+        return sub, [params[i] for i in idx]
+
     def _km_spec(self, beta, ss1, ss2, alpha):
         """Classical step of the Z -> E -> L ordering as ONE family-B layer: W = A^T with ss1 in the tied slot, all betas =
         beta, thresholds ss1*alpha and ss2 (test_syn_l1l1_scalar.py:131-160)."""
@@ -673,8 +697,8 @@ class DLADMMNet(nn.Module):
             Zp, Ep_, Lp = (Z0, E0, L0) if k == 0 else (Z[-1], E[-1], L[-1])
             Zn_KM, En_KM, Ln_KM, Tn_KM = self._one_layer(km_spec, km_params, Zp, Ep_, Lp, T[-1], X)
             if use_learned:
-                spec1 = LayerSpec(spec.family, self.m, self.d, 1, spec.precision, [spec.slots[k]], [spec.weights[k]], spec.fixed)
-                Zn, En, Ln, Tn = self._one_layer(spec1, params, Zp, Ep_, Lp, T[-1], X)
+                spec1, params1 = self._sub_spec(spec, params, (k,))
+                Zn, En, Ln, Tn = self._one_layer(spec1, params1, Zp, Ep_, Lp, T[-1], X)
             if use_safeguard:
                 s_norm = self._s_norm(Zn, En, Ln, Tn, X, Ep_, alpha)
                 outs = self._select([(Zn, Zn_KM), (En, En_KM), (Tn, Tn_KM), (Ln, Ln_KM)], s_norm, mu_state, delta, keep_all[k])
@@ -702,17 +726,16 @@ class DLADMMNet(nn.Module):
                 En_KM, Ln_KM = E0, L0
                 Zn_KM = self._steps(km1, kmp, Z0, E0, L0, X, stop_half=True)[0][0]
                 if use_learned:
-                    spec1 = LayerSpec(spec.family, self.m, self.d, 1, spec.precision, [spec.slots[0]], [spec.weights[0]], spec.fixed)
+                    spec1, params1 = self._sub_spec(spec, params, (0,))
                     En_L, Ln_L = E0, L0
-                    Zn_L = self._steps(spec1, params, Z0, E0, L0, X, stop_half=True)[0][0]
+                    Zn_L = self._steps(spec1, params1, Z0, E0, L0, X, stop_half=True)[0][0]
             else:
                 Zk, Ek, Lk, _ = self._km_elz(E[-1], L[-1], Z[-1], X, beta, ss1, alpha)
                 En_KM, Ln_KM, Zn_KM = Ek[0], Lk[0], Zk[1]
                 if use_learned:
                     # E- and L-step with layer k-1's parameters, Z-step with layer k's (:234-242)
-                    spec2 = LayerSpec(spec.family, self.m, self.d, 2, spec.precision, [spec.slots[k - 1], spec.slots[k]],
-                                      [spec.weights[k - 1], spec.weights[k]], spec.fixed)
-                    Zl, El, Ll, _ = self._steps(spec2, params, Z[-1], E[-1], L[-1], X, start_half=True, stop_half=True)
+                    spec2, params2 = self._sub_spec(spec, params, (k - 1, k))
+                    Zl, El, Ll, _ = self._steps(spec2, params2, Z[-1], E[-1], L[-1], X, start_half=True, stop_half=True)
                     En_L, Ln_L, Zn_L = El[0], Ll[0], Zl[1]
             if use_safeguard:
                 s_norm = self.Snorm_ELZ(En_L, Ln_L, Zn_L, X, alpha=alpha)
