@@ -168,7 +168,7 @@ struct UEpiBG2 {
   static constexpr int OP_STAGES = 2; // 2 operand stages, 120 KB staging ring (8 slots of 14.8 KB instead of 4): see op_stages_of
   static constexpr int NIN = 7;    // L_{k-1} (tied), T_k, cL | cE, E_{k-1}, L_{k-2}, E_{k-2}(B)   (the last four only below the top layer)
                                    // upstream cotangents gL, gE, gT (generic autograd path only) are read straight from global memory
-  struct State { float red[6]; float rv[PS ? 1 : 32]; uint32_t gmask; PV<PM> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; };
+  struct State { float red[6]; float rv[PS ? 1 : 32]; uint32_t gmask; PV<PM> b1, bL, b2, ss2, ss2_2; float s1; int lane; float lsc; int o[NIN]; int o_mk; bool fused; };
   struct Pre { unsigned mk[CHUNK]; };
   // layer k
   const float* __restrict__ Lp; const float* __restrict__ Tk; BP b1, ss1; const float* cLin; const float* cEin;
@@ -201,6 +201,7 @@ struct UEpiBG2 {
     st.s1 = ss1.p ? __ldg(ss1.p) : 1.f;
     st.lane = threadIdx.x & 31;
     st.lsc = lscale ? lw * __ldg(lscale) : 0.f;
+    st.fused = lscale != nullptr && gL == nullptr && gE == nullptr && gT == nullptr;   // the fused-loss training step: no upstream stacks
     {   // order of st.red / st.rv entries: bL, th2, ss2 (C: ss2_1), b2 (C: ss2_2), b1, ss1
       const BP* const qs[6] = {&bL, &th2, &ss2, FAM == DLADMM_FAMILY_C ? &ss2_2 : &b2, &b1, &ss1};
       st.gmask = red_mask<6>(qs);
@@ -222,29 +223,36 @@ struct UEpiBG2 {
       pre.mk[i] = ok ? (unsigned)__ldg(maskE + (i64)(row0 + i) * B + b) : 0u;
     }
   }
+  // SURE: the array is staged whenever control reaches the read (T_k and the carried dL always; the layer-below arrays behind
+  // has_prev) -- no presence test per element (they were 7 of the hot loop's 43 ISETP + the selects behind them)
+  template <bool SURE = false>
   __device__ __forceinline__ float in(const State& st, const float* slot, int a, int i, int col) const {
-    return st.o[a] >= 0 ? slot[st.o[a] + i * TILE_B + col] : 0.f;
+    if constexpr (SURE) return slot[st.o[a] + i * TILE_B + col];
+    else return st.o[a] >= 0 ? slot[st.o[a] + i * TILE_B + col] : 0.f;
   }
   template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64 group) const {
     // the common case (all rows of the chunk exist, a layer below) gets a copy of the row loop without warp-uniform
     // branches so that the rows of the chunk are scheduled together
-    if (FULL && has_prev) rows<true>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
-    else rows<false>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+    // ... and, in the fused-loss training step, without the warp-uniform tests for upstream cotangent stacks either
+    if (FULL && has_prev) {
+      if (st.fused) rows<true, true>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+      else rows<true, false>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+    } else rows<false, false>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
   }
-  template <bool FAST>
+  template <bool FAST, bool FUSED>
   __device__ __forceinline__ void rows(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                        const float (&v)[CHUNK], int n_feat, i64 group) const {
     if constexpr (!PS) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) st.rv[i] = 0.f;
     }
-    rows_body<FAST>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+    rows_body<FAST, FUSED>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
     const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
     red_flush<PS, 6, CHUNK, 32>(st, ro, slots, st.gmask, row0, n_feat, group, st.lane);
   }
-  template <bool FAST>
+  template <bool FAST, bool FUSED>
   __device__ __forceinline__ void rows_body(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                             const float (&v)[CHUNK], int n_feat, i64 group) const {
     const i64 off0 = (i64)row0 * B + b;              // one 64-bit offset per chunk, 32-bit row offsets inside it (see UEpiBG1)
@@ -257,21 +265,23 @@ struct UEpiBG2 {
       const bool ok = valid;
       const i64 off = off0 + (unsigned)i * Bu;
       const float vb1 = st.b1.at(row, b);
-      const float lp = in(st, slot, 0, i, col), tk = in(st, slot, 1, i, col);
+      const float lp = in(st, slot, 0, i, col), tk = in<true>(st, slot, 1, i, col);
       const float var = lp + vb1 * tk;                // V_k recomputed
       const float dV = -st.s1 * v[i];
       red_put<PS, 4, 6>(st, b1, i, row, b, ok, dV * tk);
       red_put<PS, 5, 6>(st, ss1, i, row, b, ok, -var * v[i]);
-      float dL = in(st, slot, 2, i, col) + dV;
+      float dL = in<true>(st, slot, 2, i, col) + dV;
       float dT = vb1 * dV;
       if (!FAST && !has_prev) continue;             // warp-uniform
       // ---- layer k-1: (dL, dT, dE) -> dR, carried dE, carried dL (m1_quad in epilogues.cuh) ----
-      float dE = in(st, slot, 3, i, col);
-      if (gL) dL += ok ? __ldg(gL + off) : 0.f;         // warp-uniform branches
-      if (gE) dE += ok ? __ldg(gE + off) : 0.f;
-      if (gT) dT += ok ? __ldg(gT + off) : 0.f;
-      const float tn = tk, ek = in(st, slot, 4, i, col), lpp = in(st, slot, 5, i, col);
-      if (lscale) { const float r = ek - tn; const float sl = st.lsc * (lkind == 2 ? r : sgn(r)); dE += sl; dT -= sl; }
+      float dE = in<true>(st, slot, 3, i, col);
+      if constexpr (!FUSED) {
+        if (gL) dL += ok ? __ldg(gL + off) : 0.f;       // warp-uniform branches
+        if (gE) dE += ok ? __ldg(gE + off) : 0.f;
+        if (gT) dT += ok ? __ldg(gT + off) : 0.f;
+      }
+      const float tn = tk, ek = in<true>(st, slot, 4, i, col), lpp = in<true>(st, slot, 5, i, col);
+      if (FUSED || lscale) { const float r = ek - tn; const float sl = st.lsc * (lkind == 2 ? r : sgn(r)); dE += sl; dT -= sl; }
       const float vbL = st.bL.at(row, b);
       red_put<PS, 0, 6>(st, bL, i, row, b, ok, dL * tn);
       const float dTt = dT + vbL * dL;
@@ -279,7 +289,7 @@ struct UEpiBG2 {
       float dRv, nE, nL;
       const unsigned mk = st.o_mk >= 0 ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
       if (FAM == DLADMM_FAMILY_B) {
-        const float ep = in(st, slot, 6, i, col);
+        const float ep = in<true>(st, slot, 6, i, col);
         const float vb2 = st.b2.at(row, b), vs2 = st.ss2.at(row, b);
         const float that = (tn - ek) + ep;
         const float q = lpp + vb2 * that;
