@@ -100,7 +100,7 @@ struct UEpiBG1 {
   static constexpr int PAIR_MIN_K = 192;           // CTA-pair kernel from this reduction length on (C1: 1.58 -> 1.45 ms per 15 layers)
   static constexpr int CHUNK = 8;
   static constexpr int NIN = 2;                    // gZ_k, carried dZ -- each optional (the fused loss takes sign(Z_k) from bits 2, 3 of the mask)
-  struct State { float red[1]; float rv[PS ? 1 : CHUNK]; uint32_t gmask; int lane; float lsc; int o_gz, o_cz, o_zk, o_mk; };
+  struct State { float red[1]; float rv[PS ? 1 : CHUNK]; uint32_t gmask; int lane; float lsc; int o_gz, o_cz, o_zk, o_mk; bool fast; };
   struct Pre { unsigned mk[CHUNK]; };
   const float* __restrict__ gZ; const float* cZin; const uint8_t* __restrict__ maskZ;
   BP th1; float* dx1; RedOut ro; i64 B;
@@ -115,6 +115,8 @@ struct UEpiBG1 {
     st.lsc = lscale ? lz * __ldg(lscale) : 0.f;
     st.o_gz = slot_rank(in_mask, 0) * SUBF(CHUNK); st.o_cz = slot_rank(in_mask, 1) * SUBF(CHUNK); st.o_zk = -1;
     st.o_mk = (in_mask & EIN_MASK_BIT) ? __popc(in_mask & ~EIN_MASK_BIT) * SUBF(CHUNK) * 4 : -1;   // byte offset of the staged mask
+    // the fused-loss training step below the top layer: carried dZ and the mask bytes staged, no upstream stack, loss term on
+    st.fast = lscale != nullptr && st.o_gz < 0 && st.o_cz >= 0 && st.o_mk >= 0;
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[1] = {SL_TH1};
@@ -131,6 +133,15 @@ struct UEpiBG1 {
   template <bool FULL>
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64 group) const {
+    // the common case (every row of the chunk exists, fused-loss step below the top layer) gets a copy of the row loop without the
+    // warp-uniform tests for which inputs exist: this epilogue is issue-bound (ncu: 67 % of the issue slots), the four tests per
+    // row were a fifth of its instructions
+    if (FULL && st.fast) body<true, true>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+    else body<FULL, false>(st, slot, col, pre, row0, b, valid, v, n_feat, group);
+  }
+  template <bool FULL, bool FAST>
+  __device__ __forceinline__ void body(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
+                                       const float (&v)[CHUNK], int n_feat, i64 group) const {
     if constexpr (!PS) {
 #pragma unroll
       for (int i = 0; i < CHUNK; ++i) st.rv[i] = 0.f;
@@ -143,16 +154,18 @@ struct UEpiBG1 {
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;         // warp-uniform
-      const bool ok = valid;
+      // FAST: a column past the batch has a zero accumulator, zero staged inputs and a zero mask byte (TMA fills out-of-bounds
+      // elements with zeros), so its contribution to the reduction is an exact zero without a select
+      const bool ok = FAST ? true : valid;
       float dz = v[i];
-      if (st.o_gz >= 0) dz += slot[st.o_gz + i * TILE_B + col];
-      if (st.o_cz >= 0) dz += slot[st.o_cz + i * TILE_B + col];
-      const unsigned mk = st.o_mk >= 0 ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
-      if (lscale) dz += st.lsc * ((mk & 4u) ? 1.f : ((mk & 8u) ? -1.f : 0.f));      // lsc * sign(Z_k)   (warp-uniform branch)
+      if (!FAST && st.o_gz >= 0) dz += slot[st.o_gz + i * TILE_B + col];
+      if (FAST || st.o_cz >= 0) dz += slot[st.o_cz + i * TILE_B + col];
+      const unsigned mk = (FAST || st.o_mk >= 0) ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
+      if (FAST || lscale) dz += st.lsc * ((mk & 4u) ? 1.f : ((mk & 8u) ? -1.f : 0.f));      // lsc * sign(Z_k)   (warp-uniform branch)
       const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_put<PS, 0, 1>(st, th1, i, row, b, ok, dz * (mn - mp));
-      if (ok) dx1c[(unsigned)i * Bu] = o;
+      if (valid) dx1c[(unsigned)i * Bu] = o;
     }
     { const int slots[1] = {SL_TH1}; red_flush<PS, 1, CHUNK, CHUNK>(st, ro, slots, st.gmask, row0, n_feat, group, st.lane); }
   }
@@ -262,7 +275,9 @@ struct UEpiBG2 {
     for (int i = 0; i < CHUNK; ++i) {
       const int row = row0 + i;
       if (!FAST && row >= n_feat) continue;         // warp-uniform
-      const bool ok = valid;
+      // fused fast path: a column past the batch has a zero accumulator and zero staged inputs (TMA fills out-of-bounds elements
+      // with zeros; sgn(0) = 0), so every reduction term is an exact zero without a select; the stores stay guarded
+      const bool ok = (FAST && FUSED) ? true : valid;
       const i64 off = off0 + (unsigned)i * Bu;
       const float vb1 = st.b1.at(row, b);
       const float lp = in(st, slot, 0, i, col), tk = in<true>(st, slot, 1, i, col);
@@ -314,7 +329,7 @@ struct UEpiBG2 {
         red_put<PS, 3, 6>(st, ss2_2, i, row, b, ok, -dEt * lpp);
         dRv = dTt - v1 * dEt; nE = 0.f; nL = dL - v2 * dEt;
       }
-      if (ok) {
+      if (valid) {
         dRc[(unsigned)i * Bu] = dRv;
         cEc[(unsigned)i * Bu] = nE;
         cLc[(unsigned)i * Bu] = nL;
