@@ -148,10 +148,13 @@ struct UEpiBG1 {
     }
     // one 64-bit address per chunk, 32-bit row offsets inside it (the host refuses batches of 2^28 columns and more): a 64-bit
     // row * B + b per row and array was 12 of the 41 instructions per element row of this issue-bound epilogue (ncu source page)
-    float* const dx1c = dx1 + ((i64)row0 * B + b);
-    const unsigned Bu = (unsigned)B;
+    // (round 2, SASS of this loop: indexing dx1c[i * B] still cost IADD3 + IMAD.X + LEA + LEA.HI.X + a constant-bank load per row;
+    // a byte pointer stepped by one 64-bit stride is two adds.  Also tried: decoding the mask byte with PRMT table lookups instead of
+    // predicates + FSEL -- ptxas re-materialises the table per PRMT, same instruction count, dropped.)
+    char* dxp = reinterpret_cast<char*>(dx1 + ((i64)row0 * B + b));
+    const i64 stride = B * (i64)sizeof(float);
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) {
+    for (int i = 0; i < CHUNK; ++i, dxp += stride) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;         // warp-uniform
       // FAST: a column past the batch has a zero accumulator, zero staged inputs and a zero mask byte (TMA fills out-of-bounds
@@ -165,7 +168,7 @@ struct UEpiBG1 {
       const float mp = (mk & 1u) ? 1.f : 0.f, mn = (mk & 2u) ? 1.f : 0.f;
       const float o = dz * (mp + mn);
       red_put<PS, 0, 1>(st, th1, i, row, b, ok, dz * (mn - mp));
-      if (valid) dx1c[(unsigned)i * Bu] = o;
+      if (valid) *reinterpret_cast<float*>(dxp) = o;
     }
     { const int slots[1] = {SL_TH1}; red_flush<PS, 1, CHUNK, CHUNK>(st, ro, slots, st.gmask, row0, n_feat, group, st.lane); }
   }
@@ -269,10 +272,12 @@ struct UEpiBG2 {
   __device__ __forceinline__ void rows_body(State& st, const float* __restrict__ slot, int col, const Pre& pre, int row0, i64 b, bool valid,
                                             const float (&v)[CHUNK], int n_feat, i64 group) const {
     const i64 off0 = (i64)row0 * B + b;              // one 64-bit offset per chunk, 32-bit row offsets inside it (see UEpiBG1)
-    float* const dRc = dR + off0; float* const cEc = cE + off0; float* const cLc = cL + off0;
+    // byte pointers stepped by one 64-bit stride (see UEpiBG1::body)
+    char* dRp = reinterpret_cast<char*>(dR + off0); char* cEp = reinterpret_cast<char*>(cE + off0); char* cLp = reinterpret_cast<char*>(cL + off0);
+    const i64 stride = B * (i64)sizeof(float);
     const unsigned Bu = (unsigned)B;
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) {
+    for (int i = 0; i < CHUNK; ++i, dRp += stride, cEp += stride, cLp += stride) {
       const int row = row0 + i;
       if (!FAST && row >= n_feat) continue;         // warp-uniform
       // fused fast path: a column past the batch has a zero accumulator and zero staged inputs (TMA fills out-of-bounds elements
@@ -330,9 +335,9 @@ struct UEpiBG2 {
         dRv = dTt - v1 * dEt; nE = 0.f; nL = dL - v2 * dEt;
       }
       if (valid) {
-        dRc[(unsigned)i * Bu] = dRv;
-        cEc[(unsigned)i * Bu] = nE;
-        cLc[(unsigned)i * Bu] = nL;
+        *reinterpret_cast<float*>(dRp) = dRv;
+        *reinterpret_cast<float*>(cEp) = nE;
+        *reinterpret_cast<float*>(cLp) = nL;
       }
     }
   }
