@@ -129,20 +129,21 @@ struct UEpiZ {
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
-    const i64 off0 = (i64)row0 * B + b;              // (one 64-bit offset per chunk, 32-bit row offsets inside it)
-    const unsigned Bu = (unsigned)B;
-    float* const Zkc = Zk + off0; uint8_t* const mZc = maskZ + off0;
+    // one 64-bit offset per chunk; the stores go through byte pointers stepped by one 64-bit stride per row (two adds per pointer
+    // and row; indexing base[i * B] compiled to IADD3 + IMAD.X + LEA + LEA.HI.X + a constant-bank load per store, SASS of round 2)
+    const i64 off0 = (i64)row0 * B + b;
+    char* zp = reinterpret_cast<char*>(Zk + off0); uint8_t* mp = maskZ + off0;
+    const i64 sf = B * (i64)sizeof(float);
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) {
+    for (int i = 0; i < CHUNK; ++i, zp += sf, mp += B) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;
-      const unsigned ro = (unsigned)i * Bu;
       const float wv = ss1.p ? fmul(st.s1, v[i]) : v[i];
       unsigned bits;
       const float z = soft_act(fsub(slot[i * TILE_B + col], wv), st.th1.at(row, b), bits);
-      Zkc[ro] = z;
+      *reinterpret_cast<float*>(zp) = z;
       if (Zh) Zh[(i64)row * ldh + b] = __float2bfloat16_rn(z);
-      if (maskZ) mZc[ro] = (uint8_t)(bits | (z > 0.f ? 4u : 0u) | (z < 0.f ? 8u : 0u));    // bits 2, 3: sign(Z_k) for the fused-loss backward
+      if (maskZ) *mp = (uint8_t)(bits | (z > 0.f ? 4u : 0u) | (z < 0.f ? 8u : 0u));    // bits 2, 3: sign(Z_k) for the fused-loss backward
       if (obj_part) st.obj += fabsf(z);
       if (sq_part) { const float dl = slot[SUBF(CHUNK) + i * TILE_B + col] - z; st.sq += dl * dl; }   // warp-uniform branch
     }
@@ -210,15 +211,15 @@ struct UEpiELT {
   __device__ __forceinline__ void apply(State& st, const float* __restrict__ slot, int col, const Pre&, int row0, i64 b, bool valid,
                                         const float (&v)[CHUNK], int n_feat, i64) const {
     if (!valid) return;
-    const i64 off0 = (i64)row0 * B + b;              // (one 64-bit offset per chunk, 32-bit row offsets inside it)
-    const unsigned Bu = (unsigned)B;
-    float* const Ekc = Ek + off0; float* const Tnc = Tn + off0; float* const Lkc = Lk + off0; float* const Vc = V + off0;
-    uint8_t* const mEc = maskE + off0;
+    const i64 off0 = (i64)row0 * B + b;              // one 64-bit offset per chunk, stepped byte pointers for the stores (see UEpiZ)
+    char* ep_ = reinterpret_cast<char*>(Ek + off0); char* tp = reinterpret_cast<char*>(Tn + off0); char* lp_ = reinterpret_cast<char*>(Lk + off0);
+    char* vp = reinterpret_cast<char*>(V + off0);
+    uint8_t* mp = maskE + off0;
+    const i64 sf = B * (i64)sizeof(float);
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) {
+    for (int i = 0; i < CHUNK; ++i, ep_ += sf, tp += sf, lp_ += sf, vp += sf, mp += B) {
       const int row = row0 + i;
       if (!FULL && row >= n_feat) continue;
-      const unsigned ro = (unsigned)i * Bu;
       const float x = slot[i * TILE_B + col], lp = slot[SUBF(CHUNK) + i * TILE_B + col], acc = v[i];
       float e;
       unsigned bits = 0;
@@ -237,7 +238,7 @@ struct UEpiELT {
       }
       const float t = fsub(fadd(acc, e), x);
       const float l = fadd(lp, fmul(st.bL.at(row, b), t));
-      Ekc[ro] = e; Tnc[ro] = t; Lkc[ro] = l;
+      *reinterpret_cast<float*>(ep_) = e; *reinterpret_cast<float*>(tp) = t; *reinterpret_cast<float*>(lp_) = l;
       if (obj_part) { const float r = fsub(e, t); st.obj += obj_kind == 2 ? 0.5f * r * r : fabsf(r); }
       if (MET) {
         const float r = fsub(e, t);
@@ -247,10 +248,10 @@ struct UEpiELT {
         st.met[4] += fabsf(e); st.met[5] += l * x;
         st.met[6] += softplus_t(l - 1.f) + softplus_t(-l - 1.f);
       }
-      if (FAM != DLADMM_FAMILY_C && maskE) mEc[ro] = (uint8_t)bits;
+      if (FAM != DLADMM_FAMILY_C && maskE) *mp = (uint8_t)bits;
       if (has_next) {
         const float vv = fadd(l, fmul(st.b1n.at(row, b), t));
-        if (V) Vc[ro] = vv;
+        if (V) *reinterpret_cast<float*>(vp) = vv;
         if (Vh) Vh[(i64)row * ldh + b] = __float2bfloat16_rn(vv);
       }
     }
