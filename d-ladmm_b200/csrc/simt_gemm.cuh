@@ -214,10 +214,11 @@ simt_gemm_nt_kernel(int M, int N, i64 B, i64 chunk, const float* __restrict__ P,
 
 // ---- standalone elementwise backward of the top layer ----------------------------------------------
 template <int FAM>
-__global__ void __launch_bounds__(256) m1_kernel(int M, i64 N, M1Args a, float* __restrict__ part, int ncolTiles, int prow) {
+__global__ void __launch_bounds__(256, 3) m1_kernel(int M, i64 N, M1Args a, float* __restrict__ part, int ncolTiles, int prow) {
   // one warp per (row, 256-column tile): same partial layout as simt_gemm_kernel.  A block is one row x 8 consecutive tiles (8 KB
   // contiguous per array).  (Measured 0.21-0.22 ms for the 475 MB of the C1 top layer with this and with the former 8 rows x 1 KB
   // mapping alike: the kernel is bound by its dependent load -> compute -> store chain per thread, not by DRAM locality.)
+  // Three blocks per SM (85 registers instead of the family-B instance's 88, which allowed two): the kernel's rate is its bytes in flight.
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int row = blockIdx.y;
   const int tile = blockIdx.x * 8 + w;
