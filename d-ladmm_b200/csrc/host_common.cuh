@@ -99,27 +99,28 @@ static inline const dladmm_bparam& betaL(const dladmm_problem* p, const dladmm_l
 }
 
 // parameter-gradient reduction jobs -------------------------------------------------------------------
-static inline void add_job(ReduceJobs& jobs, int slot, const dladmm_bparam& q, int rows) {
+static inline void add_job(ReduceJobs& jobs, int slot, const dladmm_bparam& q, int rows, i64 part_off = 0) {
   if (q.grad == nullptr || q.ptr == nullptr || q.col_period != 0) return;   // per-slot params use atomics
   ReduceJob& j = jobs.j[jobs.n++];
   j.slot = slot;
   j.scalar = q.row_stride == 0;
   j.rows = rows;
   j.grad = q.grad;
+  j.part_off = part_off;
 }
 
-static inline void add_m1_jobs(const dladmm_problem* p, ReduceJobs& jobs, const dladmm_layer& l) {
-  add_job(jobs, SL_BL, betaL(p, l), p->m);
+static inline void add_m1_jobs(const dladmm_problem* p, ReduceJobs& jobs, const dladmm_layer& l, i64 part_off = 0) {
+  add_job(jobs, SL_BL, betaL(p, l), p->m, part_off);
   if (p->family == DLADMM_FAMILY_B) {
-    add_job(jobs, SL_TH2, l.theta2, p->m);
-    add_job(jobs, SL_SS2, l.ss2, p->m);
-    add_job(jobs, SL_B2, l.beta2, p->m);
+    add_job(jobs, SL_TH2, l.theta2, p->m, part_off);
+    add_job(jobs, SL_SS2, l.ss2, p->m, part_off);
+    add_job(jobs, SL_B2, l.beta2, p->m, part_off);
   } else if (p->family == DLADMM_FAMILY_A) {
-    add_job(jobs, SL_TH2, l.theta2, p->m);
-    add_job(jobs, SL_B2, l.beta2, p->m);
+    add_job(jobs, SL_TH2, l.theta2, p->m, part_off);
+    add_job(jobs, SL_B2, l.beta2, p->m, part_off);
   } else {
-    add_job(jobs, SL_SS2, l.ss2, p->m);
-    add_job(jobs, SL_B2, l.ss2_2, p->m);
+    add_job(jobs, SL_SS2, l.ss2, p->m, part_off);
+    add_job(jobs, SL_B2, l.ss2_2, p->m, part_off);
   }
 }
 

@@ -87,10 +87,17 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
   std::vector<ScalarJob> sjobs;
   constexpr bool SC = PS == umma::PM_SCALAR;      // all parameters scalar: per-warp entries, one reduction launch at the end
   if (SC) DL_CUDA(cudaMemsetAsync(w.part, 0, sizeof(float) * layer_entries * K, st));
+  // per-row parameters: the partial blocks of up to red_group layers are kept side by side and summed by ONE launch (a launch per
+  // layer was 20 latency-bound launches of ~160 blocks, 23 us each: 0.46 ms of the `full` K = 20 step)
+  const i64 row_block = (i64)SL_COUNT * w.ngroups * w.prow;
+  ReduceJobs jobs; jobs.n = 0;
+  int pending = 0;
   for (int k = K - 1; k >= 0; --k) {
     const dladmm_layer& l = p->layers[k];
     const size_t wi = (size_t)weight_index(p, k);
     if (SC) ro.part = w.part + layer_entries * k;
+    const i64 part_off = SC ? 0 : row_block * pending;
+    if (!SC) ro.part = w.part + part_off;
     {
       umma::UEpiBG1<PS> epi;
       epi.gZ = g->gZ ? g->gZ + s.zs * k : nullptr;
@@ -136,15 +143,18 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       if ((rc = launch_umma<umma::UEpiBG2<FAM, PS>, NPASS>(DLADMM_KIND_BWD_GEMM_DV, sw.cZ, d, w.Wtb + wi * w.m256 * w.dp, w.Wts + wi * w.m256 * w.dp, w.m256, w.dp, m, B, epi, st, grid)))
         return rc;
     }
-    ReduceJobs jobs; jobs.n = 0;
-    add_job(jobs, SL_TH1, l.theta1, d);
-    add_job(jobs, SL_B1, l.beta1, m);
-    add_job(jobs, SL_SS1, l.ss1, m);
-    if (k > 0) add_m1_jobs(p, jobs, p->layers[k - 1]);
+    const int first = jobs.n;
+    add_job(jobs, SL_TH1, l.theta1, d, part_off);
+    add_job(jobs, SL_B1, l.beta1, m, part_off);
+    add_job(jobs, SL_SS1, l.ss1, m, part_off);
+    if (k > 0) add_m1_jobs(p, jobs, p->layers[k - 1], part_off);
     if (SC) {
-      for (int i = 0; i < jobs.n; ++i) sjobs.push_back(ScalarJob{ro.part + (size_t)jobs.j[i].slot * ro.nentries, jobs.j[i].grad});
+      for (int i = first; i < jobs.n; ++i) sjobs.push_back(ScalarJob{ro.part + (size_t)jobs.j[i].slot * ro.nentries, jobs.j[i].grad});
+      jobs.n = 0;
       continue;
     }
+    if (++pending < w.red_group && k > 0 && jobs.n + 7 <= MAX_REDUCE_JOBS) continue;      // keep collecting
+    pending = 0;
     if (jobs.n) {
       int ncol = ro.ngroups, prow = ro.prow;
       int maxrows = 1;
@@ -153,6 +163,7 @@ static int backward_umma(const dladmm_problem* p, const dladmm_cotangents* g, co
       dim3 rg((maxrows + 7) / 8, jobs.n);
       { LaunchScope ls(DLADMM_KIND_BWD_REDUCE, st); reduce_partials_kernel<<<rg, 256, 0, st>>>(jobs, w.part, ncol, prow); }
       DL_CUDA(cudaGetLastError());
+      jobs.n = 0;
     }
   }
   for (size_t base = 0; base < sjobs.size(); base += 120) {

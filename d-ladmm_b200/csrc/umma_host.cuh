@@ -102,6 +102,7 @@ struct UBwdWorkspace {
   float *part;         // parameter-gradient partial sums of the tcgen05 epilogues
   size_t bytes;
   int m256, d256, mp, dp, nW, ngroups, prow, nentries;
+  int red_group;       // layers whose per-(column group, row) partial blocks are kept before one reduction launch sums them
 };
 
 static UBwdWorkspace ucarve_bwd(const dladmm_problem* p, char* base) {
@@ -126,8 +127,11 @@ static UBwdWorkspace ucarve_bwd(const dladmm_problem* p, char* base) {
   w.Wtb = take((size_t)w.nW * w.m256 * w.dp);
   w.Wts = take((size_t)w.nW * w.m256 * w.dp);
   w.V = take((size_t)p->m * p->B);
-  // per-(column group, row) partials of ONE layer, or -- when every parameter is a scalar -- per-warp entries of ALL layers
-  w.part = take(std::max((size_t)SL_COUNT * w.ngroups * w.prow, (size_t)p->K * SL_COUNT * w.nentries));
+  // per-(column group, row) partials of red_group layers (at most 4, at most 512 MB), or -- when every parameter is a scalar --
+  // per-warp entries of ALL layers
+  const size_t per_layer = (size_t)SL_COUNT * w.ngroups * w.prow;
+  w.red_group = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(4, (size_t)std::max(p->K, 1)), ((size_t)128 << 20) / std::max<size_t>(per_layer, 1)));
+  w.part = take(std::max(per_layer * w.red_group, (size_t)p->K * SL_COUNT * w.nentries));
   w.bytes = off;
   return w;
 }

@@ -1,0 +1,10 @@
+#!/bin/bash
+# same-box A/B of two builds (tools/ab/libdladmm_prev.so through DLADMM_LIB_PATH against the in-tree one): the three training legs
+for i in 1 2; do
+  for lib in prev new; do
+    if [ $lib = prev ]; then export DLADMM_LIB_PATH=$PWD/tools/ab/libdladmm_prev.so; else unset DLADMM_LIB_PATH; fi
+    python bench.py --no-cpu-baseline --c5-columns 0 2>/dev/null | python -c "
+import json,sys; l=json.loads(sys.stdin.read())
+print('$lib', ' | '.join('%s %.3f ms (reduce %.3f)' % (k, l[k]['ms_per_step'], l[k]['library_kernel_ms_per_step']['bwd_reduce']) for k in ('train','train_full','train_lasso')))"
+  done
+done
