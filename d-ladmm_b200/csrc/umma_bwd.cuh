@@ -217,7 +217,6 @@ struct UEpiBG2 {
     st.s1 = ss1.p ? __ldg(ss1.p) : 1.f;
     st.lane = threadIdx.x & 31;
     st.lsc = lscale ? lw * __ldg(lscale) : 0.f;
-    st.fused = lscale != nullptr && gL == nullptr && gE == nullptr && gT == nullptr;   // the fused-loss training step: no upstream stacks
     {   // order of st.red / st.rv entries: bL, th2, ss2 (C: ss2_1), b2 (C: ss2_2), b1, ss1
       const BP* const qs[6] = {&bL, &th2, &ss2, FAM == DLADMM_FAMILY_C ? &ss2_2 : &b2, &b1, &ss1};
       st.gmask = red_mask<6>(qs);
@@ -226,6 +225,9 @@ struct UEpiBG2 {
 #pragma unroll
     for (int i = 0; i < NIN; ++i) st.o[i] = slot_rank(in_mask, i) * SUBF(CHUNK);
     st.o_mk = (in_mask & EIN_MASK_BIT) ? __popc(in_mask & ~EIN_MASK_BIT) * SUBF(CHUNK) * 4 : -1;
+    // the fused-loss training step of the untied variants: no upstream stacks, mask bytes staged (or family C: none), no L_{k-1} input
+    st.fused = lscale != nullptr && gL == nullptr && gE == nullptr && gT == nullptr && st.o[0] < 0 &&
+               (FAM == DLADMM_FAMILY_C || st.o_mk >= 0);
   }
   __device__ __forceinline__ void end(State& st, int entry, int lane) const {
     const int slots[6] = {SL_BL, SL_TH2, SL_SS2, SL_B2, SL_B1, SL_SS1};
@@ -285,11 +287,13 @@ struct UEpiBG2 {
       const bool ok = (FAST && FUSED) ? true : valid;
       const i64 off = off0 + (unsigned)i * Bu;
       const float vb1 = st.b1.at(row, b);
-      const float lp = in(st, slot, 0, i, col), tk = in<true>(st, slot, 1, i, col);
-      const float var = lp + vb1 * tk;                // V_k recomputed
+      const float tk = in<true>(st, slot, 1, i, col);
       const float dV = -st.s1 * v[i];
       red_put<PS, 4, 6>(st, b1, i, row, b, ok, dV * tk);
-      red_put<PS, 5, 6>(st, ss1, i, row, b, ok, -var * v[i]);
+      if constexpr (!FUSED) {                         // d(ss1) exists in the tied variants only: V_k = L_{k-1} + beta1 T_k recomputed
+        const float var = in(st, slot, 0, i, col) + vb1 * tk;
+        red_put<PS, 5, 6>(st, ss1, i, row, b, ok, -var * v[i]);
+      }
       float dL = in<true>(st, slot, 2, i, col) + dV;
       float dT = vb1 * dV;
       if (!FAST && !has_prev) continue;             // warp-uniform
@@ -307,7 +311,7 @@ struct UEpiBG2 {
       const float dTt = dT + vbL * dL;
       const float dEt = dE + dTt;
       float dRv, nE, nL;
-      const unsigned mk = st.o_mk >= 0 ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
+      const unsigned mk = (FAM != DLADMM_FAMILY_C && (FUSED || st.o_mk >= 0)) ? (unsigned)reinterpret_cast<const uint8_t*>(slot)[st.o_mk + i * TILE_B + col] : pre.mk[i];
       if (FAM == DLADMM_FAMILY_B) {
         const float ep = in<true>(st, slot, 6, i, col);
         const float vb2 = st.b2.at(row, b), vs2 = st.ss2.at(row, b);

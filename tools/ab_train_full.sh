@@ -5,6 +5,6 @@ for i in 1 2; do
     if [ $lib = prev ]; then export DLADMM_LIB_PATH=$PWD/tools/ab/libdladmm_prev.so; else unset DLADMM_LIB_PATH; fi
     python bench.py --no-cpu-baseline --c5-columns 0 2>/dev/null | python -c "
 import json,sys; l=json.loads(sys.stdin.read())
-print('$lib', ' | '.join('%s %.3f ms (reduce %.3f)' % (k, l[k]['ms_per_step'], l[k]['library_kernel_ms_per_step']['bwd_reduce']) for k in ('train','train_full','train_lasso')))"
+print('$lib', ' | '.join('%s %.3f ms (dV %.4f)' % (k, l[k]['ms_per_step'], l[k]['roofline']['per_kernel']['bwd_gemm_dv']['avg_launch_ms']) for k in ('train','train_full','train_lasso')))"
   done
 done
