@@ -1,4 +1,5 @@
 #!/bin/bash
+# before changing a kernel: mkdir -p tools/ab && cp d-ladmm_b200/csrc/libdladmm.so tools/ab/libdladmm_prev.so  (git-ignored, travels with gpurun)
 # same-box A/B of two builds of the library: tools/ab/libdladmm_prev.so (DLADMM_LIB_PATH) against the in-tree one, C1 forward + training
 for i in 1 2 3; do
   for lib in prev new; do

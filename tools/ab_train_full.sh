@@ -1,4 +1,5 @@
 #!/bin/bash
+# before changing a kernel: mkdir -p tools/ab && cp d-ladmm_b200/csrc/libdladmm.so tools/ab/libdladmm_prev.so  (git-ignored, travels with gpurun)
 # same-box A/B of two builds (tools/ab/libdladmm_prev.so through DLADMM_LIB_PATH against the in-tree one): the three training legs
 for i in 1 2; do
   for lib in prev new; do
